@@ -1,0 +1,158 @@
+/*
+ * recfilter_b200.h -- C ABI of the B200-native recursive-filter engine.
+ *
+ * This is the drop-in boundary: the C++ operator surface in include/recfilter.h
+ * (RecFilter, add_filter, split, realize, profile ...) is implemented on top of
+ * exactly these entry points, and a maintainer of mit-gfx/recfilter would bind
+ * the same functions from lib/recfilter.cpp.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference):
+ *
+ *   rf_plan_create      RecFilter::define + add_filter + split + finalize/compile_jit
+ *                       lib/recfilter.cpp:192-248, 260-392, 918-930; lib/split.cpp:1850-2080
+ *                       (scan list + tiling -> executable pipeline; here a launch plan
+ *                       with carry matrices instead of a Halide Func DAG)
+ *   rf_plan_execute     Func::realize on device buffers, lib/recfilter.cpp:984-989, 998-1009
+ *   rf_plan_execute_host  create_realization's copy_to_dev + realize + Image<T>(Realization)
+ *                       download, lib/recfilter.cpp:932-982, halide/src/runtime/cuda.cpp:512,575
+ *   rf_plan_profile     RecFilter::profile, lib/recfilter.cpp:991-1016 (CUDA events instead of
+ *                       an unsynchronised wall clock)
+ *   rf_plan_describe    operator<<(RecFilter) / print_synopsis, lib/recfilter.cpp:1024-1096
+ *   rf_plan_stage1/2, rf_plan_shard_*   no reference equivalent (the reference is single-GPU);
+ *                       strip-sharded execution with an order-r carry exchange
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a
+ * negative RF_E* code on failure, with a message retrievable by rf_last_error();
+ * no exceptions cross the boundary.  A plan is immutable after creation; execute
+ * may be called repeatedly.  Arrays are dense with dimension 0 contiguous (the
+ * Halide::Image layout, lib/recfilter.cpp:970-981).
+ */
+#ifndef RECFILTER_B200_H_
+#define RECFILTER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_MAX_DIMS   4
+#define RF_MAX_SCANS  64
+#define RF_MAX_ORDER  32
+
+/* element types (type of the filter = type of the RHS, lib/recfilter.cpp:197) */
+enum rf_dtype {
+    RF_F32 = 0,
+    RF_I32 = 2,
+    RF_U32 = 3,
+    RF_I16 = 4,
+    RF_U16 = 5,
+    RF_I8  = 6,
+    RF_U8  = 7
+};
+
+/* image border (RecFilter::set_clamped_image_border, lib/recfilter.cpp:252-258) */
+enum rf_border { RF_BORDER_ZERO = 0, RF_BORDER_CLAMP = 1 };
+
+/* error codes */
+enum rf_status {
+    RF_OK            =  0,
+    RF_EINVAL        = -1,   /* bad descriptor / argument */
+    RF_EUNSUPPORTED  = -2,   /* valid request this engine does not implement */
+    RF_ECUDA         = -3,   /* CUDA runtime error (message has the CUDA string) */
+    RF_ENOMEM        = -4,
+    RF_ENODEVICE     = -5    /* no CUDA device: there is no CPU fallback */
+};
+
+/* one scan = one RecFilter::add_filter call (lib/recfilter.cpp:264-392) */
+typedef struct rf_scan {
+    int32_t dim;                      /* dimension scanned, 0 = contiguous */
+    int32_t causal;                   /* 1: +x (i ascending), 0: -x */
+    int32_t order;                    /* r = number of feedback coefficients, 1..RF_MAX_ORDER */
+    float   coeff[RF_MAX_ORDER + 1];  /* {b0, a1..ar}: feedback terms are ADDED */
+} rf_scan;
+
+/* planner options; zero-initialised means "engine decides" */
+typedef struct rf_options {
+    int32_t tile[RF_MAX_DIMS];  /* split() hint per dimension; 0 = engine picks (64).
+                                   Values are clamped to the kernel's register tile. */
+    int32_t honor_tile;         /* 1: use tile[] literally (<= register tile) even if small */
+    int32_t fuse_dims;          /* 1: fuse scans of dimension 0 and 1 in one pass (default),
+                                   0: one pass per dimension (cascade_by_dimension style),
+                                   -1: engine decides */
+    int32_t open_lo;            /* sharding: the low / high face of shard_dim is an interior */
+    int32_t open_hi;            /*   cut, carries come from the neighbour shard */
+    int32_t shard_dim;          /* dimension that is sharded across devices, -1: none */
+    int32_t reserved[8];
+} rf_options;
+
+/* filter descriptor */
+typedef struct rf_desc {
+    int32_t ndim;                       /* 1..RF_MAX_DIMS */
+    int64_t extent[RF_MAX_DIMS];        /* samples per dimension, extent[0] contiguous */
+    int32_t dtype;                      /* rf_dtype */
+    int32_t border;                     /* rf_border */
+    int32_t nscans;                     /* 0..RF_MAX_SCANS, applied in this order */
+    rf_scan scans[RF_MAX_SCANS];
+    rf_options opt;
+} rf_desc;
+
+typedef struct rf_plan rf_plan;         /* opaque */
+
+/* library / device */
+const char* rf_version(void);
+const char* rf_last_error(void);
+int  rf_device_count(void);
+int  rf_set_device(int device);
+
+/* plan life cycle */
+int    rf_plan_create(const rf_desc* desc, rf_plan** out);
+void   rf_plan_destroy(rf_plan* plan);
+size_t rf_plan_workspace_bytes(const rf_plan* plan);
+int    rf_plan_num_launches(const rf_plan* plan);           /* kernels per execute */
+int    rf_plan_describe(const rf_plan* plan, char* buf, size_t n);
+
+/*
+ * Run the filter.  in_dev/out_dev are device pointers to dense arrays of the
+ * plan's dtype; they may alias (in-place).  stream is a cudaStream_t passed as
+ * void* (NULL = default stream).  Asynchronous with respect to the host.
+ */
+int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stream);
+
+/* Host buffers: H2D + execute + D2H, synchronous (the realize() path). */
+int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host);
+
+/* Time `iters` executions on device-resident data with CUDA events (ms per iteration). */
+int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter);
+
+/*
+ * Strip-sharded execution (one plan per device, opt.shard_dim set).
+ *   stage1: intra-shard work with zero incoming carries (passes before the sharded
+ *           one run to completion into out_dev); writes this shard's outgoing
+ *           boundary tails to tails_dev (rf_plan_shard_tail_bytes bytes).
+ *   the caller exchanges tails between devices (all-gather, rank order)
+ *   stage2: consumes the gathered tails of all `nshards` shards
+ *           (nshards * tail_bytes, rank-major), resolves this shard's incoming
+ *           carries and finishes the filter.
+ */
+size_t rf_plan_shard_tail_bytes(const rf_plan* plan);
+int rf_plan_stage1(rf_plan* plan, const void* in_dev, void* out_dev, void* tails_dev, void* stream);
+int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev,
+                   const void* gathered_tails_dev, int nshards, int shard_rank, void* stream);
+
+/* device memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can stage buffers */
+int rf_malloc(void** dev_ptr, size_t bytes);
+int rf_free(void* dev_ptr);
+int rf_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+int rf_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+int rf_memset(void* dst_dev, int value, size_t bytes);
+int rf_malloc_host(void** host_ptr, size_t bytes);   /* pinned */
+int rf_free_host(void* host_ptr);
+int rf_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECFILTER_B200_H_ */

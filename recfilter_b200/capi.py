@@ -1,0 +1,273 @@
+"""ctypes binding of include/recfilter_b200.h (the C ABI drop-in boundary).
+
+Mirrors the reference's operator surface at the level a host language needs:
+``Plan(extents, dtype, scans, border)`` is RecFilter::define + add_filter + split
+(/root/reference/lib/recfilter.cpp:192-392, lib/split.cpp:1850-2080), ``Plan.execute``
+is realize on device buffers (lib/recfilter.cpp:984-989), ``Plan.realize`` the
+host-buffer realize, ``Plan.profile`` RecFilter::profile (lib/recfilter.cpp:991-1016).
+
+No CPU fallback lives here: missing library or device => RecFilterError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from dataclasses import dataclass
+from typing import Iterable, Sequence
+
+import numpy as np
+
+RF_MAX_DIMS = 4
+RF_MAX_SCANS = 64
+RF_MAX_ORDER = 32
+
+DTYPES = {
+    "f32": (0, np.float32), "i32": (2, np.int32), "u32": (3, np.uint32),
+    "i16": (4, np.int16), "u16": (5, np.uint16), "i8": (6, np.int8), "u8": (7, np.uint8),
+}
+_NP_TO_NAME = {np.dtype(v[1]): k for k, v in DTYPES.items()}
+
+
+class RecFilterError(RuntimeError):
+    pass
+
+
+class _Scan(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("causal", C.c_int32), ("order", C.c_int32),
+                ("coeff", C.c_float * (RF_MAX_ORDER + 1))]
+
+
+class _Options(C.Structure):
+    _fields_ = [("tile", C.c_int32 * RF_MAX_DIMS), ("honor_tile", C.c_int32), ("fuse_dims", C.c_int32),
+                ("open_lo", C.c_int32), ("open_hi", C.c_int32), ("shard_dim", C.c_int32),
+                ("reserved", C.c_int32 * 8)]
+
+
+class _Desc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("extent", C.c_int64 * RF_MAX_DIMS), ("dtype", C.c_int32),
+                ("border", C.c_int32), ("nscans", C.c_int32), ("scans", _Scan * RF_MAX_SCANS),
+                ("opt", _Options)]
+
+
+@dataclass
+class Scan:
+    """One add_filter call: ``Scan(dim, causal, [b0, a1..ar])`` (lib/recfilter.cpp:264-287)."""
+    dim: int
+    causal: bool
+    coeff: Sequence[float]
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "librecfilter_b200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load librecfilter_b200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RecFilterError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    L.rf_version.restype = C.c_char_p
+    L.rf_last_error.restype = C.c_char_p
+    L.rf_device_count.restype = i32
+    L.rf_set_device.argtypes = [i32]
+    L.rf_plan_create.argtypes = [C.POINTER(_Desc), C.POINTER(vp)]
+    L.rf_plan_destroy.argtypes = [vp]
+    L.rf_plan_destroy.restype = None
+    L.rf_plan_workspace_bytes.argtypes = [vp]
+    L.rf_plan_workspace_bytes.restype = sz
+    L.rf_plan_num_launches.argtypes = [vp]
+    L.rf_plan_describe.argtypes = [vp, C.c_char_p, sz]
+    L.rf_plan_execute.argtypes = [vp, vp, vp, vp]
+    L.rf_plan_execute_host.argtypes = [vp, vp, vp]
+    L.rf_plan_profile.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_float)]
+    L.rf_plan_shard_tail_bytes.argtypes = [vp]
+    L.rf_plan_shard_tail_bytes.restype = sz
+    L.rf_plan_stage1.argtypes = [vp, vp, vp, vp, vp]
+    L.rf_plan_stage2.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.rf_malloc.argtypes = [C.POINTER(vp), sz]
+    L.rf_free.argtypes = [vp]
+    L.rf_memcpy_h2d.argtypes = [vp, vp, sz]
+    L.rf_memcpy_d2h.argtypes = [vp, vp, sz]
+    L.rf_memset.argtypes = [vp, i32, sz]
+    L.rf_malloc_host.argtypes = [C.POINTER(vp), sz]
+    L.rf_free_host.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def exported_symbols() -> list[str]:
+    """Every function name declared in include/recfilter_b200.h."""
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "recfilter_b200.h")
+    text = open(hdr).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", text)))
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RecFilterError(f"{what} failed ({rc}): {lib().rf_last_error().decode()}")
+
+
+def device_count() -> int:
+    return int(lib().rf_device_count())
+
+
+def _dtype_name(dtype) -> str:
+    if isinstance(dtype, str):
+        if dtype not in DTYPES:
+            raise RecFilterError(f"unsupported dtype {dtype}")
+        return dtype
+    d = np.dtype(dtype)
+    if d not in _NP_TO_NAME:
+        raise RecFilterError(f"unsupported dtype {d}")
+    return _NP_TO_NAME[d]
+
+
+class Plan:
+    """A compiled filter: scan list + extents -> launch plan on the current CUDA device.
+
+    ``extents`` are given in the reference's order, dimension 0 (x) first and
+    contiguous; numpy / torch arrays therefore have shape ``extents[::-1]``.
+    """
+
+    def __init__(self, extents: Sequence[int], dtype, scans: Iterable[Scan], border: str = "zero", *,
+                 tile: Sequence[int] | int | None = None, honor_tile: bool = False, fuse_dims: int = -1,
+                 shard_dim: int = -1, open_lo: bool = False, open_hi: bool = False):
+        self._h = C.c_void_p()
+        L = lib()
+        self.extents = tuple(int(e) for e in extents)
+        self.dtype_name = _dtype_name(dtype)
+        self.np_dtype = np.dtype(DTYPES[self.dtype_name][1])
+        scans = list(scans)
+        if len(self.extents) > RF_MAX_DIMS or len(self.extents) < 1:
+            raise RecFilterError("1..4 dimensions supported")
+        if len(scans) > RF_MAX_SCANS:
+            raise RecFilterError(f"at most {RF_MAX_SCANS} scans")
+        d = _Desc()
+        d.ndim = len(self.extents)
+        for i, e in enumerate(self.extents):
+            d.extent[i] = e
+        d.dtype = DTYPES[self.dtype_name][0]
+        if border not in ("zero", "clamp"):
+            raise RecFilterError("border must be 'zero' or 'clamp'")
+        d.border = 1 if border == "clamp" else 0
+        d.nscans = len(scans)
+        for i, s in enumerate(scans):
+            coeff = [float(c) for c in s.coeff]
+            # lib/recfilter.cpp:274-278: needs a feed-forward and at least one feedback coefficient
+            if len(coeff) < 2:
+                raise RecFilterError("Cannot add scan without feed forward and feedback coefficients")
+            if len(coeff) - 1 > RF_MAX_ORDER:
+                raise RecFilterError(f"filter order above {RF_MAX_ORDER} is not supported")
+            d.scans[i].dim = int(s.dim)
+            d.scans[i].causal = 1 if s.causal else 0
+            d.scans[i].order = len(coeff) - 1
+            for k, c in enumerate(coeff):
+                d.scans[i].coeff[k] = c
+        if tile is not None:
+            tl = [tile] * d.ndim if isinstance(tile, int) else list(tile)
+            for i, t in enumerate(tl):
+                d.opt.tile[i] = int(t)
+        d.opt.honor_tile = 1 if honor_tile else 0
+        d.opt.fuse_dims = int(fuse_dims)
+        d.opt.shard_dim = int(shard_dim)
+        d.opt.open_lo = 1 if open_lo else 0
+        d.opt.open_hi = 1 if open_hi else 0
+        self.size = int(np.prod(self.extents)) if self.extents else 0
+        _check(L.rf_plan_create(C.byref(d), C.byref(self._h)), "rf_plan_create")
+
+    # -- life cycle -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().rf_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection ----------------------------------------------------------------------
+    @property
+    def workspace_bytes(self) -> int:
+        return int(lib().rf_plan_workspace_bytes(self._h))
+
+    @property
+    def num_launches(self) -> int:
+        return int(lib().rf_plan_num_launches(self._h))
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(8192)
+        _check(lib().rf_plan_describe(self._h, buf, len(buf)), "rf_plan_describe")
+        return buf.value.decode()
+
+    @property
+    def shard_tail_bytes(self) -> int:
+        return int(lib().rf_plan_shard_tail_bytes(self._h))
+
+    # -- execution --------------------------------------------------------------------------
+    def execute_ptr(self, in_ptr: int, out_ptr: int, stream: int = 0):
+        _check(lib().rf_plan_execute(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.c_void_p(stream)),
+               "rf_plan_execute")
+
+    def execute(self, src, dst=None, stream=None):
+        """Run on torch CUDA tensors (device resident)."""
+        import torch
+        if dst is None:
+            dst = torch.empty_like(src)
+        self._check_tensor(src), self._check_tensor(dst)
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        self.execute_ptr(src.data_ptr(), dst.data_ptr(), st)
+        return dst
+
+    def _check_tensor(self, t):
+        if not t.is_cuda or not t.is_contiguous():
+            raise RecFilterError("tensors must be contiguous CUDA tensors")
+        if t.numel() != self.size or t.element_size() != self.np_dtype.itemsize:
+            raise RecFilterError("tensor size / element size does not match the plan")
+
+    def realize(self, array: np.ndarray) -> np.ndarray:
+        """Host buffers in, host buffers out (H2D + kernels + D2H): RecFilter::realize."""
+        a = np.ascontiguousarray(array, dtype=self.np_dtype)
+        if a.size != self.size:
+            raise RecFilterError(f"array has {a.size} samples, plan expects {self.size}")
+        out = np.empty_like(a)
+        _check(lib().rf_plan_execute_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)),
+               "rf_plan_execute_host")
+        return out
+
+    def realize_ptr(self, in_host_ptr: int, out_host_ptr: int):
+        _check(lib().rf_plan_execute_host(self._h, C.c_void_p(in_host_ptr), C.c_void_p(out_host_ptr)),
+               "rf_plan_execute_host")
+
+    def profile(self, src, dst, iters: int) -> float:
+        ms = C.c_float()
+        _check(lib().rf_plan_profile(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), int(iters),
+                                     C.byref(ms)), "rf_plan_profile")
+        return float(ms.value)
+
+    # -- sharded execution ------------------------------------------------------------------
+    def stage1(self, src, dst, tails, stream=None):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        _check(lib().rf_plan_stage1(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                    C.c_void_p(tails.data_ptr()), C.c_void_p(st)), "rf_plan_stage1")
+
+    def stage2(self, src, dst, gathered, nshards: int, rank: int, stream=None):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        _check(lib().rf_plan_stage2(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                    C.c_void_p(gathered.data_ptr()), int(nshards), int(rank), C.c_void_p(st)),
+               "rf_plan_stage2")

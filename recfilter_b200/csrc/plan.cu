@@ -1,0 +1,917 @@
+/*
+ * plan.cu -- launch planner and C ABI of the recursive-filter engine.
+ *
+ * Replaces lib/schedule.cpp + the GPU auto-schedules of lib/recfilter.cpp:682-870
+ * (which map tagged Halide loop variables to CUDA blocks/threads) and the host
+ * precompute of lib/coefficients.cpp:8-128 + lib/split.cpp:152-203 (tail weight
+ * matrices).  The planner turns a scan list into passes, computes every carry
+ * matrix by simulating the scans on unit vectors in fp64 (or in the integer ring
+ * for integer filters), and drives the kernels of kernels.cu.
+ *
+ * There is no CPU execution path: without a CUDA device plan creation fails with
+ * RF_ENODEVICE.
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+#include "engine.h"
+
+namespace rfb {
+
+// launchers defined in kernels.cu ---------------------------------------------------------------
+#define RFB_FOR_EACH_R(X) X(1) X(2) X(3) X(4) X(8) X(16) X(32)
+#define DECLARE_LAUNCHERS(RR)                                                                       \
+    cudaError_t launch_tile_f##RR(const PassParams<float, RR>&, const void*, void*, int, cudaStream_t);   \
+    cudaError_t launch_tile_u##RR(const PassParams<uint32_t, RR>&, const void*, void*, int, cudaStream_t);\
+    cudaError_t launch_chain_f##RR(const ChainParams<float, RR>&, cudaStream_t);                    \
+    cudaError_t launch_chain_u##RR(const ChainParams<uint32_t, RR>&, cudaStream_t);                 \
+    cudaError_t launch_cross_f##RR(const CrossParams<float, RR>&, cudaStream_t);                    \
+    cudaError_t launch_cross_u##RR(const CrossParams<uint32_t, RR>&, cudaStream_t);
+RFB_FOR_EACH_R(DECLARE_LAUNCHERS)
+
+template <typename CT, int R> struct Launch;
+#define DEFINE_LAUNCH_TRAITS(RR)                                                                    \
+    template <> struct Launch<float, RR> {                                                          \
+        static cudaError_t tile(const PassParams<float, RR>& p, const void* i, void* o, int m, cudaStream_t s) { return launch_tile_f##RR(p, i, o, m, s); } \
+        static cudaError_t chain(const ChainParams<float, RR>& p, cudaStream_t s) { return launch_chain_f##RR(p, s); } \
+        static cudaError_t cross(const CrossParams<float, RR>& p, cudaStream_t s) { return launch_cross_f##RR(p, s); } \
+    };                                                                                              \
+    template <> struct Launch<uint32_t, RR> {                                                       \
+        static cudaError_t tile(const PassParams<uint32_t, RR>& p, const void* i, void* o, int m, cudaStream_t s) { return launch_tile_u##RR(p, i, o, m, s); } \
+        static cudaError_t chain(const ChainParams<uint32_t, RR>& p, cudaStream_t s) { return launch_chain_u##RR(p, s); } \
+        static cudaError_t cross(const CrossParams<uint32_t, RR>& p, cudaStream_t s) { return launch_cross_u##RR(p, s); } \
+    };
+RFB_FOR_EACH_R(DEFINE_LAUNCH_TRAITS)
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+    do { cudaError_t e__ = (expr);                                                       \
+         if (e__ != cudaSuccess)                                                         \
+             return fail(RF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// host-side scan simulation (semantics identical to scan_regs in kernels.cu)
+//   HT = double for float filters, uint32_t (wrapping ring) for integer filters
+// ---------------------------------------------------------------------------------------------
+template <typename HT>
+static void sim_scan(std::vector<HT>& v, int len, std::vector<HT>& h, const std::vector<HT>& c,
+                     bool causal, bool clampb)
+{
+    const int R = (int)h.size();
+    for (int p = 0; p < len; ++p) {
+        const int i = causal ? p : len - 1 - p;
+        const HT x = v[i];
+        HT acc = c[0] * x;
+        if (p == 0 && clampb) {
+            for (int k = 1; k <= R; ++k) acc = acc + c[k] * x;
+            for (int k = 0; k < R; ++k) h[k] = acc;
+        } else {
+            for (int k = 1; k <= R; ++k) acc = acc + c[k] * h[k - 1];
+            for (int k = R - 1; k >= 1; --k) h[k] = h[k - 1];
+            h[0] = acc;
+        }
+        v[i] = acc;
+    }
+}
+
+struct HostScan {
+    int causal;
+    int order;
+    float coeff[RF_MAX_ORDER + 1];
+};
+
+template <typename HT> static HT cvt_coeff(float c);
+template <> double   cvt_coeff<double>(float c)   { return (double)c; }
+template <> uint32_t cvt_coeff<uint32_t>(float c) { return (uint32_t)(int64_t)c; }   // Cast::make(type, coeff), wraps
+
+template <typename HT>
+static std::vector<HT> coeff_vec(const HostScan& s, int R)
+{
+    std::vector<HT> c(R + 1, (HT)0);
+    for (int k = 0; k <= s.order; ++k) c[k] = cvt_coeff<HT>(s.coeff[k]);
+    return c;
+}
+
+struct VariantGeom { int len; int lo; int hi; };   // lo/hi: 1 = closed image border on that face
+
+static VariantGeom variant_geom(const DimGeom& g, int var)
+{
+    switch (var) {
+    case V_FIRST:    return { g.t, g.lo_closed, 0 };
+    case V_INTERIOR: return { g.t, 0, 0 };
+    case V_LAST:     return { g.len_last, 0, g.hi_closed };
+    default:         return { g.len_last, g.lo_closed, g.hi_closed };   // V_SINGLE
+    }
+}
+
+// carry matrices of one dimension
+template <typename HT>
+struct DimTables {
+    int S = 0, R = 0;
+    std::vector<HT> P;      // [V][S][R][R]
+    std::vector<HT> M;      // [V][S][S][R][R]
+    std::vector<HT> G;      // [V][S][TILE][R]
+    std::vector<HT> L;      // [V][S][R][TILE]
+    std::vector<HT> Pseg;   // [S][2][R][R]
+};
+
+template <typename HT>
+static void matmul_rr(std::vector<HT>& out, const HT* a, const HT* b, int R)   // out = a * b
+{
+    out.assign((size_t)R * R, (HT)0);
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < R; ++j) {
+            HT acc = (HT)0;
+            for (int k = 0; k < R; ++k) acc = acc + a[i * R + k] * b[k * R + j];
+            out[i * R + j] = acc;
+        }
+}
+
+template <typename HT>
+static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& scans, const DimGeom& g,
+                             int R, bool clamp, int seg, int nseg, bool want_GL)
+{
+    const int S = (int)scans.size();
+    tb.S = S; tb.R = R;
+    tb.P.assign((size_t)V_COUNT * S * R * R, (HT)0);
+    tb.M.assign((size_t)V_COUNT * S * S * R * R, (HT)0);
+    if (want_GL) {
+        tb.G.assign((size_t)V_COUNT * S * TILE * R, (HT)0);
+        tb.L.assign((size_t)V_COUNT * S * R * TILE, (HT)0);
+    }
+    std::vector<std::vector<HT>> coef(S);
+    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R);
+
+    auto closed = [&](const VariantGeom& vg, int s) { return scans[s].causal ? vg.lo : vg.hi; };
+
+    for (int var = 0; var < V_COUNT; ++var) {
+        const VariantGeom vg = variant_geom(g, var);
+        const int len = vg.len;
+        if (len <= 0) continue;
+        for (int q = 0; q < S; ++q) {
+            if (closed(vg, q)) continue;            // no carry enters this tile for scan q
+            for (int kk = 0; kk < R; ++kk) {
+                std::vector<HT> v(len, (HT)0), h(R, (HT)0);
+                h[kk] = (HT)1;
+                sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false);
+                for (int k = 0; k < R; ++k) tb.P[(((size_t)var * S + q) * R + k) * R + kk] = h[k];
+                // propagate the response through the later scans of this dimension
+                for (int s = q + 1; s < S; ++s) {
+                    std::vector<HT> hs(R, (HT)0);
+                    sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(vg, s));
+                    for (int k = 0; k < R; ++k)
+                        tb.M[((((size_t)var * S + q) * S + s) * R + k) * R + kk] = hs[k];
+                }
+                if (want_GL && len <= TILE)
+                    for (int i = 0; i < len; ++i) tb.G[(((size_t)var * S + q) * TILE + i) * R + kk] = v[i];
+            }
+        }
+        if (want_GL && len <= TILE) {
+            for (int i = 0; i < len; ++i) {
+                std::vector<HT> v(len, (HT)0);
+                v[i] = (HT)1;
+                for (int s = 0; s < S; ++s) {
+                    std::vector<HT> hs(R, (HT)0);
+                    sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(vg, s));
+                    for (int k = 0; k < R; ++k) tb.L[(((size_t)var * S + s) * R + k) * TILE + i] = hs[k];
+                }
+            }
+        }
+    }
+
+    // segment products for the two-level chain
+    tb.Pseg.assign((size_t)S * 2 * R * R, (HT)0);
+    for (int s = 0; s < S; ++s) {
+        const HT* Pint = &tb.P[(((size_t)V_INTERIOR * S + s)) * R * R];
+        std::vector<HT> acc((size_t)R * R, (HT)0), tmp;
+        for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
+        for (int i = 0; i < seg; ++i) { matmul_rr<HT>(tmp, Pint, acc.data(), R); acc = tmp; }
+        std::copy(acc.begin(), acc.end(), tb.Pseg.begin() + ((size_t)s * 2 + 0) * R * R);
+        // last segment in scan order
+        std::fill(acc.begin(), acc.end(), (HT)0);
+        for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
+        for (int jj = (nseg - 1) * seg; jj < g.nb; ++jj) {
+            const int j = scans[s].causal ? jj : g.nb - 1 - jj;
+            const int var = g.nb == 1 ? V_SINGLE : (j == 0 ? V_FIRST : (j == g.nb - 1 ? V_LAST : V_INTERIOR));
+            matmul_rr<HT>(tmp, &tb.P[((size_t)var * S + s) * R * R], acc.data(), R);
+            acc = tmp;
+        }
+        std::copy(acc.begin(), acc.end(), tb.Pseg.begin() + ((size_t)s * 2 + 1) * R * R);
+    }
+
+}
+
+// whole-dimension matrices of one shard: response of the shard's outgoing tails to its
+// incoming carries.  Pdim [S][R][R], Mdim [S][S][R][R].
+template <typename HT>
+static void build_whole_dim(std::vector<HT>& Pdim, std::vector<HT>& Mdim, const std::vector<HostScan>& scans,
+                            int64_t n, int lo_closed, int hi_closed, int R, bool clamp)
+{
+    const int S = (int)scans.size();
+    Pdim.assign((size_t)S * R * R, (HT)0);
+    Mdim.assign((size_t)S * S * R * R, (HT)0);
+    std::vector<std::vector<HT>> coef(S);
+    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R);
+    const int len = (int)n;
+    auto dclosed = [&](int s) { return scans[s].causal ? lo_closed : hi_closed; };
+    for (int q = 0; q < S; ++q) {
+        if (dclosed(q)) continue;
+        for (int kk = 0; kk < R; ++kk) {
+            std::vector<HT> v(len, (HT)0), h(R, (HT)0);
+            h[kk] = (HT)1;
+            sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false);
+            for (int k = 0; k < R; ++k) Pdim[((size_t)q * R + k) * R + kk] = h[k];
+            for (int s = q + 1; s < S; ++s) {
+                std::vector<HT> hs(R, (HT)0);
+                sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && dclosed(s));
+                for (int k = 0; k < R; ++k) Mdim[(((size_t)q * S + s) * R + k) * R + kk] = hs[k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { bytes = n; if (n == 0) return cudaSuccess; return cudaMalloc(&p, n); }
+    DevBuf() = default; DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+};
+
+template <typename HT, typename CT>
+static cudaError_t upload(DevBuf& b, const std::vector<HT>& src)
+{
+    std::vector<CT> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (CT)src[i];
+    cudaError_t e = b.alloc(tmp.size() * sizeof(CT));
+    if (e != cudaSuccess || tmp.empty()) return e;
+    return cudaMemcpy(b.p, tmp.data(), tmp.size() * sizeof(CT), cudaMemcpyHostToDevice);
+}
+
+struct PassBase {
+    virtual ~PassBase() {}
+    virtual int run_tails(const void* in, void* out, cudaStream_t st) = 0;            // K1
+    virtual int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st) = 0; // K2/K3 (ext: shard carries)
+    virtual int run_final(const void* in, void* out, cudaStream_t st) = 0;            // K4
+    virtual bool needs_carries() const = 0;
+    virtual int launches() const = 0;
+    virtual size_t workspace() const = 0;
+    virtual std::string describe() const = 0;
+    // sharding support (column dimension only)
+    virtual bool d_open() const = 0;
+    virtual size_t shard_tail_elems() const = 0;     // elements of the compute type exported per shard
+    virtual int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) = 0;
+    virtual const void* ext_buffer() const = 0;
+};
+
+template <typename CT, int R>
+struct Pass : PassBase {
+    using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
+    int dtype = RF_F32;
+    PassParams<CT, R> pp;
+    DimGeom gx, gd;
+    std::vector<HostScan> sx, sd;
+    bool fused = false;
+    int segx = 1, nsegx = 1, segd = 1, nsegd = 1;
+    DevBuf TX, CX, TY, CY, SEGT, SEGC;
+    DevBuf dPx, dMx, dPsegx, dPd, dMd, dPsegd, dG, dL;
+    DevBuf dExt, dTailOut;           // shard carries in / tails out  [s][k][ly]
+    DimTables<HT> tx_tab, td_tab;
+
+    bool x_needs() const { return gx.nscans > 0 && gx.nb > 1; }
+    bool d_needs() const { return gd.nscans > 0 && (gd.nb > 1 || !gd.lo_closed || !gd.hi_closed); }
+    bool needs_carries() const override { return x_needs() || d_needs(); }
+    bool d_open() const override { return gd.nscans > 0 && (!gd.lo_closed || !gd.hi_closed); }
+    const void* ext_buffer() const override { return dExt.p; }
+
+    size_t workspace() const override
+    {
+        return TX.bytes + CX.bytes + TY.bytes + CY.bytes + SEGT.bytes + SEGC.bytes + dPx.bytes + dMx.bytes +
+               dPsegx.bytes + dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dL.bytes + dExt.bytes + dTailOut.bytes;
+    }
+
+    int launches() const override
+    {
+        int n = 1;                                   // K4
+        if (needs_carries()) {
+            n += 1;                                  // K1
+            if (x_needs()) n += gx.nscans * (nsegx > 1 ? 3 : 1);
+            if (x_needs() && d_needs() && fused) n += 1;
+            if (d_needs()) n += gd.nscans * (nsegd > 1 ? 3 : 1);
+        }
+        return n;
+    }
+
+    int init(int64_t Nx, int64_t Nd, int64_t No, bool signal, bool clamp)
+    {
+        // geometry -> params
+        std::memset(&pp, 0, sizeof(pp));
+        pp.Nx = Nx; pp.Nd = Nd; pp.No = No; pp.nlx = Nd * No; pp.nly = Nx * No;
+        pp.signal_mode = signal ? 1 : 0;
+        pp.tx = gx.t; pp.td = gd.t; pp.nbx = gx.nb; pp.nbd = gd.nb;
+        pp.lenx_last = gx.len_last; pp.lend_last = gd.len_last;
+        pp.clamp = clamp ? 1 : 0;
+        pp.x_lo_closed = gx.lo_closed; pp.x_hi_closed = gx.hi_closed;
+        pp.d_lo_closed = gd.lo_closed; pp.d_hi_closed = gd.hi_closed;
+        pp.mx = gx.nscans; pp.md = gd.nscans;
+        for (int s = 0; s < pp.mx; ++s) {
+            pp.sx.causal[s] = sx[s].causal;
+            for (int k = 0; k <= R; ++k) pp.sx.coef[s][k] = k <= sx[s].order ? (CT)cvt_coeff<HT>(sx[s].coeff[k]) : (CT)0;
+        }
+        for (int s = 0; s < pp.md; ++s) {
+            pp.sd.causal[s] = sd[s].causal;
+            for (int k = 0; k <= R; ++k) pp.sd.coef[s][k] = k <= sd[s].order ? (CT)cvt_coeff<HT>(sd[s].coeff[k]) : (CT)0;
+        }
+        auto pick_seg = [](int nb, int& seg, int& nseg) {
+            if (nb <= 512) { seg = nb; nseg = 1; }
+            else { seg = 256; nseg = (nb + seg - 1) / seg; }
+        };
+        pick_seg(gx.nb, segx, nsegx);
+        pick_seg(gd.nb, segd, nsegd);
+
+        if (pp.mx > 0) {
+            build_dim_tables<HT>(tx_tab, sx, gx, R, clamp, segx, nsegx, fused);
+            CUDA_TRY((upload<HT, CT>(dPx, tx_tab.P)));
+            CUDA_TRY((upload<HT, CT>(dMx, tx_tab.M)));
+            CUDA_TRY((upload<HT, CT>(dPsegx, tx_tab.Pseg)));
+            if (fused) CUDA_TRY((upload<HT, CT>(dG, tx_tab.G)));
+            const size_t n = (size_t)pp.mx * R * gx.nb * pp.nlx * sizeof(CT);
+            CUDA_TRY(TX.alloc(n)); CUDA_TRY(CX.alloc(n));
+            CUDA_TRY(cudaMemset(CX.p, 0, n));
+        }
+        if (pp.md > 0) {
+            build_dim_tables<HT>(td_tab, sd, gd, R, clamp, segd, nsegd, fused);
+            CUDA_TRY((upload<HT, CT>(dPd, td_tab.P)));
+            CUDA_TRY((upload<HT, CT>(dMd, td_tab.M)));
+            CUDA_TRY((upload<HT, CT>(dPsegd, td_tab.Pseg)));
+            if (fused) CUDA_TRY((upload<HT, CT>(dL, td_tab.L)));
+            const size_t n = (size_t)pp.md * R * gd.nb * pp.nly * sizeof(CT);
+            CUDA_TRY(TY.alloc(n)); CUDA_TRY(CY.alloc(n));
+            CUDA_TRY(cudaMemset(CY.p, 0, n));
+            if (d_open()) {
+                const size_t m = (size_t)pp.md * R * pp.nly * sizeof(CT);
+                CUDA_TRY(dExt.alloc(m)); CUDA_TRY(dTailOut.alloc(m));
+                CUDA_TRY(cudaMemset(dExt.p, 0, m));
+            }
+        }
+        {
+            const size_t a = (size_t)R * nsegx * pp.nlx, b = (size_t)R * nsegd * pp.nly;
+            const size_t n = std::max(nsegx > 1 ? a : 0, nsegd > 1 ? b : 0) * sizeof(CT);
+            CUDA_TRY(SEGT.alloc(n)); CUDA_TRY(SEGC.alloc(n));
+        }
+        pp.TX = (CT*)TX.p; pp.CX = (CT*)CX.p; pp.TY = (CT*)TY.p; pp.CY = (CT*)CY.p;
+        return RF_OK;
+    }
+
+    int run_tails(const void* in, void* out, cudaStream_t st) override
+    {
+        if (!needs_carries()) return RF_OK;
+        CUDA_TRY((Launch<CT, R>::tile(pp, in, out, 0, st)));
+        return RF_OK;
+    }
+
+    int run_chain(bool xdim, const void* ext_d, void* tail_out_d, cudaStream_t st)
+    {
+        const DimGeom& g = xdim ? gx : gd;
+        ChainParams<CT, R> cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.T = (CT*)(xdim ? TX.p : TY.p);
+        cp.C = (CT*)(xdim ? CX.p : CY.p);
+        cp.nl = xdim ? pp.nlx : pp.nly;
+        cp.nb = g.nb;
+        if (xdim && pp.signal_mode) { cp.tile_stride = 1; cp.line_stride = g.nb; }
+        else                        { cp.tile_stride = cp.nl; cp.line_stride = 1; }
+        cp.plane = (int64_t)g.nb * cp.nl;
+        cp.seg = xdim ? segx : segd; cp.nseg = xdim ? nsegx : nsegd;
+        cp.P = (const CT*)(xdim ? dPx.p : dPd.p);
+        cp.M = (const CT*)(xdim ? dMx.p : dMd.p);
+        cp.S = g.nscans;
+        cp.SEGT = (CT*)SEGT.p; cp.SEGC = (CT*)SEGC.p;
+        const auto& scans = xdim ? sx : sd;
+        for (int s = 0; s < g.nscans; ++s) {
+            cp.s = s;
+            cp.causal = scans[s].causal;
+            cp.Pseg = (const CT*)(xdim ? dPsegx.p : dPsegd.p) + (size_t)s * 2 * R * R;
+            cp.ext = (!xdim && ext_d) ? (const CT*)ext_d + (size_t)s * R * cp.nl : nullptr;
+            cp.tail_out = (!xdim && tail_out_d) ? (CT*)tail_out_d + (size_t)s * R * cp.nl : nullptr;
+            CUDA_TRY((Launch<CT, R>::chain(cp, st)));
+        }
+        return RF_OK;
+    }
+
+    int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st) override
+    {
+        if (!needs_carries()) return RF_OK;
+        if (x_needs()) { int rc = run_chain(true, nullptr, nullptr, st); if (rc) return rc; }
+        if (x_needs() && d_needs() && fused) {
+            CrossParams<CT, R> cr;
+            std::memset(&cr, 0, sizeof(cr));
+            cr.Nx = pp.Nx; cr.Nd = pp.Nd; cr.No = pp.No;
+            cr.tx = pp.tx; cr.td = pp.td; cr.nbx = pp.nbx; cr.nbd = pp.nbd;
+            cr.mx = pp.mx; cr.md = pp.md;
+            cr.CX = (const CT*)CX.p; cr.TY = (CT*)TY.p;
+            cr.nlx = pp.nlx; cr.nly = pp.nly;
+            cr.G = (const CT*)dG.p; cr.L = (const CT*)dL.p;
+            CUDA_TRY((Launch<CT, R>::cross(cr, st)));
+        }
+        if (d_needs()) { int rc = run_chain(false, ext_d, tail_out_d, st); if (rc) return rc; }
+        return RF_OK;
+    }
+
+    int run_final(const void* in, void* out, cudaStream_t st) override
+    {
+        CUDA_TRY((Launch<CT, R>::tile(pp, in, out, 1, st)));
+        return RF_OK;
+    }
+
+    size_t shard_tail_elems() const override { return d_open() ? (size_t)pp.md * R * pp.nly : 0; }
+
+    // Every shard holds the zero-history tails of all shards: tails[g][s][k][ly].
+    // Resolve this shard's incoming carries with the whole-dimension matrices.
+    int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) override;
+
+    std::string describe() const override
+    {
+        char b[512];
+        snprintf(b, sizeof(b),
+                 "  pass view [%lld][%lld][%lld] %s%s: x scans %d (tile %d, %d tiles), d scans %d (tile %d, %d tiles), "
+                 "order<=%d, launches %d\n",
+                 (long long)pp.No, (long long)pp.Nd, (long long)pp.Nx, fused ? "fused " : "",
+                 pp.signal_mode ? "signal-mode" : "image-mode", pp.mx, pp.tx, pp.nbx, pp.md, pp.td, pp.nbd, R,
+                 launches());
+        return b;
+    }
+};
+
+// small kernel: strip-level carry resolution (host of the multi-GPU layer)
+template <typename CT, int R>
+__global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restrict__ ext, int64_t nl, int S,
+                                     int nshards, int rank, const CT* __restrict__ Pdim3,
+                                     const CT* __restrict__ Mdim3, const int* __restrict__ causal)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nl) return;
+    // c[q][g][k] kept in local memory (S and nshards are tiny)
+    CT c[8][8][R];
+    const int64_t shard_stride = (int64_t)S * R * nl;
+    for (int s = 0; s < S; ++s) {
+        CT tau[R];
+        for (int k = 0; k < R; ++k) tau[k] = (CT)0;
+        for (int gg = 0; gg < nshards; ++gg) {
+            const int g = causal[s] ? gg : nshards - 1 - gg;
+            const int pos = (g == 0) ? 0 : (g == nshards - 1 ? 2 : 1);     // first / interior / last shard
+            const CT* Pdim = Pdim3 + (int64_t)pos * S * R * R;
+            const CT* Mdim = Mdim3 + (int64_t)pos * S * S * R * R;
+            for (int k = 0; k < R; ++k) c[s][g][k] = tau[k];
+            CT t[R];
+            for (int k = 0; k < R; ++k) t[k] = tails[g * shard_stride + ((int64_t)s * R + k) * nl + l];
+            for (int q = 0; q < s; ++q)
+                for (int k = 0; k < R; ++k)
+                    for (int kk = 0; kk < R; ++kk)
+                        t[k] = t[k] + Mdim[(((int64_t)q * S + s) * R + k) * R + kk] * c[q][g][kk];
+            for (int k = 0; k < R; ++k)
+                for (int kk = 0; kk < R; ++kk)
+                    t[k] = t[k] + Pdim[((int64_t)s * R + k) * R + kk] * tau[kk];
+            for (int k = 0; k < R; ++k) tau[k] = t[k];
+        }
+        for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = c[s][rank][k];
+    }
+}
+
+template <typename CT, int R>
+int Pass<CT, R>::shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st)
+{
+    if (!d_open()) return RF_OK;
+    if (nshards > 8 || pp.md > 8) return fail(RF_EUNSUPPORTED, "shard_resolve supports <= 8 shards and <= 8 scans");
+    // whole-shard matrices for a first / interior / last shard (the clamp rule differs)
+    std::vector<HT> P3, M3, Pt, Mt;
+    for (int pos = 0; pos < 3; ++pos) {
+        build_whole_dim<HT>(Pt, Mt, sd, gd.n, pos == 0 ? 1 : 0, pos == 2 ? 1 : 0, R, pp.clamp != 0);
+        P3.insert(P3.end(), Pt.begin(), Pt.end());
+        M3.insert(M3.end(), Mt.begin(), Mt.end());
+    }
+    DevBuf dP, dM, dC;
+    CUDA_TRY((upload<HT, CT>(dP, P3)));
+    CUDA_TRY((upload<HT, CT>(dM, M3)));
+    std::vector<int> causal(pp.md);
+    for (int s = 0; s < pp.md; ++s) causal[s] = sd[s].causal;
+    CUDA_TRY(dC.alloc(causal.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(dC.p, causal.data(), causal.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int64_t nl = pp.nly;
+    shard_resolve_kernel<CT, R><<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(
+        (const CT*)gathered, (CT*)dExt.p, nl, pp.md, nshards, rank, (const CT*)dP.p, (const CT*)dM.p,
+        (const int*)dC.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));   // temporaries are freed on return
+    return RF_OK;
+}
+
+// narrow integer types are widened to the 32-bit compute ring on entry and truncated on exit
+// (arithmetic mod 2^16 / 2^8 is a quotient of arithmetic mod 2^32, so this is exact)
+template <typename ST>
+__global__ void widen_kernel(const ST* __restrict__ in, uint32_t* __restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (uint32_t)in[i];
+}
+template <typename ST>
+__global__ void narrow_kernel(const uint32_t* __restrict__ in, ST* __restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (ST)in[i];
+}
+
+} // namespace rfb
+
+// ---------------------------------------------------------------------------------------------
+// the opaque plan
+// ---------------------------------------------------------------------------------------------
+using namespace rfb;
+
+struct rf_plan {
+    rf_desc desc;
+    int R = 1;
+    bool is_float = true;
+    size_t elem_bytes = 4;
+    int64_t total = 1;
+    std::vector<std::unique_ptr<PassBase>> passes;
+    int shard_pass = -1;
+    std::string text;
+    DevBuf stage;            // 32-bit staging for 8/16-bit integer filters
+};
+
+static int widen_in(rf_plan* plan, const void* in_dev, cudaStream_t st)
+{
+    const int64_t n = plan->total;
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    if (plan->elem_bytes == 2) widen_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)in_dev, (uint32_t*)plan->stage.p, n);
+    else                       widen_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)in_dev, (uint32_t*)plan->stage.p, n);
+    CUDA_TRY(cudaGetLastError());
+    return RF_OK;
+}
+static int narrow_out(rf_plan* plan, void* out_dev, cudaStream_t st)
+{
+    const int64_t n = plan->total;
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    if (plan->elem_bytes == 2) narrow_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint32_t*)plan->stage.p, (uint16_t*)out_dev, n);
+    else                       narrow_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint32_t*)plan->stage.p, (uint8_t*)out_dev, n);
+    CUDA_TRY(cudaGetLastError());
+    return RF_OK;
+}
+
+static int round_order(int r)
+{
+    const int opts[] = { 1, 2, 3, 4, 8, 16, 32 };
+    for (int o : opts) if (r <= o) return o;
+    return -1;
+}
+
+template <typename CT, int R>
+static int make_pass(rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                     int64_t Nx, int64_t Nd, int64_t No, int tx, int td, bool fused, bool d_is_shard)
+{
+    const rf_desc& d = plan->desc;
+    auto ps = std::unique_ptr<Pass<CT, R>>(new (std::nothrow) Pass<CT, R>());
+    if (!ps) return fail(RF_ENOMEM, "out of host memory");
+    ps->dtype = d.dtype;
+    ps->sx = sx; ps->sd = sd; ps->fused = fused;
+    auto geom = [](DimGeom& g, int64_t n, int t, int nscans) {
+        g.n = n; g.t = t; g.nb = (int)((n + t - 1) / t); g.len_last = (int)(n - (int64_t)(g.nb - 1) * t);
+        g.nscans = nscans; g.lo_closed = 1; g.hi_closed = 1;
+    };
+    geom(ps->gx, Nx, tx, (int)sx.size());
+    geom(ps->gd, Nd, td, (int)sd.size());
+    if (d_is_shard) { ps->gd.lo_closed = d.opt.open_lo ? 0 : 1; ps->gd.hi_closed = d.opt.open_hi ? 0 : 1; }
+    // signal mode: too few rows to give every thread of a CTA its own line
+    const bool signal = sd.empty() && !sx.empty() && (Nd * No) < TILE && ps->gx.nb > 1;
+    int rc = ps->init(Nx, Nd, No, signal, d.border == RF_BORDER_CLAMP);
+    if (rc) return rc;
+    plan->passes.push_back(std::move(ps));
+    return RF_OK;
+}
+
+template <typename CT>
+static int make_pass_R(rf_plan* plan, int R, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                       int64_t Nx, int64_t Nd, int64_t No, int tx, int td, bool fused, bool d_is_shard)
+{
+    switch (R) {
+    case 1:  return make_pass<CT, 1>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    case 2:  return make_pass<CT, 2>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    case 3:  return make_pass<CT, 3>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    case 4:  return make_pass<CT, 4>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    case 8:  return make_pass<CT, 8>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    case 16: return make_pass<CT, 16>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    case 32: return make_pass<CT, 32>(plan, sx, sd, Nx, Nd, No, tx, td, fused, d_is_shard);
+    }
+    return fail(RF_EUNSUPPORTED, "unsupported padded order %d", R);
+}
+
+static size_t dtype_bytes(int dt)
+{
+    switch (dt) {
+    case RF_F32: case RF_I32: case RF_U32: return 4;
+    case RF_I16: case RF_U16: return 2;
+    case RF_I8:  case RF_U8:  return 1;
+    }
+    return 0;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* rf_version(void) { return "recfilter_b200 0.1 (sm_100a)"; }
+const char* rf_last_error(void) { return g_err; }
+
+int rf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rf_set_device(int device)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    return RF_OK;
+}
+
+int rf_plan_create(const rf_desc* desc, rf_plan** out)
+{
+    if (!desc || !out) return fail(RF_EINVAL, "null argument");
+    *out = nullptr;
+    if (desc->ndim < 1 || desc->ndim > RF_MAX_DIMS) return fail(RF_EINVAL, "ndim must be 1..%d", RF_MAX_DIMS);
+    if (desc->nscans < 0 || desc->nscans > RF_MAX_SCANS) return fail(RF_EINVAL, "nscans must be 0..%d", RF_MAX_SCANS);
+    const size_t eb = dtype_bytes(desc->dtype);
+    if (!eb) return fail(RF_EINVAL, "unknown dtype %d", desc->dtype);
+    if (desc->border != RF_BORDER_ZERO && desc->border != RF_BORDER_CLAMP) return fail(RF_EINVAL, "unknown border %d", desc->border);
+    int64_t total = 1;
+    for (int d = 0; d < desc->ndim; ++d) {
+        if (desc->extent[d] < 0) return fail(RF_EINVAL, "negative extent in dimension %d", d);
+        total *= desc->extent[d];
+    }
+    int maxr = 1;
+    for (int s = 0; s < desc->nscans; ++s) {
+        const rf_scan& sc = desc->scans[s];
+        // lib/recfilter.cpp:296-300 (unknown dimension), :274-278 (needs feed forward + feedback)
+        if (sc.dim < 0 || sc.dim >= desc->ndim) return fail(RF_EINVAL, "scan %d: dimension %d is not a filter dimension", s, sc.dim);
+        if (sc.order < 1 || sc.order > RF_MAX_ORDER) return fail(RF_EINVAL, "scan %d: order must be 1..%d", s, RF_MAX_ORDER);
+        maxr = std::max(maxr, sc.order);
+    }
+    if (rf_device_count() <= 0) return fail(RF_ENODEVICE, "no CUDA device available: this engine has no CPU fallback");
+
+    std::unique_ptr<rf_plan> plan(new (std::nothrow) rf_plan());
+    if (!plan) return fail(RF_ENOMEM, "out of host memory");
+    plan->desc = *desc;
+    plan->R = round_order(maxr);
+    plan->is_float = desc->dtype == RF_F32;
+    plan->elem_bytes = eb;
+    plan->total = total;
+
+    const rf_options& opt = desc->opt;
+    auto tile_of = [&](int d) {
+        int t = TILE;
+        if (opt.honor_tile && opt.tile[d] > 0) t = std::min(opt.tile[d], TILE);
+        return t;
+    };
+
+    if (total > 0 && desc->nscans > 0) {
+        // group scans by dimension, keeping the add_filter order inside a dimension
+        // (scans of different dimensions commute: lib/split.cpp:207-242)
+        std::vector<std::vector<HostScan>> by_dim(desc->ndim);
+        for (int s = 0; s < desc->nscans; ++s) {
+            HostScan h; h.causal = desc->scans[s].causal ? 1 : 0; h.order = desc->scans[s].order;
+            std::memcpy(h.coeff, desc->scans[s].coeff, sizeof(h.coeff));
+            by_dim[desc->scans[s].dim].push_back(h);
+        }
+        for (int d = 0; d < desc->ndim; ++d)
+            if ((int)by_dim[d].size() > MAX_SCANS_DIM)
+                return fail(RF_EUNSUPPORTED, "more than %d scans along dimension %d", MAX_SCANS_DIM, d);
+        const int shard_dim = (opt.open_lo || opt.open_hi) ? opt.shard_dim : -1;
+        if (shard_dim == 0) return fail(RF_EUNSUPPORTED, "sharding along the contiguous dimension is not supported");
+        if (shard_dim >= desc->ndim) return fail(RF_EINVAL, "shard_dim out of range");
+
+        const std::vector<HostScan> none;
+        const int R = plan->R;
+        bool fuse01 = desc->ndim >= 2 && !by_dim[0].empty() && !by_dim[1].empty() && opt.fuse_dims != 0;
+        if (fuse01 && (size_t)by_dim[0].size() * by_dim[1].size() * R * R > 2048) fuse01 = false;
+
+        auto add = [&](const std::vector<HostScan>& sx, const std::vector<HostScan>& sd, int64_t Nx, int64_t Nd,
+                       int64_t No, int tx, int td, bool fused, bool shard) -> int {
+            int rc = plan->is_float ? make_pass_R<float>(plan.get(), R, sx, sd, Nx, Nd, No, tx, td, fused, shard)
+                                    : make_pass_R<uint32_t>(plan.get(), R, sx, sd, Nx, Nd, No, tx, td, fused, shard);
+            if (rc == RF_OK && shard) plan->shard_pass = (int)plan->passes.size() - 1;
+            return rc;
+        };
+
+        int first_d = 0;
+        if (fuse01) {
+            int64_t No = 1;
+            for (int d = 2; d < desc->ndim; ++d) No *= desc->extent[d];
+            int rc = add(by_dim[0], by_dim[1], desc->extent[0], desc->extent[1], No, tile_of(0), tile_of(1), true,
+                         shard_dim == 1);
+            if (rc) return rc;
+            first_d = 2;
+        } else if (!by_dim[0].empty()) {
+            int64_t rows = 1;
+            for (int d = 1; d < desc->ndim; ++d) rows *= desc->extent[d];
+            int rc = add(by_dim[0], none, desc->extent[0], rows, 1, tile_of(0), TILE, false, false);
+            if (rc) return rc;
+            first_d = 1;
+        } else {
+            first_d = 1;
+        }
+        for (int d = first_d; d < desc->ndim; ++d) {
+            if (by_dim[d].empty()) continue;
+            int64_t inner = 1, outer = 1;
+            for (int e = 0; e < d; ++e) inner *= desc->extent[e];
+            for (int e = d + 1; e < desc->ndim; ++e) outer *= desc->extent[e];
+            int rc = add(none, by_dim[d], inner, desc->extent[d], outer, TILE, tile_of(d), false, shard_dim == d);
+            if (rc) return rc;
+        }
+        if (shard_dim >= 0 && plan->shard_pass < 0)
+            return fail(RF_EINVAL, "shard_dim %d has no scans: shard it as independent batches instead", shard_dim);
+    }
+
+    if (eb < 4 && total > 0 && !plan->passes.empty()) {
+        if (plan->shard_pass >= 0) return fail(RF_EUNSUPPORTED, "sharded plans need a 32-bit element type");
+        CUDA_TRY(plan->stage.alloc((size_t)total * 4));
+    }
+
+    char head[256];
+    snprintf(head, sizeof(head), "recfilter_b200 plan: %d-D, %lld samples, dtype %d, border %s, %d scans, %d passes\n",
+             desc->ndim, (long long)total, desc->dtype, desc->border ? "clamp" : "zero", desc->nscans,
+             (int)plan->passes.size());
+    plan->text = head;
+    for (auto& p : plan->passes) plan->text += p->describe();
+    *out = plan.release();
+    return RF_OK;
+}
+
+void rf_plan_destroy(rf_plan* plan) { delete plan; }
+
+size_t rf_plan_workspace_bytes(const rf_plan* plan)
+{
+    size_t n = 0;
+    if (plan) { for (auto& p : plan->passes) n += p->workspace(); n += plan->stage.bytes; }
+    return n;
+}
+
+int rf_plan_num_launches(const rf_plan* plan)
+{
+    int n = 0;
+    if (plan) { for (auto& p : plan->passes) n += p->launches(); if (plan->stage.p) n += 2; }
+    return n;
+}
+
+int rf_plan_describe(const rf_plan* plan, char* buf, size_t n)
+{
+    if (!plan || !buf || n == 0) return fail(RF_EINVAL, "null argument");
+    snprintf(buf, n, "%s", plan->text.c_str());
+    return RF_OK;
+}
+
+static int copy_through(rf_plan* plan, const void* in_dev, void* out_dev, cudaStream_t st)
+{
+    if (in_dev != out_dev && plan->total > 0)
+        CUDA_TRY(cudaMemcpyAsync(out_dev, in_dev, (size_t)plan->total * plan->elem_bytes, cudaMemcpyDeviceToDevice, st));
+    return RF_OK;
+}
+
+int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stream)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    if (plan->total == 0) return RF_OK;
+    if (!in_dev || !out_dev) return fail(RF_EINVAL, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->passes.empty()) return copy_through(plan, in_dev, out_dev, st);
+    const void* src = in_dev;
+    void* dst = out_dev;
+    int rc;
+    if (plan->stage.p) {
+        if ((rc = widen_in(plan, in_dev, st))) return rc;
+        src = plan->stage.p; dst = plan->stage.p;
+    }
+    for (auto& p : plan->passes) {
+        if ((rc = p->run_tails(src, dst, st))) return rc;
+        if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;
+        if ((rc = p->run_final(src, dst, st))) return rc;
+        src = dst;
+    }
+    if (plan->stage.p) return narrow_out(plan, out_dev, st);
+    return RF_OK;
+}
+
+int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    if (plan->total == 0) return RF_OK;
+    if (!in_host || !out_host) return fail(RF_EINVAL, "null buffer");
+    const size_t bytes = (size_t)plan->total * plan->elem_bytes;
+    DevBuf buf;
+    CUDA_TRY(buf.alloc(bytes));
+    CUDA_TRY(cudaMemcpy(buf.p, in_host, bytes, cudaMemcpyHostToDevice));
+    int rc = rf_plan_execute(plan, buf.p, buf.p, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(out_host, buf.p, bytes, cudaMemcpyDeviceToHost));
+    return RF_OK;
+}
+
+int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter)
+{
+    if (!plan || !ms_per_iter || iters < 1) return fail(RF_EINVAL, "bad argument");
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+    int rc = rf_plan_execute(plan, in_dev, out_dev, nullptr);          // warm-up (lib/recfilter.cpp:995-997)
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(a, 0));
+    for (int i = 0; i < iters; ++i)
+        if ((rc = rf_plan_execute(plan, in_dev, out_dev, nullptr))) return rc;
+    CUDA_TRY(cudaEventRecord(b, 0));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_per_iter = ms / iters;
+    return RF_OK;
+}
+
+size_t rf_plan_shard_tail_bytes(const rf_plan* plan)
+{
+    if (!plan || plan->shard_pass < 0) return 0;
+    return plan->passes[plan->shard_pass]->shard_tail_elems() * 4;
+}
+
+int rf_plan_stage1(rf_plan* plan, const void* in_dev, void* out_dev, void* tails_dev, void* stream)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* src = in_dev;
+    for (int i = 0; i <= plan->shard_pass; ++i) {
+        auto& p = plan->passes[i];
+        int rc;
+        if ((rc = p->run_tails(src, out_dev, st))) return rc;
+        if (i == plan->shard_pass) return p->run_carries(nullptr, tails_dev, st);
+        if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;
+        if ((rc = p->run_final(src, out_dev, st))) return rc;
+        src = out_dev;
+    }
+    return RF_OK;
+}
+
+int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev, const void* gathered_tails_dev,
+                   int nshards, int shard_rank, void* stream)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
+    if (nshards < 1 || shard_rank < 0 || shard_rank >= nshards) return fail(RF_EINVAL, "bad shard rank");
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* src = plan->shard_pass == 0 ? in_dev : out_dev;
+    for (int i = plan->shard_pass; i < (int)plan->passes.size(); ++i) {
+        auto& p = plan->passes[i];
+        int rc;
+        if (i == plan->shard_pass) {
+            if ((rc = p->shard_resolve(gathered_tails_dev, nshards, shard_rank, st))) return rc;
+            // tails of K1 are still valid: redo the carry completion with the incoming shard carries
+            if ((rc = p->run_carries(p->ext_buffer(), nullptr, st))) return rc;
+        } else {
+            if ((rc = p->run_tails(src, out_dev, st))) return rc;
+            if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;
+        }
+        if ((rc = p->run_final(src, out_dev, st))) return rc;
+        src = out_dev;
+    }
+    return RF_OK;
+}
+
+int rf_malloc(void** p, size_t bytes) { if (!p) return fail(RF_EINVAL, "null"); CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1)); return RF_OK; }
+int rf_free(void* p) { CUDA_TRY(cudaFree(p)); return RF_OK; }
+int rf_memcpy_h2d(void* d, const void* s, size_t n) { CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyHostToDevice)); return RF_OK; }
+int rf_memcpy_d2h(void* d, const void* s, size_t n) { CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost)); return RF_OK; }
+int rf_memset(void* d, int v, size_t n) { CUDA_TRY(cudaMemset(d, v, n)); return RF_OK; }
+int rf_malloc_host(void** p, size_t bytes) { if (!p) return fail(RF_EINVAL, "null"); CUDA_TRY(cudaMallocHost(p, bytes ? bytes : 1)); return RF_OK; }
+int rf_free_host(void* p) { CUDA_TRY(cudaFreeHost(p)); return RF_OK; }
+int rf_synchronize(void) { CUDA_TRY(cudaDeviceSynchronize()); return RF_OK; }
+
+} // extern "C"
+#pragma GCC visibility pop
