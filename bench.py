@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 recursive-filter engine.
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): apps/gaussian --
+3rd-order van Vliet-Young-Verbeek Gaussian (sigma 5), causal + anticausal along x and y,
+clamped border, 8192 x 8192 float32 images.  One "step" filters a batch of BATCH distinct
+synthetic images (so consecutive launches never re-read a cached input; every image,
+268 MB, is itself larger than the 126 MB L2).
+
+  N = 1   the whole image on one GPU (rf_plan_execute)
+  N > 1   every image is cut into N horizontal strips, one per rank; x scans are strip
+          local, the y scans exchange only their order-3 boundary tails (2*3*8192 floats
+          per image and rank) with ONE NCCL all-gather per step (rf_plan_stage1 /
+          all_gather / rf_plan_stage2).  Total work is fixed: "scaling": "strong".
+
+Metric: Gsamples/s = filtered output samples per second over all ranks (device time,
+CUDA events, max over ranks).  `roofline` is the dominant kernel (the final tile kernel,
+which reads the image and writes the result) against the measured HBM copy bandwidth;
+`e2e` is the same metric through the host-buffer C-ABI call (rf_plan_execute_host: H2D +
+kernels + D2H inside the timed region); `cpu_baseline` is the oracle's serial recurrence
+loops (the reference's CPU path stand-in) on the host cores.
+
+`--impl reference` times that CPU path alone (rank 0 only), same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W = H = 8192
+SIGMA, ORDER = 5.0, 3
+BATCH = 4
+METRIC = "Gsamples/s and % of HBM roofline for 2-D r=3 Gaussian 8192^2 fp32"
+WORKLOAD = "apps/gaussian: 3rd-order VYV Gaussian sigma=5, +x,-x,+y,-y, clamped border, 8192x8192 fp32"
+
+
+def scans_c3():
+    from recfilter_b200 import gaussian_weights
+    w3 = gaussian_weights(SIGMA, ORDER)
+    return [(0, True, w3), (0, False, w3), (1, True, w3), (1, False, w3)]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle): the reference-arm and the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def cpu_rate(rows: int, reps: int, threads: int):
+    """Gsamples/s of the serial recurrence loops on a `rows` x 8192 strip of the workload."""
+    from oracle import oracle
+    oracle.build()
+    rng = np.random.default_rng(2)
+    img = rng.random((rows, W), dtype=np.float32)
+    sc = scans_c3()
+    best = float("inf")
+    for _ in range(reps):
+        work = img.copy()
+        t0 = time.perf_counter()
+        oracle.apply_filter(work, sc, "clamp", threads=threads, inplace=True)
+        best = min(best, time.perf_counter() - t0)
+    return img.size / best / 1e9, best
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's CPU path stand-in (oracle port, all host threads)."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    rng = np.random.default_rng(2)
+    rows = H
+    img = rng.random((rows, W), dtype=np.float32)
+    sc = scans_c3()
+    for _ in range(max(args.warmup, 1)):
+        oracle.apply_filter(img, sc, "clamp", threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.apply_filter(img, sc, "clamp", threads=threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * img.size / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+                         "sample": "one full 8192x8192 image per step, oracle/oracle.c serial recurrence loops, "
+                                   "OpenMP over independent lines (Halide x86 JIT of the reference cannot be built here)"},
+        "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import recfilter_b200 as rf
+    from recfilter_b200 import Plan, Scan
+
+    if not torch.cuda.is_available() or rf.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    rf.lib().rf_set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N = world
+    assert N == args.gpus or world == 1, "--gpus must match the torchrun world size"
+    assert H % N == 0
+
+    scans = [Scan(*s) for s in scans_c3()]
+    B = args.batch
+    rows = H // N
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    srcs = [torch.rand((rows, W), device="cuda", dtype=torch.float32, generator=gen) for _ in range(B)]
+    dsts = [torch.empty_like(s) for s in srcs]
+
+    if N == 1:
+        plans = [Plan((W, H), "f32", scans, "clamp")]
+        launches_per_image = plans[0].num_launches
+
+        def step():
+            for s, d in zip(srcs, dsts):
+                plans[0].execute(s, d)
+    else:
+        plans = [Plan((W, rows), "f32", scans, "clamp", shard_dim=1, open_lo=rank > 0, open_hi=rank < N - 1)
+                 for _ in range(B)]
+        tail_elems = plans[0].shard_tail_bytes // 4
+        my_tails = torch.empty((B, tail_elems), device="cuda", dtype=torch.float32)
+        all_tails = torch.empty((N, B, tail_elems), device="cuda", dtype=torch.float32)
+        gathered = torch.empty((B, N, tail_elems), device="cuda", dtype=torch.float32)
+        launches_per_image = plans[0].num_launches + 3   # carry chains run twice + strip resolve
+
+        def step():
+            for i in range(B):
+                plans[i].stage1(srcs[i], dsts[i], my_tails[i])
+            dist.all_gather_into_tensor(all_tails, my_tails)
+            gathered.copy_(all_tails.transpose(0, 1))
+            for i in range(B):
+                plans[i].stage2(srcs[i], dsts[i], gathered[i], N, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    samples_per_step = B * W * H
+    value = args.steps * samples_per_step / (ms * 1e-3) / 1e9
+
+    # ---- per-kernel timing of the dominant kernel (separate loop, events around every launch) ------
+    for p in plans:
+        p.stage_timing(True)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    stage = {}
+    for p in plans:
+        for k, v in p.stage_times().items():
+            s = stage.setdefault(k, {"ms": 0.0, "launches": 0})
+            s["ms"] += v["ms"]; s["launches"] += v["launches"]
+        p.stage_timing(False)
+    peak, peak_src = measured_peaks()
+    fin = stage["tile_final"]
+    k4_ms = fin["ms"] / max(fin["launches"], 1)
+    alg_bytes = 8.0 * W * rows                       # 4 B read + 4 B written per sample of this rank's strip
+    achieved = alg_bytes / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+    total_stage_ms = sum(v["ms"] for v in stage.values())
+    roofline = {"bound": "hbm", "kernel": "tile_kernel<float,3,FINAL>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_us": k4_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes,
+                "share_of_step": fin["ms"] / total_stage_ms if total_stage_ms else None,
+                "stage_us_per_image": {k: v["ms"] * 1e3 / (3 * B) for k, v in stage.items()},
+                "whole_filter_frac_of_peak": (8.0 * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak / 1.0}
+
+    # ---- end to end through the host-buffer C ABI --------------------------------------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    host_in = [torch.empty((rows, W), dtype=torch.float32).pin_memory() for _ in range(B)]
+    host_out = [torch.empty((rows, W), dtype=torch.float32).pin_memory() for _ in range(B)]
+    for hi, s in zip(host_in, srcs):
+        hi.copy_(s)
+
+    def e2e_step():
+        if N == 1:
+            for hi, ho in zip(host_in, host_out):
+                plans[0].realize_ptr(hi.data_ptr(), ho.data_ptr())
+        else:
+            for i in range(B):
+                srcs[i].copy_(host_in[i], non_blocking=True)
+            step()
+            for i in range(B):
+                host_out[i].copy_(dsts[i], non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    e2e_value = e2e_steps * samples_per_step / dt / 1e9
+    e2e = {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 4 * samples_per_step,
+           "d2h_bytes_per_step": 4 * samples_per_step, "steps": e2e_steps,
+           "api": "rf_plan_execute_host (RecFilter::realize path)" if N == 1 else
+                  "pinned H2D + rf_plan_stage1/all_gather/rf_plan_stage2 + D2H"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        th = oracle.max_threads()
+        v_all, _ = cpu_rate(H, 3, th)
+        v_one, _ = cpu_rate(H // 4, 2, 1)
+        cpu = {"value": v_all, "unit": "Gsamples/s", "cores": th, "kind": "port",
+               "single_thread_value": v_one,
+               "sample": f"one full 8192x8192 image (best of 3) with {th} OpenMP threads; single-thread figure on a "
+                         "2048x8192 strip; oracle/oracle.c serial recurrence loops"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": N, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": B, "sharding": "none" if N == 1 else f"{N} row strips",
+                       "l2": "every image (268 MB) exceeds L2 and a step cycles through %d distinct images" % B,
+                       "tile": 64},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,
+            "hbm_roofline_pct": 100.0 * (8.0 * value) / peak,
+            "hbm_roofline_pct_of_8TBs": 100.0 * (8.0 * value) / 8000.0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -128,6 +128,18 @@ int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host);
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter);
 
 /*
+ * Per-stage device timing (development / bench aid; the reference's analogue is the
+ * nvprof kernel-sum of scripts/cuda_profile.sh:27-35).  While enabled, every kernel of
+ * rf_plan_execute / stage1 / stage2 is bracketed by CUDA events on its stream.
+ * Stages: 0 tile kernel (tails), 1 carry chains, 2 cross-dimension residual,
+ * 3 tile kernel (final), 4 integer widen/narrow.  ms[] are accumulated milliseconds and
+ * counts[] the number of launches since timing was enabled.
+ */
+#define RF_NUM_STAGES 5
+int rf_plan_stage_timing(rf_plan* plan, int enable);
+int rf_plan_stage_times(rf_plan* plan, double* ms, long* counts, int n);
+
+/*
  * Strip-sharded execution (one plan per device, opt.shard_dim set).
  *   stage1: intra-shard work with zero incoming carries (passes before the sharded
  *           one run to completion into out_dev); writes this shard's outgoing

@@ -95,6 +95,8 @@ def lib():
     L.rf_plan_shard_tail_bytes.restype = sz
     L.rf_plan_stage1.argtypes = [vp, vp, vp, vp, vp]
     L.rf_plan_stage2.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.rf_plan_stage_timing.argtypes = [vp, i32]
+    L.rf_plan_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), i32]
     L.rf_malloc.argtypes = [C.POINTER(vp), sz]
     L.rf_free.argtypes = [vp]
     L.rf_memcpy_h2d.argtypes = [vp, vp, sz]
@@ -257,6 +259,17 @@ class Plan:
         _check(lib().rf_plan_profile(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), int(iters),
                                      C.byref(ms)), "rf_plan_profile")
         return float(ms.value)
+
+    STAGES = ("tile_tails", "carry_chain", "cross_residual", "tile_final", "convert")
+
+    def stage_timing(self, enable: bool):
+        _check(lib().rf_plan_stage_timing(self._h, 1 if enable else 0), "rf_plan_stage_timing")
+
+    def stage_times(self) -> dict:
+        ms = (C.c_double * 5)()
+        cnt = (C.c_long * 5)()
+        _check(lib().rf_plan_stage_times(self._h, ms, cnt, 5), "rf_plan_stage_times")
+        return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(self.STAGES)}
 
     # -- sharded execution ------------------------------------------------------------------
     def stage1(self, src, dst, tails, stream=None):

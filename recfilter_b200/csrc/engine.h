@@ -39,6 +39,12 @@ struct DimGeom {
     int     nscans = 0;
 };
 
+// accumulation / table type of the carry algebra: the small K2/K3 kernels work in fp64 for
+// float filters (independent rounding errors of the r history values are amplified by the
+// recurrence, so carries must be much better than fp32-accurate before they are rounded once)
+template <typename CT> struct TabType { typedef CT type; };
+template <> struct TabType<float> { typedef double type; };
+
 // device-side scan table entry (coefficients already converted to the compute type)
 template <typename CT, int R>
 struct ScanTab {
@@ -68,6 +74,7 @@ struct PassParams {
 // parameters of the carry-chain kernels for one scan of one dimension
 template <typename CT, int R>
 struct ChainParams {
+    typedef typename TabType<CT>::type TT;
     CT* T; CT* C;               // tails in, carries out
     int64_t nl;                 // lines
     int nb;                     // tiles
@@ -75,11 +82,11 @@ struct ChainParams {
     int s;                      // scan being chained
     int causal;
     int seg, nseg;              // tiles per segment, segments
-    const CT* P;                // [V_COUNT][S][R][R]
-    const CT* M;                // [V_COUNT][S][S][R][R]  (q -> s)
+    const TT* P;                // [V_COUNT][S][R][R]
+    const TT* M;                // [V_COUNT][S][S][R][R]  (q -> s)
     int S;                      // scans in this dimension
-    const CT* Pseg;             // [2][R][R]: product over a full interior segment / over the last segment
-    CT* SEGT; CT* SEGC;         // [k][g][l] segment tails / carries
+    const TT* Pseg;             // [2][R][R]: product over a full interior segment / over the last segment
+    TT* SEGT; TT* SEGC;         // [k][g][l] segment tails / carries
     const CT* ext;              // external carry-in for this scan [k][l] or null
     CT* tail_out;               // final outgoing tail [k][l] or null (sharding)
 };
@@ -87,13 +94,14 @@ struct ChainParams {
 // parameters of the cross-dimension residual kernel (x carries -> d tails)
 template <typename CT, int R>
 struct CrossParams {
+    typedef typename TabType<CT>::type TT;
     int64_t Nx, Nd, No;
     int tx, td, nbx, nbd;
     int mx, md;
     const CT* CX; CT* TY;
     int64_t nlx, nly;
-    const CT* G;    // [V_COUNT][mx][TILE][R]   x response to a unit carry of scan q, after all later x scans
-    const CT* L;    // [V_COUNT][md][R][TILE]   d tail of scan s per unit impulse at row i (scans 1..s)
+    const TT* G;    // [V_COUNT][mx][TILE][R]   x response to a unit carry of scan q, after all later x scans
+    const TT* L;    // [V_COUNT][md][R][TILE]   d tail of scan s per unit impulse at row i (scans 1..s)
 };
 
 } // namespace rfb

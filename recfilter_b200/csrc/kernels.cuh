@@ -33,6 +33,7 @@ constexpr int SROW = TILE + 4;   // padded shared-memory row (words): 16B aligne
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float    madd(float a, float b, float c)          { return fmaf(a, b, c); }
 __device__ __forceinline__ uint32_t madd(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+__device__ __forceinline__ double   madd(double a, double b, double c)       { return fma(a, b, c); }
 
 
 /*
@@ -357,12 +358,12 @@ __device__ __forceinline__ int tile_variant(int j, int nb)
     return V_INTERIOR;
 }
 
-template <typename CT, int R>
-__device__ __forceinline__ void matvec_acc(CT (&y)[R], const CT* __restrict__ m, const CT (&x)[R])
+template <typename TT, int R>
+__device__ __forceinline__ void matvec_acc(TT (&y)[R], const TT* __restrict__ m, const TT (&x)[R])
 {
 #pragma unroll (R <= 8 ? R : 1)
     for (int k = 0; k < R; ++k) {
-        CT a = y[k];
+        TT a = y[k];
 #pragma unroll (R <= 8 ? R : 1)
         for (int kk = 0; kk < R; ++kk) a = madd(m[k * R + kk], x[kk], a);
         y[k] = a;
@@ -378,10 +379,11 @@ chain_local_kernel(const __grid_constant__ ChainParams<CT, R> p)
     const int64_t l = gid % p.nl;
     const int g = (int)(gid / p.nl);          // segment index in SCAN order
     const int s = p.s;
+    typedef typename TabType<CT>::type TT;
 
-    CT tau[R];
+    TT tau[R];
 #pragma unroll (R <= 8 ? R : 1)
-    for (int k = 0; k < R; ++k) tau[k] = (g == 0 && p.ext) ? p.ext[(int64_t)k * p.nl + l] : (CT)0;
+    for (int k = 0; k < R; ++k) tau[k] = (g == 0 && p.ext) ? (TT)p.ext[(int64_t)k * p.nl + l] : (TT)0;
 
     const int j_begin = g * p.seg;
     const int j_end = min(p.nb, j_begin + p.seg);
@@ -389,20 +391,20 @@ chain_local_kernel(const __grid_constant__ ChainParams<CT, R> p)
         const int j = p.causal ? jj : p.nb - 1 - jj;      // tile index in memory
         const int var = tile_variant(j, p.nb);
         const int64_t base = (int64_t)j * p.tile_stride + l * p.line_stride;
-        CT t[R];
+        TT t[R];
 #pragma unroll (R <= 8 ? R : 1)
         for (int k = 0; k < R; ++k) {
             const int64_t idx = ((int64_t)s * R + k) * p.plane + base;
-            p.C[idx] = tau[k];
-            t[k] = p.T[idx];
+            p.C[idx] = (CT)tau[k];
+            t[k] = (TT)p.T[idx];
         }
         for (int q = 0; q < s; ++q) {
-            CT cq[R];
+            TT cq[R];
 #pragma unroll (R <= 8 ? R : 1)
-            for (int k = 0; k < R; ++k) cq[k] = p.C[((int64_t)q * R + k) * p.plane + base];
-            matvec_acc<CT, R>(t, p.M + (((int64_t)var * p.S + q) * p.S + s) * R * R, cq);
+            for (int k = 0; k < R; ++k) cq[k] = (TT)p.C[((int64_t)q * R + k) * p.plane + base];
+            matvec_acc<TT, R>(t, p.M + (((int64_t)var * p.S + q) * p.S + s) * R * R, cq);
         }
-        matvec_acc<CT, R>(t, p.P + ((int64_t)var * p.S + s) * R * R, tau);
+        matvec_acc<TT, R>(t, p.P + ((int64_t)var * p.S + s) * R * R, tau);
 #pragma unroll (R <= 8 ? R : 1)
         for (int k = 0; k < R; ++k) tau[k] = t[k];
     }
@@ -411,7 +413,7 @@ chain_local_kernel(const __grid_constant__ ChainParams<CT, R> p)
         for (int k = 0; k < R; ++k) p.SEGT[((int64_t)k * p.nseg + g) * p.nl + l] = tau[k];
     } else if (p.tail_out) {
 #pragma unroll (R <= 8 ? R : 1)
-        for (int k = 0; k < R; ++k) p.tail_out[(int64_t)k * p.nl + l] = tau[k];
+        for (int k = 0; k < R; ++k) p.tail_out[(int64_t)k * p.nl + l] = (CT)tau[k];
     }
 }
 
@@ -422,25 +424,26 @@ chain_top_kernel(const __grid_constant__ ChainParams<CT, R> p)
 {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= p.nl) return;
-    CT sigma[R];
+    typedef typename TabType<CT>::type TT;
+    TT sigma[R];
 #pragma unroll (R <= 8 ? R : 1)
-    for (int k = 0; k < R; ++k) sigma[k] = (CT)0;   // segment 0 already started from ext
+    for (int k = 0; k < R; ++k) sigma[k] = (TT)0;   // segment 0 already started from ext
     for (int g = 0; g < p.nseg; ++g) {
-        CT t[R];
+        TT t[R];
 #pragma unroll (R <= 8 ? R : 1)
         for (int k = 0; k < R; ++k) {
             const int64_t idx = ((int64_t)k * p.nseg + g) * p.nl + l;
             p.SEGC[idx] = sigma[k];
             t[k] = p.SEGT[idx];
         }
-        const CT* Pm = p.Pseg + (g == p.nseg - 1 ? R * R : 0);
-        matvec_acc<CT, R>(t, Pm, sigma);
+        const TT* Pm = p.Pseg + (g == p.nseg - 1 ? R * R : 0);
+        matvec_acc<TT, R>(t, Pm, sigma);
 #pragma unroll (R <= 8 ? R : 1)
         for (int k = 0; k < R; ++k) sigma[k] = t[k];
     }
     if (p.tail_out) {
 #pragma unroll (R <= 8 ? R : 1)
-        for (int k = 0; k < R; ++k) p.tail_out[(int64_t)k * p.nl + l] = sigma[k];
+        for (int k = 0; k < R; ++k) p.tail_out[(int64_t)k * p.nl + l] = (CT)sigma[k];
     }
 }
 
@@ -454,7 +457,8 @@ chain_fix_kernel(const __grid_constant__ ChainParams<CT, R> p)
     const int64_t l = gid % p.nl;
     const int g = (int)(gid / p.nl) + 1;
     const int s = p.s;
-    CT u[R];
+    typedef typename TabType<CT>::type TT;
+    TT u[R];
 #pragma unroll (R <= 8 ? R : 1)
     for (int k = 0; k < R; ++k) u[k] = p.SEGC[((int64_t)k * p.nseg + g) * p.nl + l];
     const int j_begin = g * p.seg;
@@ -466,12 +470,12 @@ chain_fix_kernel(const __grid_constant__ ChainParams<CT, R> p)
 #pragma unroll (R <= 8 ? R : 1)
         for (int k = 0; k < R; ++k) {
             const int64_t idx = ((int64_t)s * R + k) * p.plane + base;
-            p.C[idx] = p.C[idx] + u[k];
+            p.C[idx] = (CT)((TT)p.C[idx] + u[k]);
         }
-        CT t[R];
+        TT t[R];
 #pragma unroll (R <= 8 ? R : 1)
-        for (int k = 0; k < R; ++k) t[k] = (CT)0;
-        matvec_acc<CT, R>(t, p.P + ((int64_t)var * p.S + s) * R * R, u);
+        for (int k = 0; k < R; ++k) t[k] = (TT)0;
+        matvec_acc<TT, R>(t, p.P + ((int64_t)var * p.S + s) * R * R, u);
 #pragma unroll (R <= 8 ? R : 1)
         for (int k = 0; k < R; ++k) u[k] = t[k];
     }
@@ -489,9 +493,10 @@ template <typename CT, int R>
 __global__ void __launch_bounds__(TILE)
 cross_kernel(const __grid_constant__ CrossParams<CT, R> p)
 {
-    extern __shared__ unsigned char smem_raw[];
-    CT* A = reinterpret_cast<CT*>(smem_raw);            // [md][mx][R][R]
-    CT* red = A + p.md * p.mx * R * R;                  // [TILE/32] scratch
+    typedef typename TabType<CT>::type TT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TT* A = reinterpret_cast<TT*>(smem_raw);            // [md][mx][R][R]
+    TT* red = A + p.md * p.mx * R * R;                  // [TILE/32] scratch
 
     const int tid = threadIdx.x;
     int64_t b = blockIdx.x;
@@ -509,17 +514,17 @@ cross_kernel(const __grid_constant__ CrossParams<CT, R> p)
 
     // phase 1: A[s][q][k][kk] = sum_rows L[vd][s][k][row] * CX[q][kk][bx][row]
     for (int q = 0; q < p.mx; ++q) {
-        CT cx[R];
+        TT cx[R];
 #pragma unroll (R <= 8 ? R : 1)
         for (int kk = 0; kk < R; ++kk)
-            cx[kk] = (tid < rows_valid) ? p.CX[((int64_t)q * R * p.nbx + bx) * p.nlx + lx + kk * kstride_x] : (CT)0;
+            cx[kk] = (tid < rows_valid) ? (TT)p.CX[((int64_t)q * R * p.nbx + bx) * p.nlx + lx + kk * kstride_x] : (TT)0;
         for (int s = 0; s < p.md; ++s) {
 #pragma unroll (R <= 8 ? R : 1)
             for (int k = 0; k < R; ++k) {
-                const CT lv = (tid < rows_valid) ? p.L[(((int64_t)vd * p.md + s) * R + k) * TILE + tid] : (CT)0;
+                const TT lv = (tid < rows_valid) ? p.L[(((int64_t)vd * p.md + s) * R + k) * TILE + tid] : (TT)0;
 #pragma unroll (R <= 8 ? R : 1)
                 for (int kk = 0; kk < R; ++kk) {
-                    CT part = lv * cx[kk];
+                    TT part = lv * cx[kk];
                     // block reduction (2 warps)
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1)
@@ -527,7 +532,7 @@ cross_kernel(const __grid_constant__ CrossParams<CT, R> p)
                     if ((tid & 31) == 0) red[tid >> 5] = part;
                     __syncthreads();
                     if (tid == 0) {
-                        CT tot = (CT)0;
+                        TT tot = (TT)0;
                         for (int w = 0; w < TILE / 32; ++w) tot = tot + red[w];
                         A[((s * p.mx + q) * R + k) * R + kk] = tot;
                     }
@@ -541,19 +546,19 @@ cross_kernel(const __grid_constant__ CrossParams<CT, R> p)
     // phase 2: column tid
     if (tid < cols_valid) {
         for (int s = 0; s < p.md; ++s) {
-            CT d[R];
+            TT d[R];
 #pragma unroll (R <= 8 ? R : 1)
-            for (int k = 0; k < R; ++k) d[k] = (CT)0;
+            for (int k = 0; k < R; ++k) d[k] = (TT)0;
             for (int q = 0; q < p.mx; ++q) {
-                CT gq[R];
+                TT gq[R];
 #pragma unroll (R <= 8 ? R : 1)
                 for (int kk = 0; kk < R; ++kk)
                     gq[kk] = p.G[(((int64_t)vx * p.mx + q) * TILE + tid) * R + kk];
-                matvec_acc<CT, R>(d, A + (s * p.mx + q) * R * R, gq);
+                matvec_acc<TT, R>(d, A + (s * p.mx + q) * R * R, gq);
             }
             const int64_t idx0 = ((int64_t)s * R * p.nbd + bd) * p.nly + ly;
 #pragma unroll (R <= 8 ? R : 1)
-            for (int k = 0; k < R; ++k) p.TY[idx0 + k * kstride_d] = p.TY[idx0 + k * kstride_d] + d[k];
+            for (int k = 0; k < R; ++k) p.TY[idx0 + k * kstride_d] = (CT)((TT)p.TY[idx0 + k * kstride_d] + d[k]);
         }
     }
 }

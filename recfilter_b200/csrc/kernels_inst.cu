@@ -45,7 +45,7 @@ static cudaError_t launch_cross_T(const CrossParams<CT, R>& p, cudaStream_t st)
 {
     const int64_t nblocks = (int64_t)p.nbx * p.nbd * p.No;
     if (nblocks <= 0) return cudaSuccess;
-    const size_t smem = ((size_t)p.md * p.mx * R * R + TILE / 32) * sizeof(CT);
+    const size_t smem = ((size_t)p.md * p.mx * R * R + TILE / 32) * sizeof(typename TabType<CT>::type);
     cross_kernel<CT, R><<<(unsigned)nblocks, TILE, smem, st>>>(p);
     return cudaGetLastError();
 }

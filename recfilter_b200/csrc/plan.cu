@@ -268,7 +268,39 @@ static cudaError_t upload(DevBuf& b, const std::vector<HT>& src)
     return cudaMemcpy(b.p, tmp.data(), tmp.size() * sizeof(CT), cudaMemcpyHostToDevice);
 }
 
+// optional per-stage device timing (CUDA events on the launching stream)
+enum { ST_TAILS = 0, ST_CHAIN = 1, ST_CROSS = 2, ST_FINAL = 3, ST_CONVERT = 4, ST_COUNT = 5 };
+struct StageTimer {
+    bool on = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    double ms[ST_COUNT] = { 0, 0, 0, 0, 0 };
+    long   count[ST_COUNT] = { 0, 0, 0, 0, 0 };
+    cudaEvent_t begin(cudaStream_t st, int stage)
+    {
+        if (!on) return nullptr;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        pending.push_back({ stage, { a, b } });
+        return b;
+    }
+    void end(cudaStream_t st, cudaEvent_t b) { if (b) cudaEventRecord(b, st); }
+    void collect()
+    {
+        for (auto& e : pending) {
+            cudaEventSynchronize(e.second.second);
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e.second.first, e.second.second);
+            ms[e.first] += t; count[e.first] += 1;
+            cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+        }
+        pending.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < ST_COUNT; ++i) { ms[i] = 0; count[i] = 0; } }
+};
+
 struct PassBase {
+    StageTimer* timer = nullptr;
     virtual ~PassBase() {}
     virtual int run_tails(const void* in, void* out, cudaStream_t st) = 0;            // K1
     virtual int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st) = 0; // K2/K3 (ext: shard carries)
@@ -287,6 +319,7 @@ struct PassBase {
 template <typename CT, int R>
 struct Pass : PassBase {
     using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
+    using TT = typename TabType<CT>::type;     // device table / accumulation type (== HT)
     int dtype = RF_F32;
     PassParams<CT, R> pp;
     DimGeom gx, gd;
@@ -351,20 +384,20 @@ struct Pass : PassBase {
 
         if (pp.mx > 0) {
             build_dim_tables<HT>(tx_tab, sx, gx, R, clamp, segx, nsegx, fused);
-            CUDA_TRY((upload<HT, CT>(dPx, tx_tab.P)));
-            CUDA_TRY((upload<HT, CT>(dMx, tx_tab.M)));
-            CUDA_TRY((upload<HT, CT>(dPsegx, tx_tab.Pseg)));
-            if (fused) CUDA_TRY((upload<HT, CT>(dG, tx_tab.G)));
+            CUDA_TRY((upload<HT, TT>(dPx, tx_tab.P)));
+            CUDA_TRY((upload<HT, TT>(dMx, tx_tab.M)));
+            CUDA_TRY((upload<HT, TT>(dPsegx, tx_tab.Pseg)));
+            if (fused) CUDA_TRY((upload<HT, TT>(dG, tx_tab.G)));
             const size_t n = (size_t)pp.mx * R * gx.nb * pp.nlx * sizeof(CT);
             CUDA_TRY(TX.alloc(n)); CUDA_TRY(CX.alloc(n));
             CUDA_TRY(cudaMemset(CX.p, 0, n));
         }
         if (pp.md > 0) {
             build_dim_tables<HT>(td_tab, sd, gd, R, clamp, segd, nsegd, fused);
-            CUDA_TRY((upload<HT, CT>(dPd, td_tab.P)));
-            CUDA_TRY((upload<HT, CT>(dMd, td_tab.M)));
-            CUDA_TRY((upload<HT, CT>(dPsegd, td_tab.Pseg)));
-            if (fused) CUDA_TRY((upload<HT, CT>(dL, td_tab.L)));
+            CUDA_TRY((upload<HT, TT>(dPd, td_tab.P)));
+            CUDA_TRY((upload<HT, TT>(dMd, td_tab.M)));
+            CUDA_TRY((upload<HT, TT>(dPsegd, td_tab.Pseg)));
+            if (fused) CUDA_TRY((upload<HT, TT>(dL, td_tab.L)));
             const size_t n = (size_t)pp.md * R * gd.nb * pp.nly * sizeof(CT);
             CUDA_TRY(TY.alloc(n)); CUDA_TRY(CY.alloc(n));
             CUDA_TRY(cudaMemset(CY.p, 0, n));
@@ -376,7 +409,7 @@ struct Pass : PassBase {
         }
         {
             const size_t a = (size_t)R * nsegx * pp.nlx, b = (size_t)R * nsegd * pp.nly;
-            const size_t n = std::max(nsegx > 1 ? a : 0, nsegd > 1 ? b : 0) * sizeof(CT);
+            const size_t n = std::max(nsegx > 1 ? a : 0, nsegd > 1 ? b : 0) * sizeof(TT);
             CUDA_TRY(SEGT.alloc(n)); CUDA_TRY(SEGC.alloc(n));
         }
         pp.TX = (CT*)TX.p; pp.CX = (CT*)CX.p; pp.TY = (CT*)TY.p; pp.CY = (CT*)CY.p;
@@ -386,7 +419,9 @@ struct Pass : PassBase {
     int run_tails(const void* in, void* out, cudaStream_t st) override
     {
         if (!needs_carries()) return RF_OK;
+        cudaEvent_t ev = timer ? timer->begin(st, ST_TAILS) : nullptr;
         CUDA_TRY((Launch<CT, R>::tile(pp, in, out, 0, st)));
+        if (timer) timer->end(st, ev);
         return RF_OK;
     }
 
@@ -403,18 +438,20 @@ struct Pass : PassBase {
         else                        { cp.tile_stride = cp.nl; cp.line_stride = 1; }
         cp.plane = (int64_t)g.nb * cp.nl;
         cp.seg = xdim ? segx : segd; cp.nseg = xdim ? nsegx : nsegd;
-        cp.P = (const CT*)(xdim ? dPx.p : dPd.p);
-        cp.M = (const CT*)(xdim ? dMx.p : dMd.p);
+        cp.P = (const TT*)(xdim ? dPx.p : dPd.p);
+        cp.M = (const TT*)(xdim ? dMx.p : dMd.p);
         cp.S = g.nscans;
-        cp.SEGT = (CT*)SEGT.p; cp.SEGC = (CT*)SEGC.p;
+        cp.SEGT = (TT*)SEGT.p; cp.SEGC = (TT*)SEGC.p;
         const auto& scans = xdim ? sx : sd;
         for (int s = 0; s < g.nscans; ++s) {
             cp.s = s;
             cp.causal = scans[s].causal;
-            cp.Pseg = (const CT*)(xdim ? dPsegx.p : dPsegd.p) + (size_t)s * 2 * R * R;
+            cp.Pseg = (const TT*)(xdim ? dPsegx.p : dPsegd.p) + (size_t)s * 2 * R * R;
             cp.ext = (!xdim && ext_d) ? (const CT*)ext_d + (size_t)s * R * cp.nl : nullptr;
             cp.tail_out = (!xdim && tail_out_d) ? (CT*)tail_out_d + (size_t)s * R * cp.nl : nullptr;
+            cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
             CUDA_TRY((Launch<CT, R>::chain(cp, st)));
+            if (timer) timer->end(st, ev);
         }
         return RF_OK;
     }
@@ -431,8 +468,10 @@ struct Pass : PassBase {
             cr.mx = pp.mx; cr.md = pp.md;
             cr.CX = (const CT*)CX.p; cr.TY = (CT*)TY.p;
             cr.nlx = pp.nlx; cr.nly = pp.nly;
-            cr.G = (const CT*)dG.p; cr.L = (const CT*)dL.p;
+            cr.G = (const TT*)dG.p; cr.L = (const TT*)dL.p;
+            cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
             CUDA_TRY((Launch<CT, R>::cross(cr, st)));
+            if (timer) timer->end(st, ev);
         }
         if (d_needs()) { int rc = run_chain(false, ext_d, tail_out_d, st); if (rc) return rc; }
         return RF_OK;
@@ -440,7 +479,9 @@ struct Pass : PassBase {
 
     int run_final(const void* in, void* out, cudaStream_t st) override
     {
+        cudaEvent_t ev = timer ? timer->begin(st, ST_FINAL) : nullptr;
         CUDA_TRY((Launch<CT, R>::tile(pp, in, out, 1, st)));
+        if (timer) timer->end(st, ev);
         return RF_OK;
     }
 
@@ -466,25 +507,27 @@ struct Pass : PassBase {
 // small kernel: strip-level carry resolution (host of the multi-GPU layer)
 template <typename CT, int R>
 __global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restrict__ ext, int64_t nl, int S,
-                                     int nshards, int rank, const CT* __restrict__ Pdim3,
-                                     const CT* __restrict__ Mdim3, const int* __restrict__ causal)
+                                     int nshards, int rank, const typename TabType<CT>::type* __restrict__ Pdim3,
+                                     const typename TabType<CT>::type* __restrict__ Mdim3,
+                                     const int* __restrict__ causal)
 {
+    typedef typename TabType<CT>::type TT;
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nl) return;
     // c[q][g][k] kept in local memory (S and nshards are tiny)
-    CT c[8][8][R];
+    TT c[8][8][R];
     const int64_t shard_stride = (int64_t)S * R * nl;
     for (int s = 0; s < S; ++s) {
-        CT tau[R];
-        for (int k = 0; k < R; ++k) tau[k] = (CT)0;
+        TT tau[R];
+        for (int k = 0; k < R; ++k) tau[k] = (TT)0;
         for (int gg = 0; gg < nshards; ++gg) {
             const int g = causal[s] ? gg : nshards - 1 - gg;
             const int pos = (g == 0) ? 0 : (g == nshards - 1 ? 2 : 1);     // first / interior / last shard
-            const CT* Pdim = Pdim3 + (int64_t)pos * S * R * R;
-            const CT* Mdim = Mdim3 + (int64_t)pos * S * S * R * R;
+            const TT* Pdim = Pdim3 + (int64_t)pos * S * R * R;
+            const TT* Mdim = Mdim3 + (int64_t)pos * S * S * R * R;
             for (int k = 0; k < R; ++k) c[s][g][k] = tau[k];
-            CT t[R];
-            for (int k = 0; k < R; ++k) t[k] = tails[g * shard_stride + ((int64_t)s * R + k) * nl + l];
+            TT t[R];
+            for (int k = 0; k < R; ++k) t[k] = (TT)tails[g * shard_stride + ((int64_t)s * R + k) * nl + l];
             for (int q = 0; q < s; ++q)
                 for (int k = 0; k < R; ++k)
                     for (int kk = 0; kk < R; ++kk)
@@ -494,7 +537,7 @@ __global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restric
                     t[k] = t[k] + Pdim[((int64_t)s * R + k) * R + kk] * tau[kk];
             for (int k = 0; k < R; ++k) tau[k] = t[k];
         }
-        for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = c[s][rank][k];
+        for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = (CT)c[s][rank][k];
     }
 }
 
@@ -511,15 +554,15 @@ int Pass<CT, R>::shard_resolve(const void* gathered, int nshards, int rank, cuda
         M3.insert(M3.end(), Mt.begin(), Mt.end());
     }
     DevBuf dP, dM, dC;
-    CUDA_TRY((upload<HT, CT>(dP, P3)));
-    CUDA_TRY((upload<HT, CT>(dM, M3)));
+    CUDA_TRY((upload<HT, TT>(dP, P3)));
+    CUDA_TRY((upload<HT, TT>(dM, M3)));
     std::vector<int> causal(pp.md);
     for (int s = 0; s < pp.md; ++s) causal[s] = sd[s].causal;
     CUDA_TRY(dC.alloc(causal.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpyAsync(dC.p, causal.data(), causal.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     const int64_t nl = pp.nly;
     shard_resolve_kernel<CT, R><<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(
-        (const CT*)gathered, (CT*)dExt.p, nl, pp.md, nshards, rank, (const CT*)dP.p, (const CT*)dM.p,
+        (const CT*)gathered, (CT*)dExt.p, nl, pp.md, nshards, rank, (const TT*)dP.p, (const TT*)dM.p,
         (const int*)dC.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(st));   // temporaries are freed on return
@@ -558,6 +601,7 @@ struct rf_plan {
     int shard_pass = -1;
     std::string text;
     DevBuf stage;            // 32-bit staging for 8/16-bit integer filters
+    StageTimer timer;
 };
 
 static int widen_in(rf_plan* plan, const void* in_dev, cudaStream_t st)
@@ -762,7 +806,7 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
              desc->ndim, (long long)total, desc->dtype, desc->border ? "clamp" : "zero", desc->nscans,
              (int)plan->passes.size());
     plan->text = head;
-    for (auto& p : plan->passes) plan->text += p->describe();
+    for (auto& p : plan->passes) { plan->text += p->describe(); p->timer = &plan->timer; }
     *out = plan.release();
     return RF_OK;
 }
@@ -901,6 +945,22 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev, const void*
         if ((rc = p->run_final(src, out_dev, st))) return rc;
         src = out_dev;
     }
+    return RF_OK;
+}
+
+int rf_plan_stage_timing(rf_plan* plan, int enable)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    plan->timer.reset();
+    plan->timer.on = enable != 0;
+    return RF_OK;
+}
+
+int rf_plan_stage_times(rf_plan* plan, double* ms, long* counts, int n)
+{
+    if (!plan || !ms || !counts) return fail(RF_EINVAL, "null argument");
+    plan->timer.collect();
+    for (int i = 0; i < n && i < ST_COUNT; ++i) { ms[i] = plan->timer.ms[i]; counts[i] = plan->timer.count[i]; }
     return RF_OK;
 }
 

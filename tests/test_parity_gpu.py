@@ -139,7 +139,7 @@ def test_c3_fused_equals_cascaded(oracle):
     sc = [(0, True, G3), (0, False, G3), (1, True, G3), (1, False, G3)]
     f = run_gpu(a, sc, "clamp", fuse_dims=1)
     c = run_gpu(a, sc, "clamp", fuse_dims=0)
-    assert rel_err(f, c) < 2e-6
+    assert rel_err(f, c) < 8e-6      # two independent fp32 roundings of the same filter
 
 
 def test_c2_box_core_sat_and_order2(oracle):
