@@ -56,6 +56,10 @@ enum rf_dtype {
 /* image border (RecFilter::set_clamped_image_border, lib/recfilter.cpp:252-258) */
 enum rf_border { RF_BORDER_ZERO = 0, RF_BORDER_CLAMP = 1 };
 
+/* tile engines: the fused fast path (128x128 / 64x64 register tiles, orders <= 4, extents that are
+ * multiples of the tile) and the generic engine (any order <= 32, ragged extents, honoured split() tiles) */
+enum rf_engine { RF_ENGINE_AUTO = 0, RF_ENGINE_GENERIC = 1, RF_ENGINE_FUSED = 2 };
+
 /* error codes */
 enum rf_status {
     RF_OK            =  0,
@@ -85,7 +89,8 @@ typedef struct rf_options {
     int32_t open_lo;            /* sharding: the low / high face of shard_dim is an interior */
     int32_t open_hi;            /*   cut, carries come from the neighbour shard */
     int32_t shard_dim;          /* dimension that is sharded across devices, -1: none */
-    int32_t reserved[8];
+    int32_t engine;             /* rf_engine: which tile engine a pass may use (0: planner decides) */
+    int32_t reserved[7];
 } rf_options;
 
 /* filter descriptor */

@@ -26,6 +26,7 @@ DTYPES = {
     "f32": (0, np.float32), "i32": (2, np.int32), "u32": (3, np.uint32),
     "i16": (4, np.int16), "u16": (5, np.uint16), "i8": (6, np.int8), "u8": (7, np.uint8),
 }
+ENGINES = {"auto": 0, "generic": 1, "fused": 2}
 _NP_TO_NAME = {np.dtype(v[1]): k for k, v in DTYPES.items()}
 
 
@@ -41,7 +42,7 @@ class _Scan(C.Structure):
 class _Options(C.Structure):
     _fields_ = [("tile", C.c_int32 * RF_MAX_DIMS), ("honor_tile", C.c_int32), ("fuse_dims", C.c_int32),
                 ("open_lo", C.c_int32), ("open_hi", C.c_int32), ("shard_dim", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("engine", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class _Desc(C.Structure):
@@ -145,7 +146,7 @@ class Plan:
 
     def __init__(self, extents: Sequence[int], dtype, scans: Iterable[Scan], border: str = "zero", *,
                  tile: Sequence[int] | int | None = None, honor_tile: bool = False, fuse_dims: int = -1,
-                 shard_dim: int = -1, open_lo: bool = False, open_hi: bool = False):
+                 shard_dim: int = -1, open_lo: bool = False, open_hi: bool = False, engine: str = "auto"):
         self._h = C.c_void_p()
         L = lib()
         self.extents = tuple(int(e) for e in extents)
@@ -184,6 +185,9 @@ class Plan:
         d.opt.honor_tile = 1 if honor_tile else 0
         d.opt.fuse_dims = int(fuse_dims)
         d.opt.shard_dim = int(shard_dim)
+        if engine not in ENGINES:
+            raise RecFilterError(f"engine must be one of {sorted(ENGINES)}")
+        d.opt.engine = ENGINES[engine]
         d.opt.open_lo = 1 if open_lo else 0
         d.opt.open_hi = 1 if open_hi else 0
         self.size = int(np.prod(self.extents)) if self.extents else 0

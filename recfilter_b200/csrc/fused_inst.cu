@@ -1,0 +1,95 @@
+/*
+ * fused_inst.cu -- explicit instantiation of the fused fast path for one padded filter
+ * order (compile with -DRFB_R=<1|2|3|4>); one object per order so the orders build in
+ * parallel.
+ */
+#include <type_traits>
+#include "fused.cuh"
+
+#ifndef RFB_R
+#error "compile with -DRFB_R=<order>"
+#endif
+
+namespace rfb {
+
+template <typename CT, int R, int TS>
+static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void* in, void* out, int mode,
+                                        cudaStream_t st)
+{
+    const int64_t nblocks = (int64_t)p.nbx * p.nbd * p.No;
+    if (nblocks <= 0) return cudaSuccess;
+    if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const size_t smem = fused_tile_smem_bytes(TS);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e;
+        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const bool is_float = std::is_same<CT, float>::value;
+    CUtensorMap tm_in, tm_out;
+    cudaError_t e = make_tile_map(&tm_in, in, p.Nx, p.No * p.Nd, TS, is_float);
+    if (e != cudaSuccess) return e;
+    if (mode == FMODE_P1) {
+        fused_tile_kernel<CT, R, TS, FMODE_P1><<<(unsigned)nblocks, TS, smem, st>>>(p, tm_in, tm_in);
+    } else {
+        e = make_tile_map(&tm_out, out, p.Nx, p.No * p.Nd, TS, is_float);
+        if (e != cudaSuccess) return e;
+        fused_tile_kernel<CT, R, TS, FMODE_P2><<<(unsigned)nblocks, TS, smem, st>>>(p, tm_in, tm_out);
+    }
+    return cudaGetLastError();
+}
+
+template <typename CT, int R>
+static cudaError_t launch_fused_tile_T(const FusedParams<CT, R>& p, const void* in, void* out, int mode, int ts,
+                                       cudaStream_t st)
+{
+    if (ts == 128) return launch_fused_tile_TS<CT, R, 128>(p, in, out, mode, st);
+    if (ts == 64)  return launch_fused_tile_TS<CT, R, 64>(p, in, out, mode, st);
+    return cudaErrorInvalidValue;
+}
+
+template <typename CT, int R>
+static cudaError_t launch_fchain_T(const FChainParams<CT, R>& p, cudaStream_t st)
+{
+    if (p.nl <= 0 || p.nb <= 0) return cudaSuccess;
+    if (p.nseg < 1 || p.nseg > 16) return cudaErrorInvalidConfiguration;
+    const dim3 block(32, p.nseg);
+    const unsigned grid = (unsigned)((p.nl + 31) / 32);
+    const size_t smem = (size_t)p.nseg * R * 32 * sizeof(typename TabType<CT>::type);
+    fchain_kernel<CT, R><<<grid, block, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename CT, int R>
+static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& p, int ts, cudaStream_t st)
+{
+    const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
+    if (ntiles <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((ntiles + 3) / 4);
+    if (ts == 128)     fcross_kernel<CT, R, 128><<<grid, 128, 0, st>>>(p);
+    else if (ts == 64) fcross_kernel<CT, R, 64><<<grid, 128, 0, st>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+#define RFB_CAT_(a, b) a##b
+#define RFB_CAT(a, b) RFB_CAT_(a, b)
+
+cudaError_t RFB_CAT(launch_fused_tile_f, RFB_R)(const FusedParams<float, RFB_R>& p, const void* in, void* out, int mode, int ts, cudaStream_t st)
+{ return launch_fused_tile_T<float, RFB_R>(p, in, out, mode, ts, st); }
+cudaError_t RFB_CAT(launch_fused_tile_u, RFB_R)(const FusedParams<uint32_t, RFB_R>& p, const void* in, void* out, int mode, int ts, cudaStream_t st)
+{ return launch_fused_tile_T<uint32_t, RFB_R>(p, in, out, mode, ts, st); }
+cudaError_t RFB_CAT(launch_fchain_f, RFB_R)(const FChainParams<float, RFB_R>& p, cudaStream_t st)
+{ return launch_fchain_T<float, RFB_R>(p, st); }
+cudaError_t RFB_CAT(launch_fchain_u, RFB_R)(const FChainParams<uint32_t, RFB_R>& p, cudaStream_t st)
+{ return launch_fchain_T<uint32_t, RFB_R>(p, st); }
+cudaError_t RFB_CAT(launch_fcross_f, RFB_R)(const FCrossParams<float, RFB_R>& p, int ts, cudaStream_t st)
+{ return launch_fcross_T<float, RFB_R>(p, ts, st); }
+cudaError_t RFB_CAT(launch_fcross_u, RFB_R)(const FCrossParams<uint32_t, RFB_R>& p, int ts, cudaStream_t st)
+{ return launch_fcross_T<uint32_t, RFB_R>(p, ts, st); }
+
+} // namespace rfb

@@ -1,0 +1,73 @@
+#pragma once
+/*
+ * fused_params.h -- kernel parameter blocks of the fused fast path (shared by the launch
+ * planner in plan.cu and the kernels in fused.cuh).  See fused.cuh for the algorithm.
+ */
+#include <stdint.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "engine.h"
+
+namespace rfb {
+
+constexpr int FMAX_SCANS = 4;     // scans per dimension handled by the fused path
+constexpr int FCHAIN_L   = 8;     // tiles per thread in the carry chain
+
+enum { FMODE_P1 = 0, FMODE_P2 = 1 };
+
+template <typename CT, int R>
+struct FusedScanTab {
+    int causal[FMAX_SCANS];
+    CT  a[FMAX_SCANS][R + 1];     // a[s][0]: clamp-history factor (1/b0); a[s][1..R]: feedback
+};
+
+template <typename CT, int R>
+struct FusedParams {
+    int64_t Nx, Nd, No;
+    int nbx, nbd;
+    int clamp;
+    int x_lo_closed, x_hi_closed, d_lo_closed, d_hi_closed;
+    int mx, md;
+    int reverse;                  // walk the tiles backwards (pass 2: most recently read first)
+    CT  gain;                     // product of the feed-forward coefficients
+    CT* TX; const CT* CX;         // x tails (out, P1) / carries (in, P2)   [s][k][bx][lx]
+    CT* TY; const CT* CY;         // d tails / carries                     [s][k][bd][ly]
+    int64_t nlx, nly;
+    FusedScanTab<CT, R> sx, sd;
+};
+
+template <typename CT, int R>
+struct FChainParams {
+    typedef typename TabType<CT>::type TT;
+    const CT* T; CT* C;           // [s][k][j][l]
+    int64_t nl; int nb; int S;
+    int nseg;                     // segments of FCHAIN_L tiles (threadIdx.y)
+    int causal[FMAX_SCANS];
+    const TT* P;                  // [V][S][R][R]
+    const TT* M;                  // [V][S][S][R][R]   (q -> s)
+    const TT* Pseg;               // [S][nseg][R][R]   product over a segment, segments in scan order
+    const CT* ext;                // [s][k][l] carry entering the first tile (shard cut) or null
+    CT* tail_out;                 // [s][k][l] completed tail leaving the last tile or null
+    // cross-dimension residual (x chain of a fused pass), null otherwise
+    const TT* A;                  // [o][bd][bx][sd][sx][R][R]
+    const TT* G;                  // [V][Sd][TS][R]
+    int Sd, TS, nbd; int64_t Nd;
+};
+
+template <typename CT, int R>
+struct FCrossParams {
+    typedef typename TabType<CT>::type TT;
+    const CT* CY;                 // [sd][k][bd][ly]
+    const TT* L;                  // [V][Sx][R][TS]
+    TT* A;                        // [o][bd][bx][sd][sx][R][R]
+    int64_t Nx, No; int nbx, nbd; int Sx, Sd; int64_t nly;
+};
+
+// dynamic shared memory of one tile CTA: the swizzled boxes, alignment slack, the mbarrier
+inline size_t fused_tile_smem_bytes(int ts) { return (size_t)ts * ts * 4 + 1024 + 16; }
+
+// TMA descriptor of a dense [rows][Nx] matrix of 4-byte elements, box = 32 columns x ts rows, 128 B swizzle
+// (defined once in plan.cu; resolves cuTensorMapEncodeTiled through the runtime, no libcuda link)
+cudaError_t make_tile_map(CUtensorMap* map, const void* base, int64_t Nx, int64_t rows, int ts, bool is_float);
+
+} // namespace rfb

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include "engine.h"
+#include "fused_params.h"
 
 namespace rfb {
 
@@ -35,6 +36,30 @@ namespace rfb {
     cudaError_t launch_cross_f##RR(const CrossParams<float, RR>&, cudaStream_t);                    \
     cudaError_t launch_cross_u##RR(const CrossParams<uint32_t, RR>&, cudaStream_t);
 RFB_FOR_EACH_R(DECLARE_LAUNCHERS)
+
+#define RFB_FOR_EACH_FR(X) X(1) X(2) X(3) X(4)
+#define DECLARE_FLAUNCHERS(RR)                                                                      \
+    cudaError_t launch_fused_tile_f##RR(const FusedParams<float, RR>&, const void*, void*, int, int, cudaStream_t);    \
+    cudaError_t launch_fused_tile_u##RR(const FusedParams<uint32_t, RR>&, const void*, void*, int, int, cudaStream_t); \
+    cudaError_t launch_fchain_f##RR(const FChainParams<float, RR>&, cudaStream_t);                  \
+    cudaError_t launch_fchain_u##RR(const FChainParams<uint32_t, RR>&, cudaStream_t);               \
+    cudaError_t launch_fcross_f##RR(const FCrossParams<float, RR>&, int, cudaStream_t);             \
+    cudaError_t launch_fcross_u##RR(const FCrossParams<uint32_t, RR>&, int, cudaStream_t);
+RFB_FOR_EACH_FR(DECLARE_FLAUNCHERS)
+
+template <typename CT, int R> struct FLaunch;
+#define DEFINE_FLAUNCH_TRAITS(RR)                                                                   \
+    template <> struct FLaunch<float, RR> {                                                         \
+        static cudaError_t tile(const FusedParams<float, RR>& p, const void* i, void* o, int m, int ts, cudaStream_t s) { return launch_fused_tile_f##RR(p, i, o, m, ts, s); } \
+        static cudaError_t chain(const FChainParams<float, RR>& p, cudaStream_t s) { return launch_fchain_f##RR(p, s); } \
+        static cudaError_t cross(const FCrossParams<float, RR>& p, int ts, cudaStream_t s) { return launch_fcross_f##RR(p, ts, s); } \
+    };                                                                                              \
+    template <> struct FLaunch<uint32_t, RR> {                                                      \
+        static cudaError_t tile(const FusedParams<uint32_t, RR>& p, const void* i, void* o, int m, int ts, cudaStream_t s) { return launch_fused_tile_u##RR(p, i, o, m, ts, s); } \
+        static cudaError_t chain(const FChainParams<uint32_t, RR>& p, cudaStream_t s) { return launch_fchain_u##RR(p, s); } \
+        static cudaError_t cross(const FCrossParams<uint32_t, RR>& p, int ts, cudaStream_t s) { return launch_fcross_u##RR(p, ts, s); } \
+    };
+RFB_FOR_EACH_FR(DEFINE_FLAUNCH_TRAITS)
 
 template <typename CT, int R> struct Launch;
 #define DEFINE_LAUNCH_TRAITS(RR)                                                                    \
@@ -68,20 +93,54 @@ static int fail(int code, const char* fmt, ...)
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// TMA descriptors (fused path).  cuTensorMapEncodeTiled is a driver entry point; it is resolved
+// through the runtime so that the library links against cudart only.
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+cudaError_t make_tile_map(CUtensorMap* map, const void* base, int64_t Nx, int64_t rows, int ts, bool is_float)
+{
+    static encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+        encode = (encode_tiled_fn)fn;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return cudaErrorMisalignedAddress;
+    const cuuint64_t dims[2]    = { (cuuint64_t)Nx, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)Nx * 4 };
+    const cuuint32_t box[2]     = { 32u, (cuuint32_t)ts };
+    const cuuint32_t estr[2]    = { 1u, 1u };
+    const CUresult r = encode(map, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                              const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side scan simulation (semantics identical to scan_regs in kernels.cu)
 //   HT = double for float filters, uint32_t (wrapping ring) for integer filters
 // ---------------------------------------------------------------------------------------------
+//   scaled: the unit-feed-forward form of the fused path (scan_line in fused.cuh); c[0] is then
+//   the clamp-history factor 1/b0 instead of b0
 template <typename HT>
 static void sim_scan(std::vector<HT>& v, int len, std::vector<HT>& h, const std::vector<HT>& c,
-                     bool causal, bool clampb)
+                     bool causal, bool clampb, bool scaled = false)
 {
     const int R = (int)h.size();
     for (int p = 0; p < len; ++p) {
         const int i = causal ? p : len - 1 - p;
         const HT x = v[i];
-        HT acc = c[0] * x;
+        HT acc = scaled ? x : c[0] * x;
         if (p == 0 && clampb) {
-            for (int k = 1; k <= R; ++k) acc = acc + c[k] * x;
+            const HT tap = scaled ? x * c[0] : x;
+            for (int k = 1; k <= R; ++k) acc = acc + c[k] * tap;
             for (int k = 0; k < R; ++k) h[k] = acc;
         } else {
             for (int k = 1; k <= R; ++k) acc = acc + c[k] * h[k - 1];
@@ -102,11 +161,16 @@ template <typename HT> static HT cvt_coeff(float c);
 template <> double   cvt_coeff<double>(float c)   { return (double)c; }
 template <> uint32_t cvt_coeff<uint32_t>(float c) { return (uint32_t)(int64_t)c; }   // Cast::make(type, coeff), wraps
 
+template <typename HT> static HT clamp_factor(float b0);
+template <> double   clamp_factor<double>(float b0)   { return (double)(float)(1.0 / (double)b0); }   // as the device holds it
+template <> uint32_t clamp_factor<uint32_t>(float)    { return 1u; }                                  // b0 == 1 required
+
 template <typename HT>
-static std::vector<HT> coeff_vec(const HostScan& s, int R)
+static std::vector<HT> coeff_vec(const HostScan& s, int R, bool scaled = false)
 {
     std::vector<HT> c(R + 1, (HT)0);
     for (int k = 0; k <= s.order; ++k) c[k] = cvt_coeff<HT>(s.coeff[k]);
+    if (scaled) c[0] = clamp_factor<HT>(s.coeff[0]);
     return c;
 }
 
@@ -147,7 +211,7 @@ static void matmul_rr(std::vector<HT>& out, const HT* a, const HT* b, int R)   /
 
 template <typename HT>
 static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& scans, const DimGeom& g,
-                             int R, bool clamp, int seg, int nseg, bool want_GL)
+                             int R, bool clamp, int seg, int nseg, bool want_GL, bool scaled = false, int TILE = rfb::TILE)
 {
     const int S = (int)scans.size();
     tb.S = S; tb.R = R;
@@ -158,7 +222,7 @@ static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& sca
         tb.L.assign((size_t)V_COUNT * S * R * TILE, (HT)0);
     }
     std::vector<std::vector<HT>> coef(S);
-    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R);
+    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R, scaled);
 
     auto closed = [&](const VariantGeom& vg, int s) { return scans[s].causal ? vg.lo : vg.hi; };
 
@@ -171,12 +235,12 @@ static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& sca
             for (int kk = 0; kk < R; ++kk) {
                 std::vector<HT> v(len, (HT)0), h(R, (HT)0);
                 h[kk] = (HT)1;
-                sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false);
+                sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false, scaled);
                 for (int k = 0; k < R; ++k) tb.P[(((size_t)var * S + q) * R + k) * R + kk] = h[k];
                 // propagate the response through the later scans of this dimension
                 for (int s = q + 1; s < S; ++s) {
                     std::vector<HT> hs(R, (HT)0);
-                    sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(vg, s));
+                    sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(vg, s), scaled);
                     for (int k = 0; k < R; ++k)
                         tb.M[((((size_t)var * S + q) * S + s) * R + k) * R + kk] = hs[k];
                 }
@@ -190,7 +254,7 @@ static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& sca
                 v[i] = (HT)1;
                 for (int s = 0; s < S; ++s) {
                     std::vector<HT> hs(R, (HT)0);
-                    sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(vg, s));
+                    sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(vg, s), scaled);
                     for (int k = 0; k < R; ++k) tb.L[(((size_t)var * S + s) * R + k) * TILE + i] = hs[k];
                 }
             }
@@ -199,7 +263,7 @@ static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& sca
 
     // segment products for the two-level chain
     tb.Pseg.assign((size_t)S * 2 * R * R, (HT)0);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < S && seg > 0; ++s) {
         const HT* Pint = &tb.P[(((size_t)V_INTERIOR * S + s)) * R * R];
         std::vector<HT> acc((size_t)R * R, (HT)0), tmp;
         for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
@@ -223,13 +287,13 @@ static void build_dim_tables(DimTables<HT>& tb, const std::vector<HostScan>& sca
 // incoming carries.  Pdim [S][R][R], Mdim [S][S][R][R].
 template <typename HT>
 static void build_whole_dim(std::vector<HT>& Pdim, std::vector<HT>& Mdim, const std::vector<HostScan>& scans,
-                            int64_t n, int lo_closed, int hi_closed, int R, bool clamp)
+                            int64_t n, int lo_closed, int hi_closed, int R, bool clamp, bool scaled = false)
 {
     const int S = (int)scans.size();
     Pdim.assign((size_t)S * R * R, (HT)0);
     Mdim.assign((size_t)S * S * R * R, (HT)0);
     std::vector<std::vector<HT>> coef(S);
-    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R);
+    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R, scaled);
     const int len = (int)n;
     auto dclosed = [&](int s) { return scans[s].causal ? lo_closed : hi_closed; };
     for (int q = 0; q < S; ++q) {
@@ -237,11 +301,11 @@ static void build_whole_dim(std::vector<HT>& Pdim, std::vector<HT>& Mdim, const 
         for (int kk = 0; kk < R; ++kk) {
             std::vector<HT> v(len, (HT)0), h(R, (HT)0);
             h[kk] = (HT)1;
-            sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false);
+            sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false, scaled);
             for (int k = 0; k < R; ++k) Pdim[((size_t)q * R + k) * R + kk] = h[k];
             for (int s = q + 1; s < S; ++s) {
                 std::vector<HT> hs(R, (HT)0);
-                sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && dclosed(s));
+                sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && dclosed(s), scaled);
                 for (int k = 0; k < R; ++k) Mdim[(((size_t)q * S + s) * R + k) * R + kk] = hs[k];
             }
         }
@@ -299,11 +363,89 @@ struct StageTimer {
     void reset() { collect(); for (int i = 0; i < ST_COUNT; ++i) { ms[i] = 0; count[i] = 0; } }
 };
 
+// small kernel: strip-level carry resolution (host of the multi-GPU layer, SURVEY 8e)
+template <typename CT, int R>
+__global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restrict__ ext, int64_t nl, int S,
+                                     int nshards, int rank, const typename TabType<CT>::type* __restrict__ Pdim3,
+                                     const typename TabType<CT>::type* __restrict__ Mdim3,
+                                     const int* __restrict__ causal)
+{
+    typedef typename TabType<CT>::type TT;
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nl) return;
+    // c[q][g][k] kept in local memory (S and nshards are tiny)
+    TT c[8][8][R];
+    const int64_t shard_stride = (int64_t)S * R * nl;
+    for (int s = 0; s < S; ++s) {
+        TT tau[R];
+        for (int k = 0; k < R; ++k) tau[k] = (TT)0;
+        for (int gg = 0; gg < nshards; ++gg) {
+            const int g = causal[s] ? gg : nshards - 1 - gg;
+            const int pos = (g == 0) ? 0 : (g == nshards - 1 ? 2 : 1);     // first / interior / last shard
+            const TT* Pdim = Pdim3 + (int64_t)pos * S * R * R;
+            const TT* Mdim = Mdim3 + (int64_t)pos * S * S * R * R;
+            for (int k = 0; k < R; ++k) c[s][g][k] = tau[k];
+            TT t[R];
+            for (int k = 0; k < R; ++k) t[k] = (TT)tails[g * shard_stride + ((int64_t)s * R + k) * nl + l];
+            for (int q = 0; q < s; ++q)
+                for (int k = 0; k < R; ++k)
+                    for (int kk = 0; kk < R; ++kk)
+                        t[k] = t[k] + Mdim[(((int64_t)q * S + s) * R + k) * R + kk] * c[q][g][kk];
+            for (int k = 0; k < R; ++k)
+                for (int kk = 0; kk < R; ++kk)
+                    t[k] = t[k] + Pdim[((int64_t)s * R + k) * R + kk] * tau[kk];
+            for (int k = 0; k < R; ++k) tau[k] = t[k];
+        }
+        for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = (CT)c[s][rank][k];
+    }
+}
+
+// Every shard holds the zero-history tails of all shards: tails[g][s][k][ly].  Resolve the carries
+// entering this shard with the whole-dimension matrices of a first / interior / last shard
+// (built once, at plan creation).
+template <typename CT, int R>
+struct ShardResolver {
+    using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
+    using TT = typename TabType<CT>::type;
+    DevBuf dP, dM, dC;
+    int md = 0;
+    bool ready = false;
+    int init(const std::vector<HostScan>& sd, int64_t n, bool clamp, bool scaled)
+    {
+        md = (int)sd.size();
+        if (md > 8) return fail(RF_EUNSUPPORTED, "sharded execution supports <= 8 scans along the sharded dimension");
+        std::vector<HT> P3, M3, Pt, Mt;
+        for (int pos = 0; pos < 3; ++pos) {
+            build_whole_dim<HT>(Pt, Mt, sd, n, pos == 0 ? 1 : 0, pos == 2 ? 1 : 0, R, clamp, scaled);
+            P3.insert(P3.end(), Pt.begin(), Pt.end());
+            M3.insert(M3.end(), Mt.begin(), Mt.end());
+        }
+        CUDA_TRY((upload<HT, TT>(dP, P3)));
+        CUDA_TRY((upload<HT, TT>(dM, M3)));
+        std::vector<int> causal(md);
+        for (int s = 0; s < md; ++s) causal[s] = sd[s].causal;
+        CUDA_TRY(dC.alloc(causal.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(dC.p, causal.data(), causal.size() * sizeof(int), cudaMemcpyHostToDevice));
+        ready = true;
+        return RF_OK;
+    }
+    int run(int64_t nl, const void* gathered, int nshards, int rank, void* ext_out, cudaStream_t st)
+    {
+        if (!ready) return fail(RF_EINVAL, "plan was not created for sharded execution");
+        if (nshards > 8) return fail(RF_EUNSUPPORTED, "sharded execution supports <= 8 shards");
+        shard_resolve_kernel<CT, R><<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(
+            (const CT*)gathered, (CT*)ext_out, nl, md, nshards, rank, (const TT*)dP.p, (const TT*)dM.p,
+            (const int*)dC.p);
+        CUDA_TRY(cudaGetLastError());
+        return RF_OK;
+    }
+};
+
 struct PassBase {
     StageTimer* timer = nullptr;
     virtual ~PassBase() {}
     virtual int run_tails(const void* in, void* out, cudaStream_t st) = 0;            // K1
-    virtual int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st) = 0; // K2/K3 (ext: shard carries)
+    virtual int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st, int stage = 0) = 0; // K2/K3 (ext: shard carries; stage 1/2 of a sharded run)
     virtual int run_final(const void* in, void* out, cudaStream_t st) = 0;            // K4
     virtual bool needs_carries() const = 0;
     virtual int launches() const = 0;
@@ -330,6 +472,7 @@ struct Pass : PassBase {
     DevBuf dPx, dMx, dPsegx, dPd, dMd, dPsegd, dG, dL;
     DevBuf dExt, dTailOut;           // shard carries in / tails out  [s][k][ly]
     DimTables<HT> tx_tab, td_tab;
+    std::unique_ptr<ShardResolver<CT, R>> resolver;
 
     bool x_needs() const { return gx.nscans > 0 && gx.nb > 1; }
     bool d_needs() const { return gd.nscans > 0 && (gd.nb > 1 || !gd.lo_closed || !gd.hi_closed); }
@@ -405,6 +548,9 @@ struct Pass : PassBase {
                 const size_t m = (size_t)pp.md * R * pp.nly * sizeof(CT);
                 CUDA_TRY(dExt.alloc(m)); CUDA_TRY(dTailOut.alloc(m));
                 CUDA_TRY(cudaMemset(dExt.p, 0, m));
+                resolver.reset(new ShardResolver<CT, R>());
+                int rc = resolver->init(sd, gd.n, clamp, false);
+                if (rc) return rc;
             }
         }
         {
@@ -456,9 +602,12 @@ struct Pass : PassBase {
         return RF_OK;
     }
 
-    int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st) override
+    int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st, int stage) override
     {
         if (!needs_carries()) return RF_OK;
+        // stage 2 of a sharded run: the x carries and the cross residual (added to TY in place) are
+        // already complete from stage 1; only the d chain is redone with the incoming shard carries
+        if (stage == 2) return d_needs() ? run_chain(false, ext_d, tail_out_d, st) : RF_OK;
         if (x_needs()) { int rc = run_chain(true, nullptr, nullptr, st); if (rc) return rc; }
         if (x_needs() && d_needs() && fused) {
             CrossParams<CT, R> cr;
@@ -489,7 +638,11 @@ struct Pass : PassBase {
 
     // Every shard holds the zero-history tails of all shards: tails[g][s][k][ly].
     // Resolve this shard's incoming carries with the whole-dimension matrices.
-    int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) override;
+    int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) override
+    {
+        if (!d_open()) return RF_OK;
+        return resolver->run(pp.nly, gathered, nshards, rank, dExt.p, st);
+    }
 
     std::string describe() const override
     {
@@ -504,70 +657,209 @@ struct Pass : PassBase {
     }
 };
 
-// small kernel: strip-level carry resolution (host of the multi-GPU layer, SURVEY 8e)
+// ---------------------------------------------------------------------------------------------
+// the fused fast path (kernels in fused.cuh): full TS x TS tiles, unit-feed-forward scans,
+// d scans before x scans, one carry-chain launch per dimension
+// ---------------------------------------------------------------------------------------------
 template <typename CT, int R>
-__global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restrict__ ext, int64_t nl, int S,
-                                     int nshards, int rank, const typename TabType<CT>::type* __restrict__ Pdim3,
-                                     const typename TabType<CT>::type* __restrict__ Mdim3,
-                                     const int* __restrict__ causal)
-{
-    typedef typename TabType<CT>::type TT;
-    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nl) return;
-    // c[q][g][k] kept in local memory (S and nshards are tiny)
-    TT c[8][8][R];
-    const int64_t shard_stride = (int64_t)S * R * nl;
-    for (int s = 0; s < S; ++s) {
-        TT tau[R];
-        for (int k = 0; k < R; ++k) tau[k] = (TT)0;
-        for (int gg = 0; gg < nshards; ++gg) {
-            const int g = causal[s] ? gg : nshards - 1 - gg;
-            const int pos = (g == 0) ? 0 : (g == nshards - 1 ? 2 : 1);     // first / interior / last shard
-            const TT* Pdim = Pdim3 + (int64_t)pos * S * R * R;
-            const TT* Mdim = Mdim3 + (int64_t)pos * S * S * R * R;
-            for (int k = 0; k < R; ++k) c[s][g][k] = tau[k];
-            TT t[R];
-            for (int k = 0; k < R; ++k) t[k] = (TT)tails[g * shard_stride + ((int64_t)s * R + k) * nl + l];
-            for (int q = 0; q < s; ++q)
-                for (int k = 0; k < R; ++k)
-                    for (int kk = 0; kk < R; ++kk)
-                        t[k] = t[k] + Mdim[(((int64_t)q * S + s) * R + k) * R + kk] * c[q][g][kk];
-            for (int k = 0; k < R; ++k)
-                for (int kk = 0; kk < R; ++kk)
-                    t[k] = t[k] + Pdim[((int64_t)s * R + k) * R + kk] * tau[kk];
-            for (int k = 0; k < R; ++k) tau[k] = t[k];
-        }
-        for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = (CT)c[s][rank][k];
-    }
-}
+struct FusedPass : PassBase {
+    using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
+    using TT = typename TabType<CT>::type;
+    FusedParams<CT, R> fp;
+    int ts = 128;
+    DimGeom gx, gd;
+    std::vector<HostScan> sx, sd;
+    bool clamp = false;
+    int nsegx = 1, nsegd = 1;
+    DevBuf TX, CX, TY, CY, dA;
+    DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
+    DevBuf dExt, dTailOut;
+    DimTables<HT> tx_tab, td_tab;
+    std::unique_ptr<ShardResolver<CT, R>> resolver;
 
-template <typename CT, int R>
-int Pass<CT, R>::shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st)
-{
-    if (!d_open()) return RF_OK;
-    if (nshards > 8 || pp.md > 8) return fail(RF_EUNSUPPORTED, "shard_resolve supports <= 8 shards and <= 8 scans");
-    // whole-shard matrices for a first / interior / last shard (the clamp rule differs)
-    std::vector<HT> P3, M3, Pt, Mt;
-    for (int pos = 0; pos < 3; ++pos) {
-        build_whole_dim<HT>(Pt, Mt, sd, gd.n, pos == 0 ? 1 : 0, pos == 2 ? 1 : 0, R, pp.clamp != 0);
-        P3.insert(P3.end(), Pt.begin(), Pt.end());
-        M3.insert(M3.end(), Mt.begin(), Mt.end());
+    bool x_needs() const { return gx.nscans > 0 && gx.nb > 1; }
+    bool d_needs() const { return gd.nscans > 0 && (gd.nb > 1 || !gd.lo_closed || !gd.hi_closed); }
+    bool needs_carries() const override { return x_needs() || d_needs(); }
+    bool d_open() const override { return gd.nscans > 0 && (!gd.lo_closed || !gd.hi_closed); }
+    const void* ext_buffer() const override { return dExt.p; }
+    bool cross_needed() const { return x_needs() && d_needs(); }
+
+    size_t workspace() const override
+    {
+        return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dA.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
+               dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes;
     }
-    DevBuf dP, dM, dC;
-    CUDA_TRY((upload<HT, TT>(dP, P3)));
-    CUDA_TRY((upload<HT, TT>(dM, M3)));
-    std::vector<int> causal(pp.md);
-    for (int s = 0; s < pp.md; ++s) causal[s] = sd[s].causal;
-    CUDA_TRY(dC.alloc(causal.size() * sizeof(int)));
-    CUDA_TRY(cudaMemcpyAsync(dC.p, causal.data(), causal.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    const int64_t nl = pp.nly;
-    shard_resolve_kernel<CT, R><<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(
-        (const CT*)gathered, (CT*)dExt.p, nl, pp.md, nshards, rank, (const TT*)dP.p, (const TT*)dM.p,
-        (const int*)dC.p);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(st));   // temporaries are freed on return
-    return RF_OK;
-}
+    int launches() const override
+    {
+        int n = 1;
+        if (needs_carries()) n += 1 + (d_needs() ? 1 : 0) + (cross_needed() ? 1 : 0) + (x_needs() ? 1 : 0);
+        return n;
+    }
+
+    // product of the per-tile transition matrices over each segment of FCHAIN_L tiles, segments in scan order
+    static std::vector<HT> build_fseg(const DimTables<HT>& tb, const std::vector<HostScan>& scans, int nb, int nseg)
+    {
+        const int S = (int)scans.size();
+        std::vector<HT> out((size_t)S * nseg * R * R, (HT)0), tmp;
+        for (int s = 0; s < S; ++s)
+            for (int gs = 0; gs < nseg; ++gs) {
+                const int g = scans[s].causal ? gs : nseg - 1 - gs;          // memory segment
+                const int j0 = g * FCHAIN_L, j1 = std::min(nb, j0 + FCHAIN_L);
+                std::vector<HT> acc((size_t)R * R, (HT)0);
+                for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
+                for (int t = 0; t < j1 - j0; ++t) {
+                    const int j = scans[s].causal ? j0 + t : j1 - 1 - t;
+                    const int var = nb == 1 ? V_SINGLE : (j == 0 ? V_FIRST : (j == nb - 1 ? V_LAST : V_INTERIOR));
+                    matmul_rr<HT>(tmp, &tb.P[((size_t)var * S + s) * R * R], acc.data(), R);
+                    acc = tmp;
+                }
+                std::copy(acc.begin(), acc.end(), out.begin() + ((size_t)s * nseg + gs) * R * R);
+            }
+        return out;
+    }
+
+    int init(int64_t Nx, int64_t Nd, int64_t No, bool clamp_)
+    {
+        clamp = clamp_;
+        std::memset(&fp, 0, sizeof(fp));
+        fp.Nx = Nx; fp.Nd = Nd; fp.No = No;
+        fp.nbx = gx.nb; fp.nbd = gd.nb;
+        fp.clamp = clamp ? 1 : 0;
+        fp.x_lo_closed = gx.lo_closed; fp.x_hi_closed = gx.hi_closed;
+        fp.d_lo_closed = gd.lo_closed; fp.d_hi_closed = gd.hi_closed;
+        fp.mx = gx.nscans; fp.md = gd.nscans;
+        fp.nlx = Nd * No; fp.nly = Nx * No;
+        double gain = 1.0; uint32_t gain_u = 1u;
+        auto fill = [&](FusedScanTab<CT, R>& tab, const std::vector<HostScan>& sc) {
+            for (size_t s = 0; s < sc.size(); ++s) {
+                tab.causal[s] = sc[s].causal;
+                const std::vector<HT> c = coeff_vec<HT>(sc[s], R, true);
+                for (int k = 0; k <= R; ++k) tab.a[s][k] = (CT)c[k];
+                gain *= (double)sc[s].coeff[0];
+                gain_u *= cvt_coeff<uint32_t>(sc[s].coeff[0]);
+            }
+        };
+        fill(fp.sx, sx); fill(fp.sd, sd);
+        fp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
+        nsegx = (gx.nb + FCHAIN_L - 1) / FCHAIN_L;
+        nsegd = (gd.nb + FCHAIN_L - 1) / FCHAIN_L;
+
+        if (fp.mx > 0) {
+            build_dim_tables<HT>(tx_tab, sx, gx, R, clamp, 0, 0, true, true, ts);
+            CUDA_TRY((upload<HT, TT>(dPx, tx_tab.P)));
+            CUDA_TRY((upload<HT, TT>(dMx, tx_tab.M)));
+            CUDA_TRY((upload<HT, TT>(dL, tx_tab.L)));
+            CUDA_TRY((upload<HT, TT>(dPsegx, build_fseg(tx_tab, sx, gx.nb, nsegx))));
+            const size_t n = (size_t)fp.mx * R * gx.nb * fp.nlx * sizeof(CT);
+            CUDA_TRY(TX.alloc(n)); CUDA_TRY(CX.alloc(n));
+            CUDA_TRY(cudaMemset(CX.p, 0, n));
+        }
+        if (fp.md > 0) {
+            build_dim_tables<HT>(td_tab, sd, gd, R, clamp, 0, 0, true, true, ts);
+            CUDA_TRY((upload<HT, TT>(dPd, td_tab.P)));
+            CUDA_TRY((upload<HT, TT>(dMd, td_tab.M)));
+            CUDA_TRY((upload<HT, TT>(dG, td_tab.G)));
+            CUDA_TRY((upload<HT, TT>(dPsegd, build_fseg(td_tab, sd, gd.nb, nsegd))));
+            const size_t n = (size_t)fp.md * R * gd.nb * fp.nly * sizeof(CT);
+            CUDA_TRY(TY.alloc(n)); CUDA_TRY(CY.alloc(n));
+            CUDA_TRY(cudaMemset(CY.p, 0, n));
+            if (d_open()) {
+                const size_t m = (size_t)fp.md * R * fp.nly * sizeof(CT);
+                CUDA_TRY(dExt.alloc(m)); CUDA_TRY(dTailOut.alloc(m));
+                CUDA_TRY(cudaMemset(dExt.p, 0, m));
+                resolver.reset(new ShardResolver<CT, R>());
+                int rc = resolver->init(sd, gd.n, clamp, true);
+                if (rc) return rc;
+            }
+        }
+        if (fp.mx > 0 && fp.md > 0)
+            CUDA_TRY(dA.alloc((size_t)gx.nb * gd.nb * No * fp.md * fp.mx * R * R * sizeof(TT)));
+        fp.TX = (CT*)TX.p; fp.CX = (const CT*)CX.p; fp.TY = (CT*)TY.p; fp.CY = (const CT*)CY.p;
+        return RF_OK;
+    }
+
+    int run_tails(const void* in, void* out, cudaStream_t st) override
+    {
+        if (!needs_carries()) return RF_OK;
+        cudaEvent_t ev = timer ? timer->begin(st, ST_TAILS) : nullptr;
+        fp.reverse = 0;
+        CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P1, ts, st)));
+        if (timer) timer->end(st, ev);
+        return RF_OK;
+    }
+
+    int run_chain(bool xdim, const void* ext_d, void* tail_out_d, cudaStream_t st)
+    {
+        FChainParams<CT, R> cp;
+        std::memset(&cp, 0, sizeof(cp));
+        const DimGeom& g = xdim ? gx : gd;
+        const auto& scans = xdim ? sx : sd;
+        cp.T = (const CT*)(xdim ? TX.p : TY.p);
+        cp.C = (CT*)(xdim ? CX.p : CY.p);
+        cp.nl = xdim ? fp.nlx : fp.nly;
+        cp.nb = g.nb; cp.S = g.nscans;
+        cp.nseg = xdim ? nsegx : nsegd;
+        for (int s = 0; s < g.nscans; ++s) cp.causal[s] = scans[s].causal;
+        cp.P = (const TT*)(xdim ? dPx.p : dPd.p);
+        cp.M = (const TT*)(xdim ? dMx.p : dMd.p);
+        cp.Pseg = (const TT*)(xdim ? dPsegx.p : dPsegd.p);
+        cp.ext = xdim ? nullptr : (const CT*)ext_d;
+        cp.tail_out = xdim ? nullptr : (CT*)tail_out_d;
+        if (xdim && cross_needed()) {
+            cp.A = (const TT*)dA.p; cp.G = (const TT*)dG.p;
+            cp.Sd = fp.md; cp.TS = ts; cp.nbd = gd.nb; cp.Nd = fp.Nd;
+        }
+        cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
+        CUDA_TRY((FLaunch<CT, R>::chain(cp, st)));
+        if (timer) timer->end(st, ev);
+        return RF_OK;
+    }
+
+    int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st, int stage) override
+    {
+        if (!needs_carries()) return RF_OK;
+        if (d_needs()) { int rc = run_chain(false, ext_d, tail_out_d, st); if (rc) return rc; }
+        if (stage == 1) return RF_OK;                // stage 1 of a sharded run: only the outgoing tails are needed
+        if (cross_needed()) {
+            FCrossParams<CT, R> cr;
+            std::memset(&cr, 0, sizeof(cr));
+            cr.CY = (const CT*)CY.p; cr.L = (const TT*)dL.p; cr.A = (TT*)dA.p;
+            cr.Nx = fp.Nx; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md; cr.nly = fp.nly;
+            cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
+            CUDA_TRY((FLaunch<CT, R>::cross(cr, ts, st)));
+            if (timer) timer->end(st, ev);
+        }
+        if (x_needs()) { int rc = run_chain(true, nullptr, nullptr, st); if (rc) return rc; }
+        return RF_OK;
+    }
+
+    int run_final(const void* in, void* out, cudaStream_t st) override
+    {
+        cudaEvent_t ev = timer ? timer->begin(st, ST_FINAL) : nullptr;
+        fp.reverse = needs_carries() ? 1 : 0;
+        CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P2, ts, st)));
+        if (timer) timer->end(st, ev);
+        return RF_OK;
+    }
+
+    size_t shard_tail_elems() const override { return d_open() ? (size_t)fp.md * R * fp.nly : 0; }
+    int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) override
+    {
+        if (!d_open()) return RF_OK;
+        return resolver->run(fp.nly, gathered, nshards, rank, dExt.p, st);
+    }
+
+    std::string describe() const override
+    {
+        char b[512];
+        snprintf(b, sizeof(b),
+                 "  fused pass view [%lld][%lld][%lld]: %dx%d register tiles, d scans %d (%d tiles) then x scans %d "
+                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), launches %d\n",
+                 (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
+                 launches());
+        return b;
+    }
+};
 
 // narrow integer types are widened to the 32-bit compute ring on entry and truncated on exit
 // (arithmetic mod 2^16 / 2^8 is a quotient of arithmetic mod 2^32, so this is exact)
@@ -652,6 +944,69 @@ static int make_pass(rf_plan* plan, const std::vector<HostScan>& sx, const std::
     if (rc) return rc;
     plan->passes.push_back(std::move(ps));
     return RF_OK;
+}
+
+template <typename CT, int R>
+static int make_fused_pass(rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                           int64_t Nx, int64_t Nd, int64_t No, int ts, bool d_is_shard)
+{
+    const rf_desc& d = plan->desc;
+    auto ps = std::unique_ptr<FusedPass<CT, R>>(new (std::nothrow) FusedPass<CT, R>());
+    if (!ps) return fail(RF_ENOMEM, "out of host memory");
+    ps->sx = sx; ps->sd = sd; ps->ts = ts;
+    auto geom = [ts](DimGeom& g, int64_t n, int nscans) {
+        g.n = n; g.t = ts; g.nb = (int)(n / ts); g.len_last = ts;
+        g.nscans = nscans; g.lo_closed = 1; g.hi_closed = 1;
+    };
+    geom(ps->gx, Nx, (int)sx.size());
+    geom(ps->gd, Nd, (int)sd.size());
+    if (d_is_shard) { ps->gd.lo_closed = d.opt.open_lo ? 0 : 1; ps->gd.hi_closed = d.opt.open_hi ? 0 : 1; }
+    int rc = ps->init(Nx, Nd, No, d.border == RF_BORDER_CLAMP);
+    if (rc) return rc;
+    plan->passes.push_back(std::move(ps));
+    return RF_OK;
+}
+
+// tile size of the fused fast path for this pass, or 0 when the pass must take the generic engine
+static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                           int64_t Nx, int64_t Nd, int64_t No)
+{
+    const rf_options& opt = plan->desc.opt;
+    if (opt.engine == RF_ENGINE_GENERIC || opt.honor_tile) return 0;
+    if (plan->R > 4) return 0;
+    if (sx.size() > (size_t)FMAX_SCANS || sd.size() > (size_t)FMAX_SCANS || (sx.empty() && sd.empty())) return 0;
+    for (const auto* v : { &sx, &sd })
+        for (const HostScan& h : *v) {
+            if (plan->is_float) {
+                const double inv = 1.0 / (double)h.coeff[0];
+                if (h.coeff[0] == 0.f || !std::isfinite((float)inv)) return 0;
+            } else if (cvt_coeff<uint32_t>(h.coeff[0]) != 1u) return 0;
+        }
+    for (int ts : { 128, 64 }) {
+        if (Nx % ts || Nd % ts) continue;
+        const int64_t nbx = Nx / ts, nbd = Nd / ts;
+        if (!sx.empty() && nbx > 16 * FCHAIN_L) continue;
+        if (!sd.empty() && nbd > 16 * FCHAIN_L) continue;
+        if (nbx * nbd * No > 0x7fffffffLL) continue;
+        if (ts == 128 && nbx * nbd * No < 2 * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
+            (sx.empty() || Nx / 64 <= 16 * FCHAIN_L) && (sd.empty() || Nd / 64 <= 16 * FCHAIN_L))
+            continue;                       // small problem: smaller tiles fill the machine better
+        return ts;
+    }
+    return 0;
+}
+
+template <typename CT>
+static int make_fused_pass_R(rf_plan* plan, int R, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                             int64_t Nx, int64_t Nd, int64_t No, int ts, bool d_is_shard)
+{
+    switch (R) {
+    case 1: return make_fused_pass<CT, 1>(plan, sx, sd, Nx, Nd, No, ts, d_is_shard);
+    case 2: return make_fused_pass<CT, 2>(plan, sx, sd, Nx, Nd, No, ts, d_is_shard);
+    case 3: return make_fused_pass<CT, 3>(plan, sx, sd, Nx, Nd, No, ts, d_is_shard);
+    case 4: return make_fused_pass<CT, 4>(plan, sx, sd, Nx, Nd, No, ts, d_is_shard);
+    }
+    return fail(RF_EUNSUPPORTED, "the fused path supports orders <= 4");
 }
 
 template <typename CT>
@@ -761,8 +1116,15 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
 
         auto add = [&](const std::vector<HostScan>& sx, const std::vector<HostScan>& sd, int64_t Nx, int64_t Nd,
                        int64_t No, int tx, int td, bool fused, bool shard) -> int {
-            int rc = plan->is_float ? make_pass_R<float>(plan.get(), R, sx, sd, Nx, Nd, No, tx, td, fused, shard)
-                                    : make_pass_R<uint32_t>(plan.get(), R, sx, sd, Nx, Nd, No, tx, td, fused, shard);
+            const int fts = fused_tile_size(plan.get(), sx, sd, Nx, Nd, No);
+            if (!fts && opt.engine == RF_ENGINE_FUSED)
+                return fail(RF_EUNSUPPORTED, "engine=fused requested but a pass is not eligible (needs order <= 4, "
+                            "extents that are multiples of 64, non-zero float / unit integer feed-forward)");
+            int rc;
+            if (fts) rc = plan->is_float ? make_fused_pass_R<float>(plan.get(), R, sx, sd, Nx, Nd, No, fts, shard)
+                                         : make_fused_pass_R<uint32_t>(plan.get(), R, sx, sd, Nx, Nd, No, fts, shard);
+            else     rc = plan->is_float ? make_pass_R<float>(plan.get(), R, sx, sd, Nx, Nd, No, tx, td, fused, shard)
+                                         : make_pass_R<uint32_t>(plan.get(), R, sx, sd, Nx, Nd, No, tx, td, fused, shard);
             if (rc == RF_OK && shard) plan->shard_pass = (int)plan->passes.size() - 1;
             return rc;
         };
@@ -915,7 +1277,7 @@ int rf_plan_stage1(rf_plan* plan, const void* in_dev, void* out_dev, void* tails
         auto& p = plan->passes[i];
         int rc;
         if ((rc = p->run_tails(src, out_dev, st))) return rc;
-        if (i == plan->shard_pass) return p->run_carries(nullptr, tails_dev, st);
+        if (i == plan->shard_pass) return p->run_carries(nullptr, tails_dev, st, 1);
         if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;
         if ((rc = p->run_final(src, out_dev, st))) return rc;
         src = out_dev;
@@ -937,7 +1299,7 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev, const void*
         if (i == plan->shard_pass) {
             if ((rc = p->shard_resolve(gathered_tails_dev, nshards, shard_rank, st))) return rc;
             // tails of K1 are still valid: redo the carry completion with the incoming shard carries
-            if ((rc = p->run_carries(p->ext_buffer(), nullptr, st))) return rc;
+            if ((rc = p->run_carries(p->ext_buffer(), nullptr, st, 2))) return rc;
         } else {
             if ((rc = p->run_tails(src, out_dev, st))) return rc;
             if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;

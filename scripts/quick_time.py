@@ -20,6 +20,12 @@ def run(name, ext, dtype, scans, border="zero", **kw):
     src = (torch.rand(n, device="cuda") if dtype == "f32" else torch.randint(0, 255, (n,), device="cuda", dtype=tdt))
     dst = torch.empty_like(src)
     ms = timeit(plan, src, dst)
+    plan.stage_timing(True)
+    for _ in range(5): plan.execute(src, dst)
+    torch.cuda.synchronize()
+    st = plan.stage_times()
+    plan.stage_timing(False)
+    print("   stages(us/exec):", {k: round(v["ms"] * 1e3 / 5, 1) for k, v in st.items() if v["launches"]})
     gs = n / ms / 1e6
     print(f"{name:28s} {ms*1e3:9.1f} us  {gs:8.1f} Gsamples/s  {8*n/ms/1e6:8.1f} GB/s algorithmic  launches={plan.num_launches} ws={plan.workspace_bytes/1e6:.0f}MB", flush=True)
     print(plan.describe())

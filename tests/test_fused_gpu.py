@@ -1,0 +1,221 @@
+"""GPU parity tests of the fused fast path (recfilter_b200/csrc/fused.cuh) through the C ABI.
+
+Every case is run with engine="fused" (plan creation fails if a pass is not eligible, so a
+silent fall back to the generic engine cannot hide a bug), compared with the oracle exactly
+like tests/test_parity_gpu.py, and -- where cheap -- also against the generic engine.
+Strip-sharded execution (rf_plan_stage1 / rf_plan_stage2) is checked with virtual strips on
+one device: the same kernels and the same tail exchange a multi-GPU run uses.
+"""
+import numpy as np
+import pytest
+
+from recfilter_b200 import Plan, Scan, RecFilterError, gaussian_weights
+from helpers import rand_image, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+G3 = gaussian_weights(5.0, 3)
+G2 = gaussian_weights(5.0, 2)
+G1 = gaussian_weights(5.0, 1)
+W2 = [[1.0, 0.5, 0.25], [1.0, 0.5, 0.125], [1.0, 0.5, 0.0625], [1.0, 0.5, 0.125], [1.0, 0.5, 0.25], [1.0, 0.5, 0.0625]]
+C3 = [(0, True, G3), (0, False, G3), (1, True, G3), (1, False, G3)]
+
+
+def run(a, scans, border="zero", engine="fused", **kw):
+    plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in scans], border, engine=engine, **kw)
+    if engine == "fused":
+        assert "fused pass" in plan.describe()
+    out = plan.realize(a)
+    plan.close()
+    return out
+
+
+def check_float(oracle, a, scans, border="zero", tol=TOL):
+    out = run(a, scans, border)
+    truth = oracle.apply_filter(a.astype(np.float64), scans, border, threads=8)
+    ref32 = oracle.apply_filter(a, scans, border, threads=8)
+    e_gpu, e_cpu = rel_err(out, truth), rel_err(ref32, truth)
+    assert np.isfinite(out).all()
+    assert e_gpu <= tol, f"fused rel err {e_gpu:.3e} (serial fp32 loop {e_cpu:.3e})"
+    assert e_gpu <= 8 * e_cpu + 2e-6, f"fused {e_gpu:.3e} much worse than the serial fp32 loop {e_cpu:.3e}"
+    return out
+
+
+def check_int(oracle, a, scans, border="zero"):
+    out = run(a, scans, border)
+    np.testing.assert_array_equal(out, oracle.apply_filter(a, scans, border, threads=8))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (256, 384), (64, 64), (192, 320), (512, 128), (128, 1024), (1024, 1024)])
+@pytest.mark.parametrize("border", ["clamp", "zero"])
+def test_c3_gaussian(oracle, shape, border):
+    a = rand_image(shape, np.float32, 300)
+    out = check_float(oracle, a, C3, border)
+    gen = run(a, C3, border, engine="generic")
+    assert rel_err(out, gen) < 8e-6
+
+
+def test_c3_full_size_8192(oracle):
+    a = rand_image((8192, 8192), np.float32, 2)
+    out = check_float(oracle, a, C3, "clamp")
+    # unit DC gain + clamped border: a constant image is a fixed point, at full size too
+    c = run(np.full((8192, 8192), 0.625, np.float32), C3, "clamp")
+    np.testing.assert_allclose(c, 0.625, rtol=3e-4)
+    # linearity at full size: F(2a) == 2 F(a) exactly in floating point (power-of-two scale)
+    np.testing.assert_array_equal(run(a * np.float32(2), C3, "clamp"), out * np.float32(2))
+
+
+@pytest.mark.parametrize("n", [64, 128, 2048])
+def test_c1_sat_u32_bit_exact(oracle, n):
+    rng = np.random.default_rng(20240601)
+    a = rng.integers(0, 256, size=(n, n), dtype=np.uint32)
+    sat = [(0, True, [1, 1]), (1, True, [1, 1])]
+    check_int(oracle, a, sat)
+    if n == 2048:
+        ones = run(np.ones((n, n), np.uint32), sat)
+        yy, xx = np.mgrid[0:n, 0:n]
+        np.testing.assert_array_equal(ones, ((xx + 1) * (yy + 1)).astype(np.uint32))
+        full = rand_image((n, n), np.uint32, 21)            # full-range: wraparound must match
+        check_int(oracle, full, sat)
+
+
+def test_c2_box_core(oracle):
+    a = rand_image((4096, 4096), np.float32, 1)
+    out = check_float(oracle, a, [(0, True, [1, 1]), (1, True, [1, 1])])
+    assert out[-1, -1] == pytest.approx(float(a.astype(np.float64).sum()), rel=1e-5)
+    b = rand_image((256, 384), np.float32, 41)
+    check_float(oracle, b, [(0, True, [1, 2, -1]), (1, True, [1, 2, -1])], tol=2e-5)
+
+
+def test_int_types_and_mixed_scans(oracle):
+    for dt in (np.int32, np.uint32, np.uint16, np.int8):
+        a = rand_image((128, 192), dt, 90)
+        check_int(oracle, a, [(0, True, [1, 1]), (1, False, [1, -1, 3]), (0, False, [1, 1]), (1, True, [1, 2, -1])])
+        check_int(oracle, a, [(1, False, [1, 3, 1, -2, 1]), (0, True, [1, -1])], "clamp")
+
+
+def test_integer_feedforward_not_one_takes_generic_engine():
+    with pytest.raises(RecFilterError, match="not eligible"):
+        Plan((128, 128), "u32", [Scan(0, True, [2, 1])], engine="fused")
+    with pytest.raises(RecFilterError, match="not eligible"):
+        Plan((100, 128), "f32", [Scan(0, True, [1.0, 0.5])], engine="fused")
+    with pytest.raises(RecFilterError, match="not eligible"):
+        Plan((128, 128), "f32", [Scan(0, True, [1.0] + [0.1] * 5)], engine="fused")
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("border", ["clamp", "zero"])
+def test_orders_and_single_dimension_passes(oracle, order, border):
+    coeff = [0.7] + [0.9 / order / (1 + 0.1 * k) for k in range(order)]
+    a = rand_image((256, 384), np.float32, 70 + order)
+    check_float(oracle, a, [(0, True, coeff), (0, False, coeff)], border)        # x only
+    check_float(oracle, a, [(1, False, coeff), (1, True, coeff)], border)        # d only
+    check_float(oracle, a, [(0, False, coeff), (1, True, coeff)], border)
+
+
+def test_four_scans_per_dimension_mixed_orders(oracle):
+    a = rand_image((256, 256), np.float32, 80)
+    sc = [(0, True, [1, .5]), (0, False, [.8, .3, .2, .1]), (0, True, [.5, .2, .2]), (0, False, [1, .4]),
+          (1, False, [.9, .3, -.1]), (1, True, [.5, .5]), (1, True, G3), (1, False, G2)]
+    check_float(oracle, a, sc)
+    check_float(oracle, a, sc, "clamp")
+
+
+def test_ref_style_causal_anticausal_orderings(oracle):
+    # the patterns of tests/test_generic_xy.cpp (+x,-x,+x,-x,+y,-y,-y) at a fused-eligible size
+    a = rand_image((128, 192), np.float32, 17)
+    sc = [(0, True, W2[0]), (0, False, W2[1]), (0, True, W2[2]), (0, False, W2[3]),
+          (1, True, W2[4]), (1, False, W2[5]), (1, False, W2[0])]
+    check_float(oracle, a, sc)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 128), (128, 128, 128), (3, 256, 128)])
+def test_c5_volume(oracle, shape):
+    a = rand_image(shape, np.float32, 60)
+    sc = [(0, True, W2[0]), (0, False, W2[1]), (1, True, W2[2]), (1, False, W2[3])]
+    if shape[0] % 64 == 0:
+        sc += [(2, True, W2[4]), (2, False, W2[5])]
+    check_float(oracle, a, sc)
+    check_float(oracle, a, sc, "clamp")
+
+
+def test_c5_full_size_512(oracle):
+    a = rand_image((512, 512, 512), np.float32, 4)
+    sc = [(0, True, W2[0]), (0, False, W2[1]), (1, True, W2[2]), (1, False, W2[3]), (2, True, W2[4]), (2, False, W2[5])]
+    check_float(oracle, a, sc)
+
+
+def test_long_rows_many_tiles(oracle):
+    a = rand_image((128, 16384), np.float32, 53)           # 128 tiles of 128 along x
+    check_float(oracle, a, [(0, True, G3), (0, False, G3)], "clamp")
+    b = rand_image((8192, 64), np.float32, 54)             # 128 tiles of 64 along d
+    check_float(oracle, b, [(1, True, G2), (1, False, G3)])
+
+
+def test_device_resident_in_place(oracle):
+    import torch
+    a = rand_image((256, 384), np.float32, 92)
+    plan = Plan((384, 256), "f32", [Scan(*s) for s in C3], "clamp", engine="fused")
+    src = torch.from_numpy(a).cuda()
+    dst = plan.execute(src)
+    torch.cuda.synchronize()
+    host = plan.realize(a)
+    np.testing.assert_array_equal(dst.cpu().numpy(), host)
+    plan.execute(src, src)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(src.cpu().numpy(), host)
+
+
+# ---- strip-sharded execution with virtual strips on one device -------------------------------------------
+def run_sharded(a, scans, border, nshards, shard_dim, engine):
+    import torch
+    nd = a.ndim
+    ax = nd - 1 - shard_dim
+    np_dtype = a.dtype
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)                                # torch has no full uint32 support; same bits
+    strips = np.split(a, nshards, axis=ax)
+    plans, srcs, dsts, tails = [], [], [], []
+    for r, s in enumerate(strips):
+        p = Plan(s.shape[::-1], np_dtype, [Scan(*x) for x in scans], border, engine=engine, shard_dim=shard_dim,
+                 open_lo=r > 0, open_hi=r < nshards - 1)
+        plans.append(p)
+        srcs.append(torch.from_numpy(np.ascontiguousarray(s)).cuda())
+        dsts.append(torch.empty_like(srcs[-1]))
+        tails.append(torch.zeros(p.shard_tail_bytes // 4, device="cuda", dtype=srcs[-1].dtype))
+    for p, s, d, t in zip(plans, srcs, dsts, tails):
+        p.stage1(s, d, t)
+    gathered = torch.stack(tails).contiguous()              # what an all-gather delivers, rank major
+    for r, (p, s, d) in enumerate(zip(plans, srcs, dsts)):
+        p.stage2(s, d, gathered, nshards, r)
+    torch.cuda.synchronize()
+    out = np.concatenate([d.cpu().numpy() for d in dsts], axis=ax).view(np_dtype)
+    for p in plans:
+        p.close()
+    return out
+
+
+@pytest.mark.parametrize("engine", ["fused", "generic"])
+@pytest.mark.parametrize("nshards", [2, 4, 8])
+def test_strip_sharded_gaussian(oracle, engine, nshards):
+    a = rand_image((1024, 512), np.float32, 500 + nshards)
+    for border in ("clamp", "zero"):
+        out = run_sharded(a, C3, border, nshards, 1, engine)
+        truth = oracle.apply_filter(a.astype(np.float64), C3, border, threads=8)
+        assert rel_err(out, truth) <= TOL
+        whole = run(a, C3, border, engine=engine)
+        assert rel_err(out, whole) < 4e-6
+
+
+@pytest.mark.parametrize("engine", ["fused", "generic"])
+def test_strip_sharded_sat_u32_and_volume(oracle, engine):
+    a = rand_image((512, 256), np.uint32, 600)
+    sat = [(0, True, [1, 1]), (1, True, [1, 1]), (1, False, [1, 1])]
+    np.testing.assert_array_equal(run_sharded(a, sat, "zero", 4, 1, engine), oracle.apply_filter(a, sat, threads=8))
+    v = rand_image((256, 128, 128), np.float32, 601)
+    sc = [(0, True, W2[0]), (0, False, W2[1]), (1, True, W2[2]), (1, False, W2[3]), (2, True, W2[4]), (2, False, W2[5])]
+    out = run_sharded(v, sc, "zero", 4, 2, engine)
+    truth = oracle.apply_filter(v.astype(np.float64), sc, threads=8)
+    assert rel_err(out, truth) <= TOL
