@@ -43,7 +43,9 @@ struct DimGeom {
 // float filters (independent rounding errors of the r history values are amplified by the
 // recurrence, so carries must be much better than fp32-accurate before they are rounded once)
 template <typename CT> struct TabType { typedef CT type; };
+#ifndef RFB_FP32_CARRY_ALGEBRA
 template <> struct TabType<float> { typedef double type; };
+#endif
 
 // device-side scan table entry (coefficients already converted to the compute type)
 template <typename CT, int R>

@@ -17,6 +17,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 #include <new>
 #include <string>
@@ -982,13 +983,15 @@ static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx,
                 if (h.coeff[0] == 0.f || !std::isfinite((float)inv)) return 0;
             } else if (cvt_coeff<uint32_t>(h.coeff[0]) != 1u) return 0;
         }
+    const char* force = getenv("RFB_FUSED_TS");          // development knob: force a tile size
     for (int ts : { 128, 64 }) {
+        if (force && atoi(force) != ts) continue;
         if (Nx % ts || Nd % ts) continue;
         const int64_t nbx = Nx / ts, nbd = Nd / ts;
         if (!sx.empty() && nbx > 16 * FCHAIN_L) continue;
         if (!sd.empty() && nbd > 16 * FCHAIN_L) continue;
         if (nbx * nbd * No > 0x7fffffffLL) continue;
-        if (ts == 128 && nbx * nbd * No < 2 * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
+        if (!force && ts == 128 && nbx * nbd * No < 2 * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
             (sx.empty() || Nx / 64 <= 16 * FCHAIN_L) && (sd.empty() || Nd / 64 <= 16 * FCHAIN_L))
             continue;                       // small problem: smaller tiles fill the machine better
         return ts;
