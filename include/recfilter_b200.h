@@ -159,6 +159,15 @@ int rf_plan_stage1(rf_plan* plan, const void* in_dev, void* out_dev, void* tails
 int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev,
                    const void* gathered_tails_dev, int nshards, int shard_rank, void* stream);
 
+/*
+ * Device-side stopwatch for a sequence of asynchronous calls on one stream (CUDA events):
+ * what RecFilter::profile needs to time a chain of plans (lib/recfilter.cpp:998-1011, which uses
+ * an unsynchronised wall clock).  rf_clock_end waits for the work, returns the elapsed
+ * milliseconds and releases the clock.
+ */
+int rf_clock_begin(void* stream, void** clock);
+int rf_clock_end(void* clock, void* stream, float* ms);
+
 /* device memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can stage buffers */
 int rf_malloc(void** dev_ptr, size_t bytes);
 int rf_free(void* dev_ptr);

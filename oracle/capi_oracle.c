@@ -1,0 +1,132 @@
+/*
+ * capi_oracle.c -- the C ABI of include/recfilter_b200.h implemented on the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  It exists for one purpose: to link the reference's own test
+ * programs (/root/reference/tests/*.cpp, compiled unchanged against include/recfilter.h) with
+ * the oracle instead of the CUDA engine, so that the inline serial loops those programs carry
+ * pin the oracle (oracle/pin_reference.py -> tests/golden/PIN_REPORT.json).  The product
+ * (recfilter_b200/) never links or loads this file; "device" pointers here are host pointers.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "../include/recfilter_b200.h"
+
+int oracle_filter(void* data, int dtype, int ndim, const int64_t* extents, int clamp, int nscans,
+                  const int* scan_dim, const int* scan_causal, const int* scan_ncoeff, const float* coeffs,
+                  int nthreads);
+
+struct rf_plan { rf_desc d; size_t total; size_t eb; };
+
+static char g_err[256] = "";
+static size_t elem_bytes(int dt)
+{
+    switch (dt) { case RF_F32: case RF_I32: case RF_U32: return 4; case RF_I16: case RF_U16: return 2;
+                  case RF_I8: case RF_U8: return 1; }
+    return 0;
+}
+
+const char* rf_version(void) { return "recfilter oracle backend (CPU, test infrastructure)"; }
+const char* rf_last_error(void) { return g_err; }
+int rf_device_count(void) { return 1; }
+int rf_set_device(int device) { (void)device; return RF_OK; }
+
+void oracle_set_sum_order(int order);
+
+int rf_plan_create(const rf_desc* desc, rf_plan** out)
+{
+    const char* so = getenv("ORACLE_SUM_ORDER");                 /* "tests": see oracle.c */
+    oracle_set_sum_order(so && strcmp(so, "tests") == 0);
+    if (!desc || !out) { snprintf(g_err, sizeof g_err, "null argument"); return RF_EINVAL; }
+    rf_plan* p = (rf_plan*)calloc(1, sizeof(rf_plan));
+    if (!p) return RF_ENOMEM;
+    p->d = *desc;
+    p->eb = elem_bytes(desc->dtype);
+    if (!p->eb) { free(p); snprintf(g_err, sizeof g_err, "unknown dtype"); return RF_EINVAL; }
+    p->total = 1;
+    for (int i = 0; i < desc->ndim; ++i) p->total *= (size_t)desc->extent[i];
+    for (int s = 0; s < desc->nscans; ++s)
+        if (desc->scans[s].dim < 0 || desc->scans[s].dim >= desc->ndim || desc->scans[s].order < 1) {
+            free(p); snprintf(g_err, sizeof g_err, "bad scan %d", s); return RF_EINVAL;
+        }
+    *out = p;
+    return RF_OK;
+}
+void rf_plan_destroy(rf_plan* plan) { free(plan); }
+size_t rf_plan_workspace_bytes(const rf_plan* plan) { (void)plan; return 0; }
+int rf_plan_num_launches(const rf_plan* plan) { (void)plan; return 0; }
+int rf_plan_describe(const rf_plan* plan, char* buf, size_t n)
+{
+    snprintf(buf, n, "oracle backend: %d scans applied serially on the CPU (test infrastructure)\n", plan->d.nscans);
+    return RF_OK;
+}
+
+/* oracle.c numbers the element types like rf_dtype (F32 0, I32 2, U32 3, I16 4, U16 5, I8 6, U8 7) */
+int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stream)
+{
+    (void)stream;
+    const rf_desc* d = &plan->d;
+    if (plan->total == 0) return RF_OK;
+    if (in_dev != out_dev) memmove(out_dev, in_dev, plan->total * plan->eb);
+    int dims[RF_MAX_SCANS], causal[RF_MAX_SCANS], nco[RF_MAX_SCANS];
+    float* co = (float*)malloc(sizeof(float) * RF_MAX_SCANS * (RF_MAX_ORDER + 1));
+    size_t k = 0;
+    for (int s = 0; s < d->nscans; ++s) {
+        dims[s] = d->scans[s].dim; causal[s] = d->scans[s].causal; nco[s] = d->scans[s].order + 1;
+        for (int j = 0; j <= d->scans[s].order; ++j) co[k++] = d->scans[s].coeff[j];
+    }
+    int rc = oracle_filter(out_dev, d->dtype, d->ndim, d->extent, d->border == RF_BORDER_CLAMP, d->nscans,
+                           dims, causal, nco, co, 1);
+    free(co);
+    if (rc) { snprintf(g_err, sizeof g_err, "oracle_filter failed"); return RF_EINVAL; }
+    return RF_OK;
+}
+int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host) { return rf_plan_execute(plan, in_host, out_host, 0); }
+int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms)
+{
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int i = 0; i < iters; ++i) { int rc = rf_plan_execute(plan, in_dev, out_dev, 0); if (rc) return rc; }
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    *ms = (float)(((b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6) / iters);
+    return RF_OK;
+}
+int rf_plan_stage_timing(rf_plan* plan, int enable) { (void)plan; (void)enable; return RF_OK; }
+int rf_plan_stage_times(rf_plan* plan, double* ms, long* counts, int n)
+{
+    (void)plan;
+    for (int i = 0; i < n; ++i) { ms[i] = 0; counts[i] = 0; }
+    return RF_OK;
+}
+size_t rf_plan_shard_tail_bytes(const rf_plan* plan) { (void)plan; return 0; }
+int rf_plan_stage1(rf_plan* p, const void* i, void* o, void* t, void* s) { (void)p; (void)i; (void)o; (void)t; (void)s; return RF_EUNSUPPORTED; }
+int rf_plan_stage2(rf_plan* p, const void* i, void* o, const void* g, int n, int r, void* s)
+{ (void)p; (void)i; (void)o; (void)g; (void)n; (void)r; (void)s; return RF_EUNSUPPORTED; }
+
+int rf_clock_begin(void* stream, void** clock)
+{
+    (void)stream;
+    struct timespec* t = (struct timespec*)malloc(sizeof(struct timespec));
+    clock_gettime(CLOCK_MONOTONIC, t);
+    *clock = t;
+    return RF_OK;
+}
+int rf_clock_end(void* clock, void* stream, float* ms)
+{
+    (void)stream;
+    struct timespec b, *a = (struct timespec*)clock;
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    *ms = (float)((b.tv_sec - a->tv_sec) * 1e3 + (b.tv_nsec - a->tv_nsec) * 1e-6);
+    free(a);
+    return RF_OK;
+}
+
+int rf_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? RF_OK : RF_ENOMEM; }
+int rf_free(void* p) { free(p); return RF_OK; }
+int rf_memcpy_h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); return RF_OK; }
+int rf_memcpy_d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); return RF_OK; }
+int rf_memset(void* d, int v, size_t n) { memset(d, v, n); return RF_OK; }
+int rf_malloc_host(void** p, size_t bytes) { return rf_malloc(p, bytes); }
+int rf_free_host(void* p) { free(p); return RF_OK; }
+int rf_synchronize(void) { return RF_OK; }

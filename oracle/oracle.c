@@ -39,6 +39,17 @@
 
 #define ORACLE_MAX_ORDER 64
 
+/*
+ * Summation order inside one sample:
+ *   0  library order: ((b0*x + a1*t1) + a2*t2) + ...          lib/recfilter.cpp:324-341 (the default)
+ *   1  test-loop order: b0*x + ((a1*t1 + a2*t2) + ...)        how the reference's test programs write
+ *      their inline checks (tests/test_causal_xy.cpp:57-64: ref += t1 + t2 + t3).  Used only by the
+ *      pin (oracle/pin_reference.py) to show that, rounding order aside, the oracle and those loops
+ *      agree bit for bit.
+ */
+static int g_sum_order = 0;
+void oracle_set_sum_order(int order) { g_sum_order = order ? 1 : 0; }
+
 enum { ORACLE_F32 = 0, ORACLE_F64 = 1, ORACLE_I32 = 2, ORACLE_U32 = 3,
        ORACLE_I16 = 4, ORACLE_U16 = 5, ORACLE_I8 = 6, ORACLE_U8 = 7 };
 
@@ -88,6 +99,11 @@ static void NAME(T* data, int64_t outer, int64_t n, int64_t inner, int causal,  
                     for (int64_t x = x0; x < x1; x++) {                             \
                         const T old = row[x];                                       \
                         T acc = MUL(c[0], old);                                    \
+                        if (g_sum_order) {                                          \
+                            T ts = MUL(c[1], old);                                 \
+                            for (int j = 2; j <= r; j++) ts = (T)(ts + MUL(c[j], old)); \
+                            acc = (T)(acc + ts);                                    \
+                        } else                                                      \
                         for (int j = 1; j <= r; j++) acc = (T)(acc + MUL(c[j], old)); \
                         row[x] = acc;                                               \
                     }                                                               \
@@ -99,6 +115,14 @@ static void NAME(T* data, int64_t outer, int64_t n, int64_t inner, int causal,  
                     if (sj < 0) { tap[j] = clamp ? (causal ? base : base + (n - 1) * inner) : 0; } \
                     else        { tap[j] = base + (causal ? sj : n - 1 - sj) * inner; } \
                 }                                                                   \
+                if (g_sum_order) {                                                  \
+                    for (int64_t x = x0; x < x1; x++) {                             \
+                        T ts = MUL(c[1], tap[1] ? tap[1][x] : (T)0);               \
+                        for (int j = 2; j <= r; j++)                                \
+                            ts = (T)(ts + MUL(c[j], tap[j] ? tap[j][x] : (T)0));   \
+                        row[x] = (T)(MUL(c[0], row[x]) + ts);                      \
+                    }                                                               \
+                } else                                                              \
                 for (int64_t x = x0; x < x1; x++) {                                 \
                     T acc = MUL(c[0], row[x]);                                     \
                     for (int j = 1; j <= r; j++) {                                  \
@@ -137,14 +161,16 @@ static void NAME(T* data, int64_t lines, int64_t n, int causal, int clamp,      
             const int64_t i = causal ? s : n - 1 - s;                               \
             const T cur = f[i];                                                     \
             T acc = MUL(c[0], cur);                                                \
+            T ts = (T)0;                                                            \
             for (int j = 1; j <= r; j++) {                                          \
                 T t;                                                                \
                 if (s - j >= 0)      t = f[causal ? i - j : i + j];                 \
                 else if (clamp)      t = (s == 0) ? cur : f[causal ? 0 : n - 1];    \
                 else                 t = (T)0;                                      \
-                acc = (T)(acc + MUL(c[j], t));                                     \
+                if (g_sum_order) ts = (j == 1) ? MUL(c[j], t) : (T)(ts + MUL(c[j], t)); \
+                else             acc = (T)(acc + MUL(c[j], t));                    \
             }                                                                       \
-            f[i] = acc;                                                             \
+            f[i] = g_sum_order ? (T)(acc + ts) : acc;                               \
         }                                                                           \
     }                                                                               \
 }

@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Pin the oracle against the reference's own test programs.  TEST INFRASTRUCTURE.
+
+The reference cannot be built here (its Halide fork needs LLVM 3.4), but every program under
+/root/reference/tests carries its expected answer as inline serial loops.  oracle/Makefile
+compiles those programs UNCHANGED against include/recfilter.h and links them with the oracle
+(capi_oracle.c) instead of the CUDA engine; each program then prints the relative error between
+its own loops and the oracle.  This script runs them
+
+  * in the oracle's library summation order (lib/recfilter.cpp:324-341): agreement to the last
+    ulp or two is expected, because the test loops add the taps in a different order;
+  * in the test-loop summation order (ORACLE_SUM_ORDER=tests): agreement must be bit exact, except
+    for test_causal_anticausal_xy whose check applies the scans in another (commuting) order;
+
+and writes
+  tests/golden/PIN_REPORT.json          the verdict per program
+  tests/golden/reference_tests.json     the "Reference" arrays those programs printed -- outputs of
+                                        the reference's own code -- with the filter each one checks,
+                                        used as golden vectors by tests/test_golden.py (CPU: oracle,
+                                        GPU: CUDA engine).
+Run it in the build container (it needs /root/reference): python oracle/pin_reference.py
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+
+TESTS = ["test_type_invariance", "test_repeated_causal", "test_repeated_anticausal", "test_causal_anticausal",
+         "test_causal_xy", "test_causal_anticausal_xy", "test_generic_xy", "test_generic_xyz",
+         "test_overlap_filter_order"]
+# test_overlap_filter_order compares two library results (cascade vs overlapped filter): it pins
+# overlap_to_higher_order_filter, but its "Reference" is not the output of an inline loop -> no golden vector
+NO_GOLDEN = {"test_overlap_filter_order"}
+
+
+def parse_block(text, title, nvals):
+    """Numbers printed after `title` by operator<<(Image) (x fastest, '--' between planes)."""
+    i = text.find(title + "\n")
+    if i < 0:
+        return None
+    vals = []
+    for line in text[i + len(title) + 1:].splitlines():
+        line = line.strip()
+        if line == "--" or not line:
+            if len(vals) >= nvals:
+                break
+            continue
+        try:
+            vals.extend(float(t) for t in line.split())
+        except ValueError:
+            break
+        if len(vals) >= nvals:
+            break
+    return vals[:nvals] if len(vals) >= nvals else None
+
+
+def run(prog, order, dump=None):
+    env = dict(os.environ)
+    if order == "tests":
+        env["ORACLE_SUM_ORDER"] = "tests"
+    if dump:
+        if os.path.exists(dump):
+            os.remove(dump)
+        env["RECFILTER_DUMP_FILTER"] = dump
+    p = subprocess.run([os.path.join(HERE, "_ref", "pin", prog)], capture_output=True, text=True, env=env, timeout=120)
+    out = p.stdout + p.stderr
+    m = re.search(r"Max\s+relative error = (\S+) %", out)
+    return (float(m.group(1)) if m else None), out, p.returncode
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("needs /root/reference (build container only)")
+    subprocess.check_call(["make", "-j", "8"], cwd=HERE)
+    report, golden = {}, {}
+    ok = True
+    dump = os.path.join(HERE, "_ref", "filter_dump.jsonl")
+    for prog in TESTS:
+        e_lib, out_lib, rc1 = run(prog, "library", dump)
+        filt = json.loads(open(dump).readline())            # the filter as the program declared it
+        e_tst, _, rc2 = run(prog, "tests")
+        exact_expected = prog != "test_causal_anticausal_xy"
+        verdict = (rc1 == 0 and rc2 == 0 and e_lib is not None and e_lib <= 1e-4 and
+                   (e_tst == 0.0 if exact_expected else e_tst <= 1e-4))
+        ok &= verdict
+        report[prog] = {"max_rel_err_percent_library_order": e_lib, "max_rel_err_percent_test_loop_order": e_tst,
+                        "bit_exact_in_test_loop_order": e_tst == 0.0, "pass": verdict}
+        n = 1
+        for e in filt["extent"]:
+            n *= e
+        ref = parse_block(out_lib, "Reference", n)
+        if ref is not None and prog not in NO_GOLDEN:
+            golden[prog] = {"extent": filt["extent"], "dtype": filt["dtype"], "border": filt["border"], "input": "ones",
+                            "stages": filt["stages"], "reference_output": ref,
+                            "note": "printed by the reference test's own inline loops, 6 significant digits"}
+        print(f"{prog:32s} library order {e_lib} %   test-loop order {e_tst} %   {'ok' if verdict else 'FAIL'}")
+    report["_summary"] = {"all_pass": ok, "reference": "mit-gfx/recfilter tests/*.cpp compiled unchanged (oracle/Makefile)",
+                          "oracle": "oracle/oracle.c through oracle/capi_oracle.c",
+                          "expected": "bit exact in test-loop summation order except test_causal_anticausal_xy "
+                                      "(its check applies the scans in another, commuting, order)"}
+    json.dump(report, open(os.path.join(ROOT, "tests", "golden", "PIN_REPORT.json"), "w"), indent=1)
+    json.dump(golden, open(os.path.join(ROOT, "tests", "golden", "reference_tests.json"), "w"))
+    print("pin", "PASSED" if ok else "FAILED", "-> tests/golden/PIN_REPORT.json, reference_tests.json")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

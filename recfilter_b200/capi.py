@@ -98,6 +98,8 @@ def lib():
     L.rf_plan_stage2.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     L.rf_plan_stage_timing.argtypes = [vp, i32]
     L.rf_plan_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), i32]
+    L.rf_clock_begin.argtypes = [vp, C.POINTER(vp)]
+    L.rf_clock_end.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.rf_malloc.argtypes = [C.POINTER(vp), sz]
     L.rf_free.argtypes = [vp]
     L.rf_memcpy_h2d.argtypes = [vp, vp, sz]

@@ -1329,6 +1329,29 @@ int rf_plan_stage_times(rf_plan* plan, double* ms, long* counts, int n)
     return RF_OK;
 }
 
+int rf_clock_begin(void* stream, void** clock)
+{
+    if (!clock) return fail(RF_EINVAL, "null argument");
+    cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[2];
+    if (!ev) return fail(RF_ENOMEM, "out of host memory");
+    CUDA_TRY(cudaEventCreate(&ev[0])); CUDA_TRY(cudaEventCreate(&ev[1]));
+    CUDA_TRY(cudaEventRecord(ev[0], (cudaStream_t)stream));
+    *clock = ev;
+    return RF_OK;
+}
+
+int rf_clock_end(void* clock, void* stream, float* ms)
+{
+    if (!clock || !ms) return fail(RF_EINVAL, "null argument");
+    cudaEvent_t* ev = (cudaEvent_t*)clock;
+    CUDA_TRY(cudaEventRecord(ev[1], (cudaStream_t)stream));
+    CUDA_TRY(cudaEventSynchronize(ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(ms, ev[0], ev[1]));
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    delete[] ev;
+    return RF_OK;
+}
+
 int rf_malloc(void** p, size_t bytes) { if (!p) return fail(RF_EINVAL, "null"); CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1)); return RF_OK; }
 int rf_free(void* p) { CUDA_TRY(cudaFree(p)); return RF_OK; }
 int rf_memcpy_h2d(void* d, const void* s, size_t n) { CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyHostToDevice)); return RF_OK; }

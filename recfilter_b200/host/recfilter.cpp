@@ -1,0 +1,651 @@
+/*
+ * recfilter.cpp -- the RecFilter operator surface (include/recfilter.h) on top of the C ABI of
+ * the B200 engine (include/recfilter_b200.h).  Host C++ only: no CUDA headers, no Halide.
+ *
+ * Mirrors /root/reference/lib/recfilter.cpp (define :192-248, add_filter :260-392,
+ * set_clamped_image_border :252-258, realize :984-989, profile :991-1016, as_func :886-903),
+ * lib/split.cpp:1850-2111 (split: here it only records the tile hint -- tiling is the
+ * planner's business), lib/reorder.cpp (cascade :28-229, overlap_to_higher_order_filter
+ * :231-381) and lib/recfilter_utils.cpp (Arguments :31-112, operator+/- :274-275).
+ *
+ * The filter is a value: dimensions, element type, the array it filters (an image, or the
+ * result of another RecFilter), the scan list in add_filter order, the border mode.  realize()
+ * resolves the input chain, creates (once) a launch plan per filter through rf_plan_create and
+ * runs the plans on device-resident buffers.  There is no CPU execution path.
+ */
+#include <recfilter.h>
+#include <iir_coeff.h>
+#include <recfilter_b200.h>
+
+#include <cassert>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+using namespace Halide;
+using std::cerr;
+using std::endl;
+using std::string;
+using std::vector;
+
+// ---------------------------------------------------------------------------------------------
+// filter state
+// ---------------------------------------------------------------------------------------------
+struct ScanDef {
+    int dim;
+    bool causal;
+    vector<float> coeff;            // {b0, a1..ar}
+};
+
+struct RecFilterContents {
+    string name;
+    vector<RecFilterDim> dims;
+    Type type;
+    bool defined = false;
+    bool clamped = false;
+    bool tiled = false;
+    vector<Expr> rhs;               // pure definition as written by the user
+    // resolved input: an image (dense host buffer) or the result of another filter
+    std::shared_ptr<BufferData> src_image;
+    std::shared_ptr<RecFilterContents> src_filter;
+    vector<ScanDef> scans;
+    std::map<string, int> tiles;    // split() hints
+    rf_plan* plan = nullptr;
+    void* dev_out = nullptr;        // device result buffer, reused across realize()/profile()
+    ~RecFilterContents()
+    {
+        if (plan) rf_plan_destroy(plan);
+        if (dev_out) rf_free(dev_out);
+    }
+    size_t count() const { size_t n = 1; for (const auto& d : dims) n *= (size_t)d.num_pixels(); return n; }
+    int dim_index(const string& var) const
+    {
+        for (size_t i = 0; i < dims.size(); ++i) if (dims[i].var().name() == var) return (int)i;
+        return -1;
+    }
+};
+
+namespace {
+
+[[noreturn]] void die(const string& msg)
+{
+    cerr << msg << endl;
+    assert(false);
+    abort();                        // asserts are live in the reference build; keep failing without them
+}
+
+void engine_check(int rc, const char* what)
+{
+    if (rc != RF_OK) die(string(what) + " failed: " + rf_last_error());
+}
+
+int engine_dtype(Type t)
+{
+    if (t == Float(32)) return RF_F32;
+    if (t == Int(32)) return RF_I32;
+    if (t == UInt(32)) return RF_U32;
+    if (t == Int(16)) return RF_I16;
+    if (t == UInt(16)) return RF_U16;
+    if (t == Int(8)) return RF_I8;
+    if (t == UInt(8)) return RF_U8;
+    die("RecFilter: element type not supported by the B200 engine (float32 and 8/16/32-bit integers are)");
+}
+
+// is `e` the variable `name`, possibly wrapped in clamp(name, 0, extent-1) (an identity inside the domain)?
+bool is_identity_index(const Expr& e, const string& name, int extent)
+{
+    if (!e.defined()) return false;
+    const ExprNode& n = *e.node;
+    if (n.kind == ExprNode::Variable) return n.name == name;
+    if (n.kind == ExprNode::Max && n.args.size() == 2) {          // clamp(x, lo, hi) == max(min(x, hi), lo)
+        const Expr &inner = n.args[0], &lo = n.args[1];
+        if (lo.node->kind != ExprNode::Const || lo.node->value != 0.0) return false;
+        if (inner.node->kind != ExprNode::Min || inner.node->args.size() != 2) return false;
+        const Expr &v = inner.node->args[0], &hi = inner.node->args[1];
+        if (hi.node->kind != ExprNode::Const || hi.node->value < double(extent - 1)) return false;
+        return is_identity_index(v, name, extent);
+    }
+    return false;
+}
+
+void build_plan(RecFilterContents& c)
+{
+    if (c.plan) return;
+    rf_desc d;
+    std::memset(&d, 0, sizeof(d));
+    if (c.dims.size() > RF_MAX_DIMS) die("RecFilter: at most 4 dimensions are supported");
+    if (c.scans.size() > RF_MAX_SCANS) die("RecFilter: too many scans");
+    d.ndim = (int)c.dims.size();
+    for (int i = 0; i < d.ndim; ++i) d.extent[i] = c.dims[i].num_pixels();
+    d.dtype = engine_dtype(c.type);
+    d.border = c.clamped ? RF_BORDER_CLAMP : RF_BORDER_ZERO;
+    d.nscans = (int)c.scans.size();
+    for (int s = 0; s < d.nscans; ++s) {
+        const ScanDef& sc = c.scans[s];
+        if ((int)sc.coeff.size() - 1 > RF_MAX_ORDER) die("RecFilter: filter order above 32 is not supported");
+        d.scans[s].dim = sc.dim;
+        d.scans[s].causal = sc.causal ? 1 : 0;
+        d.scans[s].order = (int)sc.coeff.size() - 1;
+        for (size_t k = 0; k < sc.coeff.size(); ++k) d.scans[s].coeff[k] = sc.coeff[k];
+    }
+    for (int i = 0; i < d.ndim; ++i) {
+        auto it = c.tiles.find(c.dims[i].var().name());
+        d.opt.tile[i] = it == c.tiles.end() ? 0 : it->second;      // a hint: the planner picks its own register tile
+    }
+    d.opt.fuse_dims = -1;
+    d.opt.shard_dim = -1;
+    engine_check(rf_plan_create(&d, &c.plan), "rf_plan_create");
+}
+
+// Device buffer holding the input of `c` (uploads an image, or evaluates the upstream filter).
+// `owned` tells the caller whether it must free the buffer.
+void* evaluate_device(RecFilterContents& c);
+
+void* input_device(RecFilterContents& c, bool& owned)
+{
+    const size_t bytes = c.count() * (size_t)c.type.bytes();
+    if (c.src_filter) { owned = false; return evaluate_device(*c.src_filter); }
+    if (!c.src_image) die("RecFilter " + c.name + ": the input image is not set (ImageParam::set was not called?)");
+    void* dev = nullptr;
+    engine_check(rf_malloc(&dev, bytes), "rf_malloc");
+    owned = true;
+    const BufferData& b = *c.src_image;
+    bool same = b.dims == (int)c.dims.size();
+    for (int i = 0; same && i < b.dims; ++i) same = b.extent[i] == c.dims[i].num_pixels();
+    if (same) {
+        engine_check(rf_memcpy_h2d(dev, b.bytes.data(), bytes), "rf_memcpy_h2d");
+    } else {
+        // the image is larger than the filter domain: pack the [0, extent) box
+        const int eb = c.type.bytes();
+        vector<unsigned char> packed(bytes);
+        int ext[4] = { 1, 1, 1, 1 }, bext[4] = { 1, 1, 1, 1 };
+        for (size_t i = 0; i < c.dims.size(); ++i) { ext[i] = c.dims[i].num_pixels(); bext[i] = b.extent[i]; }
+        size_t o = 0;
+        for (int w = 0; w < ext[3]; ++w)
+            for (int z = 0; z < ext[2]; ++z)
+                for (int y = 0; y < ext[1]; ++y) {
+                    const size_t src = (((size_t)w * bext[2] + z) * bext[1] + y) * (size_t)bext[0];
+                    std::memcpy(&packed[o * eb], &b.bytes[src * eb], (size_t)ext[0] * eb);
+                    o += (size_t)ext[0];
+                }
+        engine_check(rf_memcpy_h2d(dev, packed.data(), bytes), "rf_memcpy_h2d");
+    }
+    return dev;
+}
+
+void* evaluate_device(RecFilterContents& c)
+{
+    if (!c.defined) die("RecFilter " + c.name + " is used before it is defined");
+    build_plan(c);
+    const size_t bytes = c.count() * (size_t)c.type.bytes();
+    if (!c.dev_out) engine_check(rf_malloc(&c.dev_out, bytes), "rf_malloc");
+    bool owned = false;
+    void* in = input_device(c, owned);
+    engine_check(rf_plan_execute(c.plan, in, c.dev_out, nullptr), "rf_plan_execute");
+    if (owned) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(in), "rf_free"); }
+    return c.dev_out;
+}
+
+// every plan of the chain ending in c, upstream first
+void collect_chain(RecFilterContents& c, vector<RecFilterContents*>& chain)
+{
+    if (c.src_filter) collect_chain(*c.src_filter, chain);
+    chain.push_back(&c);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// operators, statics
+// ---------------------------------------------------------------------------------------------
+RecFilterDimAndCausality operator+(RecFilterDim x) { return RecFilterDimAndCausality(x, true); }
+RecFilterDimAndCausality operator-(RecFilterDim x) { return RecFilterDimAndCausality(x, false); }
+
+int RecFilter::max_threads_per_cuda_warp = 0;
+int RecFilter::vectorization_width = 0;
+
+void RecFilter::set_max_threads_per_cuda_warp(int v)
+{
+    if (v % 32 != 0) die("Error: max threads per CUDA warp must be a multiple of 32");     // lib/recfilter.cpp:39-47
+    max_threads_per_cuda_warp = v;
+}
+void RecFilter::set_vectorization_width(int v) { vectorization_width = v; }
+
+// ---------------------------------------------------------------------------------------------
+// construction and definition
+// ---------------------------------------------------------------------------------------------
+RecFilter::RecFilter(string n) : contents(std::make_shared<RecFilterContents>())
+{
+    static int counter = 0;
+    contents->name = n.empty() ? "RecFilter_" + std::to_string(counter++) : n;
+}
+
+RecFilter& RecFilter::operator=(const RecFilter& r) { contents = r.contents; return *this; }
+string RecFilter::name() const { return contents->name; }
+
+RecFilterRefVar RecFilter::operator()(RecFilterDim x) { return RecFilterRefVar(*this, { x }); }
+RecFilterRefVar RecFilter::operator()(RecFilterDim x, RecFilterDim y) { return RecFilterRefVar(*this, { x, y }); }
+RecFilterRefVar RecFilter::operator()(RecFilterDim x, RecFilterDim y, RecFilterDim z) { return RecFilterRefVar(*this, { x, y, z }); }
+RecFilterRefVar RecFilter::operator()(vector<RecFilterDim> x) { return RecFilterRefVar(*this, x); }
+
+RecFilterRefExpr RecFilter::operator()(Var x) { return RecFilterRefExpr(*this, { Expr(x) }); }
+RecFilterRefExpr RecFilter::operator()(Var x, Var y) { return RecFilterRefExpr(*this, { Expr(x), Expr(y) }); }
+RecFilterRefExpr RecFilter::operator()(Var x, Var y, Var z) { return RecFilterRefExpr(*this, { Expr(x), Expr(y), Expr(z) }); }
+RecFilterRefExpr RecFilter::operator()(vector<Var> x)
+{
+    vector<Expr> a;
+    for (const Var& v : x) a.push_back(Expr(v));
+    return RecFilterRefExpr(*this, a);
+}
+RecFilterRefExpr RecFilter::operator()(Expr x) { return RecFilterRefExpr(*this, { x }); }
+RecFilterRefExpr RecFilter::operator()(Expr x, Expr y) { return RecFilterRefExpr(*this, { x, y }); }
+RecFilterRefExpr RecFilter::operator()(Expr x, Expr y, Expr z) { return RecFilterRefExpr(*this, { x, y, z }); }
+RecFilterRefExpr RecFilter::operator()(vector<Expr> x) { return RecFilterRefExpr(*this, x); }
+
+void RecFilterRefVar::operator=(Expr pure_def) { rf.define(args, { pure_def }); }
+void RecFilterRefVar::operator=(const Tuple& pure_def) { rf.define(args, pure_def.as_vector()); }
+void RecFilterRefVar::operator=(FuncRefExpr pure_def) { rf.define(args, { Expr(pure_def) }); }
+void RecFilterRefVar::operator=(vector<Expr> pure_def) { rf.define(args, pure_def); }
+RecFilterRefVar::operator Expr()
+{
+    vector<Expr> a;
+    for (const RecFilterDim& d : args) a.push_back(Expr(d));
+    return Expr(FuncRefExpr(rf.handle(), a));
+}
+Expr RecFilterRefVar::operator[](int i)
+{
+    vector<Expr> a;
+    for (const RecFilterDim& d : args) a.push_back(Expr(d));
+    return FuncRefExpr(rf.handle(), a)[i];
+}
+RecFilterRefExpr::operator Expr() { return Expr(FuncRefExpr(rf.handle(), args)); }
+Expr RecFilterRefExpr::operator[](int i) { return FuncRefExpr(rf.handle(), args)[i]; }
+
+void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
+{
+    RecFilterContents& c = *contents;
+    if (pure_args.empty() || pure_def.empty()) die("RecFilter " + c.name + ": empty definition");
+    if (pure_def.size() != 1)
+        die("RecFilter " + c.name + ": Tuple (multi-output) filters are not supported by the B200 engine yet; "
+            "filter each channel as its own RecFilter");
+    const Expr& e = pure_def[0];
+    if (!e.defined()) die("RecFilter " + c.name + ": undefined expression in the definition");
+    c.dims = pure_args;
+    c.rhs = pure_def;
+    c.scans.clear();
+    c.src_image.reset(); c.src_filter.reset();
+    if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
+
+    const ExprNode& n = *e.node;
+    bool identity = n.args.size() == c.dims.size();
+    for (size_t i = 0; identity && i < c.dims.size(); ++i)
+        identity = is_identity_index(n.args[i], c.dims[i].var().name(), c.dims[i].num_pixels());
+    if (n.kind == ExprNode::Load && identity) {
+        if (!n.buffer) die("RecFilter " + c.name + ": the image in the definition has no data");
+        for (size_t i = 0; i < c.dims.size(); ++i)
+            if (n.buffer->extent[i] < c.dims[i].num_pixels())
+                die("RecFilter " + c.name + ": the image is smaller than the filter domain");
+        c.src_image = n.buffer;
+        c.type = n.buffer->type;                                    // type of the filter = type of the RHS (lib/recfilter.cpp:197)
+    } else if (n.kind == ExprNode::Call && identity && n.filter) {
+        if (!n.filter->defined) die("RecFilter " + c.name + ": the filter called in the definition is not defined");
+        if (n.filter->dims.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch with the called filter");
+        c.src_filter = n.filter;
+        c.type = n.filter->type;
+    } else {
+        die("RecFilter " + c.name + ": the B200 engine filters an image or another filter's result indexed by the "
+            "filter's own dimensions (optionally clamped to the image); general expressions are not supported");
+    }
+    c.defined = true;
+}
+
+void RecFilter::set_clamped_image_border()
+{
+    if (contents->defined) die("Border clamping must be set before defining the filter");           // lib/recfilter.cpp:252-258
+    contents->clamped = true;
+}
+
+void RecFilter::add_filter(RecFilterDim x, vector<float> coeff) { add_filter(RecFilterDimAndCausality(x, true), coeff); }
+
+void RecFilter::add_filter(RecFilterDimAndCausality x, vector<float> coeff)
+{
+    RecFilterContents& c = *contents;
+    if (!c.defined) die("Cannot add scans to the filter " + c.name + " before it is defined");       // lib/recfilter.cpp:268-272
+    if (coeff.size() < 2) die("Cannot add scan without feed forward and feedback coefficients");     // :274-278
+    if (c.tiled) die("Cannot add scans to the filter " + c.name + " after it is tiled");
+    const int dim = c.dim_index(x.var().name());
+    if (dim < 0) die("Variable " + x.var().name() + " is not one of the dimensions of the filter " + c.name);   // :296-300
+    if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
+    c.scans.push_back({ dim, x.causal(), coeff });
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiling: recorded as a hint.  The reference rewrites the pipeline here (lib/split.cpp:1850-2080);
+// the engine's planner tiles every filter itself, with register tiles sized for B200.
+// ---------------------------------------------------------------------------------------------
+void RecFilter::split(std::map<string, int> dim_tile)
+{
+    RecFilterContents& c = *contents;
+    if (c.tiled) die("Recursive filter " + c.name + " cannot be tiled twice");                       // lib/split.cpp:1851-1854
+    if (!c.defined) die("Recursive filter " + c.name + " must be defined before it is tiled");
+    for (const auto& kv : dim_tile) {
+        const int dim = c.dim_index(kv.first);
+        if (dim < 0) die("Variable " + kv.first + " to be tiled is not one of the dimensions of the filter " + c.name);   // :1967-1971
+        bool has_scan = false;
+        for (const ScanDef& s : c.scans) has_scan = has_scan || s.dim == dim;
+        if (!has_scan) die("Dimension " + kv.first + " of the filter " + c.name + " has no scans, it cannot be tiled");    // :1879-1883
+        if (kv.second <= 0 || c.dims[dim].num_pixels() % kv.second != 0)
+            die("Tile width must be a positive divisor of the image width in dimension " + kv.first);                     // lib/recfilter.h:311
+        c.tiles[kv.first] = kv.second;
+    }
+    c.tiled = true;
+    if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
+}
+void RecFilter::split(RecFilterDim x, int tx) { split(std::map<string, int>{ { x.var().name(), tx } }); }
+void RecFilter::split(RecFilterDim x, int tx, RecFilterDim y, int ty)
+{
+    split(std::map<string, int>{ { x.var().name(), tx }, { y.var().name(), ty } });
+}
+void RecFilter::split(RecFilterDim x, int tx, RecFilterDim y, int ty, RecFilterDim z, int tz)
+{
+    split(std::map<string, int>{ { x.var().name(), tx }, { y.var().name(), ty }, { z.var().name(), tz } });
+}
+void RecFilter::split_all_dimensions(int tx)
+{
+    std::map<string, int> m;
+    for (size_t i = 0; i < contents->dims.size(); ++i) {
+        bool has_scan = false;
+        for (const ScanDef& s : contents->scans) has_scan = has_scan || s.dim == (int)i;
+        if (has_scan) m[contents->dims[i].var().name()] = tx;        // dimensions without scans stay untiled (lib/split.cpp:1888-1898)
+    }
+    split(m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cascade / overlap (lib/reorder.cpp)
+// ---------------------------------------------------------------------------------------------
+vector<RecFilter> RecFilter::cascade(vector<int> a, vector<int> b) { return cascade(vector<vector<int> >{ a, b }); }
+
+vector<RecFilter> RecFilter::cascade(vector<vector<int> > groups)
+{
+    RecFilterContents& c = *contents;
+    if (c.tiled) die("Cascading must be done before the filter " + c.name + " is tiled");
+    const int n = (int)c.scans.size();
+    vector<int> group_of(n, -1);
+    for (size_t g = 0; g < groups.size(); ++g)
+        for (int s : groups[g]) {
+            if (s < 0 || s >= n) die("Scan index " + std::to_string(s) + " in cascade() is out of range");
+            if (group_of[s] >= 0) die("Scan " + std::to_string(s) + " appears twice in cascade()");
+            group_of[s] = (int)g;
+        }
+    for (int s = 0; s < n; ++s)
+        if (group_of[s] < 0) die("Scan " + std::to_string(s) + " is missing from cascade()");
+    // scans of one dimension with opposite causality do not commute: their order must survive (lib/reorder.cpp:55-78)
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (c.scans[i].dim == c.scans[j].dim && c.scans[i].causal != c.scans[j].causal && group_of[i] > group_of[j])
+                die("Cascade would reorder scans " + std::to_string(i) + " and " + std::to_string(j) +
+                    " of opposite causality along the same dimension");
+    vector<RecFilter> out;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        RecFilter f(c.name + "_" + std::to_string(g));
+        RecFilterContents& fc = *f.contents;
+        fc.dims = c.dims; fc.type = c.type; fc.clamped = c.clamped; fc.defined = true;
+        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; }
+        else        { fc.src_filter = out[g - 1].contents; }
+        vector<int> ids = groups[g];
+        std::sort(ids.begin(), ids.end());                           // add_filter order inside a group
+        for (int s : ids) fc.scans.push_back(c.scans[s]);
+        out.push_back(f);
+    }
+    return out;
+}
+
+vector<RecFilter> RecFilter::cascade_by_dimension()
+{
+    vector<vector<int> > groups;
+    for (size_t d = 0; d < contents->dims.size(); ++d) {
+        vector<int> g;
+        for (size_t s = 0; s < contents->scans.size(); ++s) if (contents->scans[s].dim == (int)d) g.push_back((int)s);
+        if (!g.empty()) groups.push_back(g);
+    }
+    return cascade(groups);
+}
+
+vector<RecFilter> RecFilter::cascade_by_causality()
+{
+    vector<int> causal, anticausal;
+    for (size_t s = 0; s < contents->scans.size(); ++s) (contents->scans[s].causal ? causal : anticausal).push_back((int)s);
+    vector<vector<int> > groups;
+    if (!causal.empty()) groups.push_back(causal);
+    if (!anticausal.empty()) groups.push_back(anticausal);
+    return cascade(groups);
+}
+
+RecFilter RecFilter::overlap_to_higher_order_filter(RecFilter fB, string overlap_name)
+{
+    RecFilterContents& a = *contents;
+    RecFilterContents& b = *fB.contents;
+    if (a.tiled || b.tiled) die("Overlapping directive overlap() cannot be used after the filter is already tiled");
+    if (b.src_filter.get() != &a)
+        die("Filters cannot be overlapped because the input to second does not match the output of the first");
+    if (a.clamped != b.clamped) die("Filters cannot be overlapped because one clamps image border while the other does not");
+    if (a.type != b.type) die("Filters cannot be overlapped because they have different types");
+    RecFilter ab(overlap_name);
+    RecFilterContents& c = *ab.contents;
+    c.dims = a.dims; c.type = a.type; c.clamped = a.clamped; c.defined = true;
+    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter;
+    for (size_t d = 0; d < a.dims.size(); ++d) {
+        vector<const ScanDef*> sa, sb;
+        for (const ScanDef& s : a.scans) if (s.dim == (int)d) sa.push_back(&s);
+        for (const ScanDef& s : b.scans) if (s.dim == (int)d) sb.push_back(&s);
+        if (sa.size() != sb.size())
+            die("Filters cannot be overlapped because they have different num scans in dimension " + std::to_string(d));
+        for (size_t j = 0; j < sa.size(); ++j) {
+            if (sa[j]->causal != sb[j]->causal)
+                die("Filters cannot be overlapped because they have different causality in scan " + std::to_string(j) +
+                    " of dimension " + std::to_string(d));
+            vector<float> fa(sa[j]->coeff.begin() + 1, sa[j]->coeff.end());
+            vector<float> fb(sb[j]->coeff.begin() + 1, sb[j]->coeff.end());
+            vector<float> coeff = overlap_feedback_coeff(fa, fb);
+            coeff.insert(coeff.begin(), sa[j]->coeff[0] * sb[j]->coeff[0]);
+            c.scans.push_back({ (int)d, sa[j]->causal, coeff });
+        }
+    }
+    return ab;
+}
+
+// ---------------------------------------------------------------------------------------------
+// execution
+// ---------------------------------------------------------------------------------------------
+Target RecFilter::target() { return Target(); }
+void RecFilter::apply_bounds() {}
+void RecFilter::compile_jit(string) { if (contents->defined) build_plan(*contents); }
+
+Realization RecFilter::realize()
+{
+    RecFilterContents& c = *contents;
+    if (!c.defined) die("Filter " + c.name + " cannot be realized before it is defined");
+    void* dev = evaluate_device(c);
+    vector<int> ext;
+    for (const RecFilterDim& d : c.dims) ext.push_back(d.num_pixels());
+    Buffer out(c.type, ext);
+    engine_check(rf_memcpy_d2h(out.host_ptr(), dev, out.size_in_bytes()), "rf_memcpy_d2h");
+    if (const char* path = getenv("RECFILTER_DUMP_FILTER")) {
+        // one JSON line per realize(): the filter chain as declared (used to label golden vectors)
+        vector<RecFilterContents*> chain;
+        collect_chain(c, chain);
+        std::ofstream f(path, std::ios::app);
+        f << "{\"name\": \"" << c.name << "\", \"extent\": [";
+        for (size_t i = 0; i < ext.size(); ++i) f << (i ? ", " : "") << ext[i];
+        f << "], \"dtype\": \"" << (c.type.is_float() ? "float" : (c.type.is_int() ? "int" : "uint")) << c.type.bits
+          << "\", \"border\": \"" << (c.clamped ? "clamp" : "zero") << "\", \"stages\": [";
+        for (size_t g = 0; g < chain.size(); ++g) {
+            f << (g ? ", " : "") << "[";
+            for (size_t k = 0; k < chain[g]->scans.size(); ++k) {
+                const ScanDef& sc = chain[g]->scans[k];
+                f << (k ? ", " : "") << "[" << sc.dim << ", " << (sc.causal ? "true" : "false") << ", [";
+                f << std::setprecision(9);
+                for (size_t j = 0; j < sc.coeff.size(); ++j) f << (j ? ", " : "") << sc.coeff[j];
+                f << "]]";
+            }
+            f << "]";
+        }
+        f << "]}\n";
+    }
+    return Realization(vector<Buffer>{ out });
+}
+
+float RecFilter::profile(int iterations)
+{
+    RecFilterContents& c = *contents;
+    if (!c.defined) die("Filter " + c.name + " cannot be profiled before it is defined");
+    if (iterations < 1) iterations = 1;
+    vector<RecFilterContents*> chain;
+    collect_chain(c, chain);
+    for (RecFilterContents* f : chain) {
+        build_plan(*f);
+        if (!f->dev_out) engine_check(rf_malloc(&f->dev_out, f->count() * (size_t)f->type.bytes()), "rf_malloc");
+    }
+    bool owned = false;
+    void* root_in = input_device(*chain[0], owned);                   // the image stays resident: kernels only are timed
+    auto run_chain = [&]() {
+        const void* in = root_in;
+        for (RecFilterContents* f : chain) {
+            engine_check(rf_plan_execute(f->plan, in, f->dev_out, nullptr), "rf_plan_execute");
+            in = f->dev_out;
+        }
+    };
+    run_chain();                                                      // warm-up (lib/recfilter.cpp:995-997)
+    void* clock = nullptr;
+    engine_check(rf_clock_begin(nullptr, &clock), "rf_clock_begin");
+    for (int i = 0; i < iterations; ++i) run_chain();
+    float ms = 0.0f;
+    engine_check(rf_clock_end(clock, nullptr, &ms), "rf_clock_end");
+    if (owned) engine_check(rf_free(root_in), "rf_free");
+    const float per_iter = ms / float(iterations);
+    cerr << c.name << ": " << per_iter << " ms per iteration over " << iterations << " iteration(s), "
+         << (double(c.count()) / (per_iter * 1e-3) / 1e9) << " Gsamples/s" << endl;
+    return per_iter;
+}
+
+Func RecFilter::as_func() { return Func(contents, contents->name); }
+Func RecFilter::func(string func_name) { return Func(contents, func_name); }
+
+// ---------------------------------------------------------------------------------------------
+// schedules: accepted, ignored (the planner replaces lib/schedule.cpp)
+// ---------------------------------------------------------------------------------------------
+RecFilterSchedule RecFilter::intra_schedule(int) { return RecFilterSchedule(*this, { contents->name }); }
+RecFilterSchedule RecFilter::inter_schedule() { return RecFilterSchedule(*this, { contents->name }); }
+RecFilterSchedule RecFilter::full_schedule() { return RecFilterSchedule(*this, { contents->name }); }
+void RecFilter::compute_at(RecFilter) {}
+void RecFilter::compute_at(Func, Var) {}
+void RecFilter::gpu_auto_full_schedule(int) {}
+void RecFilter::gpu_auto_schedule(int)
+{
+    if (max_threads_per_cuda_warp <= 0)
+        die("Use RecFilter::set_max_threads_per_cuda_warp() to specify the maximum number of threads in each CUDA warp");   // lib/recfilter.cpp:699-704
+}
+void RecFilter::gpu_auto_inter_schedule() {}
+void RecFilter::gpu_auto_intra_schedule(int) {}
+void RecFilter::cpu_auto_schedule() {}
+void RecFilter::cpu_auto_full_schedule() {}
+void RecFilter::cpu_auto_inter_schedule() {}
+void RecFilter::cpu_auto_intra_schedule() {}
+
+VarTag RecFilter::full(int i) { return VarTag(FULL, i); }
+VarTag RecFilter::inner(int i) { return VarTag(INNER, i); }
+VarTag RecFilter::outer(int i) { return VarTag(OUTER, i); }
+VarTag RecFilter::tail() { return VarTag(TAIL); }
+VarTag RecFilter::full_scan() { return VarTag(SCAN, 0); }
+VarTag RecFilter::inner_scan() { return VarTag(SCAN, 1); }
+VarTag RecFilter::outer_scan() { return VarTag(SCAN, 2); }
+VarTag RecFilter::inner_channels() { return VarTag(CHANNEL, 0); }
+VarTag RecFilter::outer_channels() { return VarTag(CHANNEL, 1); }
+
+// ---------------------------------------------------------------------------------------------
+// printing: the filter as declared, and the launch plan when a device is present
+// ---------------------------------------------------------------------------------------------
+string RecFilter::print_synopsis() const
+{
+    const RecFilterContents& c = *contents;
+    std::ostringstream s;
+    s << "RecFilter " << c.name << "(";
+    for (size_t i = 0; i < c.dims.size(); ++i) s << (i ? ", " : "") << c.dims[i].var().name() << ":" << c.dims[i].num_pixels();
+    s << ")" << (c.clamped ? " clamped border" : " zero border");
+    if (c.src_filter) s << ", input = " << c.src_filter->name;
+    s << "\n";
+    for (size_t i = 0; i < c.scans.size(); ++i) {
+        s << "  scan " << i << ": " << (c.scans[i].causal ? "+" : "-") << c.dims[c.scans[i].dim].var().name() << " {";
+        for (size_t k = 0; k < c.scans[i].coeff.size(); ++k) s << (k ? ", " : "") << c.scans[i].coeff[k];
+        s << "}\n";
+    }
+    for (const auto& kv : c.tiles) s << "  split " << kv.first << " by " << kv.second << " (hint)\n";
+    return s.str();
+}
+string RecFilter::print_functions() const { return print_synopsis(); }
+string RecFilter::print_schedule() const
+{
+    if (contents->defined && rf_device_count() > 0) {
+        build_plan(*contents);
+        char buf[8192];
+        if (rf_plan_describe(contents->plan, buf, sizeof(buf)) == RF_OK) return string(buf);
+    }
+    return "launch plan: built at the first realize() on a CUDA device\n";
+}
+string RecFilter::print_hl_code() const { return print_synopsis(); }
+
+std::ostream& operator<<(std::ostream& s, const RecFilter& r)
+{
+    s << r.print_synopsis() << r.print_schedule();
+    return s;
+}
+std::ostream& operator<<(std::ostream& s, const RecFilterDim& f)
+{
+    s << f.var().name() << "[" << f.num_pixels() << "]";
+    return s;
+}
+std::ostream& operator<<(std::ostream& s, const Func& f)
+{
+    s << "Func " << f.name();
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// command line of the tests and apps (lib/recfilter_utils.cpp:31-112): same flags, same defaults
+// ---------------------------------------------------------------------------------------------
+Arguments::Arguments(int argc, char** argv)
+    : width(4096), max_width(4096), min_width(4096), block(32), iterations(1), nocheck(false), noschedule(false)
+{
+    const string usage = string("\nUsage\n ") + argv[0] +
+        " [-width|-w w] [-tile|-t b] [-iter i] [-nocheck] [-help]\n\n"
+        "\twidth    image width, 0 sweeps all widths and forces -nocheck [default = 4096]\n"
+        "\ttile     tile width for splitting each dimension [default = 32]\n"
+        "\tnocheck  do not check against the reference solution, forced when width=0 or iter>1 [default = false]\n"
+        "\titer     number of profiling iterations [default = 1]\n"
+        "\thelp     show this message\n";
+    auto is = [](const string& o, const char* n) { return o == string("-") + n || o == string("--") + n; };
+    try {
+        for (int i = 1; i < argc; ++i) {
+            const string o = argv[i];
+            auto value = [&](const char* what) {
+                if (i + 1 >= argc) throw std::runtime_error(string(what) + " requires an integer value");
+                return atoi(argv[++i]);
+            };
+            if (is(o, "help")) throw std::runtime_error("Showing help message");
+            else if (is(o, "nocheck")) nocheck = true;
+            else if (is(o, "iter")) iterations = value("-iter");
+            else if (is(o, "w") || is(o, "width")) width = value("-width");
+            else if (is(o, "t") || is(o, "tile")) block = value("-tile");
+            else throw std::runtime_error("Bad command line option " + o);
+        }
+        if (block <= 0 || width % block) throw std::runtime_error("Width should be a multiple of block size");
+        if (width) { max_width = width; min_width = width; }
+        else { min_width = 2 * block; max_width = (4096 / block) * block; nocheck = true; }
+        if (iterations > 1) nocheck = true;
+    } catch (std::runtime_error& e) {
+        cerr << endl << e.what() << endl << usage << endl;
+        exit(EXIT_FAILURE);
+    }
+}

@@ -1,0 +1,95 @@
+"""Strip-sharded execution of one large image / volume over the ranks of a torch.distributed job.
+
+The reference is single-GPU; this layer is new.  A 2-D image is cut into
+`world` horizontal strips (a volume into z slabs), one per rank / GPU.  Scans along the other
+dimensions are strip local.  For the scans along the cut dimension every rank
+
+  stage 1   filters its strip with zero incoming carries (rf_plan_stage1) and obtains, per line
+            crossing the cut, the order-r tail of every scan: `shard_tail_bytes` bytes
+            (2 scans x r=3 x 8192 columns x 4 B = 196 KB for the headline Gaussian);
+  exchange  ONE all-gather of those tails (NCCL over NVLink; gloo in the CPU tests);
+  stage 2   resolves the carries entering its strip from the gathered tails with the whole-strip
+            transition matrices (a tiny kernel, redundantly on every rank) and finishes the filter
+            (rf_plan_stage2).
+
+No image data crosses the link.  Batches of independent images need no exchange at all.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+from .capi import Plan, Scan
+
+
+def exchange_tails(my_tails: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """All-gather per-image tails: [B, E] on every rank -> [B, world, E], rank-major per image
+    (the layout rf_plan_stage2 expects for one image is [world, E])."""
+    if my_tails.dim() != 2:
+        raise ValueError("my_tails must be [images, tail elements]")
+    if world == 1:
+        return my_tails.unsqueeze(1).contiguous()
+    b, e = my_tails.shape
+    # concatenated output form (world*B, E): accepted by both the NCCL and the gloo backend
+    gathered = torch.empty((world * b, e), dtype=my_tails.dtype, device=my_tails.device)
+    dist.all_gather_into_tensor(gathered, my_tails.contiguous(), group=group)
+    return gathered.view(world, b, e).transpose(0, 1).contiguous()
+
+
+def strip_bounds(extent: int, world: int, rank: int, multiple: int = 1) -> tuple[int, int]:
+    """[lo, hi) of rank's strip along the cut dimension: equal strips, `multiple` keeps tile alignment."""
+    if extent % (world * multiple) != 0:
+        raise ValueError(f"extent {extent} is not divisible into {world} strips that are multiples of {multiple}")
+    n = extent // world
+    return rank * n, (rank + 1) * n
+
+
+class ShardedFilter:
+    """One rank's share of a strip-sharded filter over a batch of `batch` images.
+
+    extents    full extents, dimension 0 (contiguous) first
+    shard_dim  dimension that is cut (must carry at least one scan; not 0)
+    """
+
+    def __init__(self, extents: Sequence[int], dtype, scans: Sequence[Scan], border: str, *, rank: int, world: int,
+                 shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None):
+        self.rank, self.world, self.group, self.batch = rank, world, group, batch
+        extents = list(int(e) for e in extents)
+        self.shard_dim = len(extents) - 1 if shard_dim is None else shard_dim
+        lo, hi = strip_bounds(extents[self.shard_dim], world, rank)
+        self.local_extents = list(extents)
+        self.local_extents[self.shard_dim] = hi - lo
+        self.rows = (lo, hi)
+        kw = dict(engine=engine)
+        if world > 1:
+            kw.update(shard_dim=self.shard_dim, open_lo=rank > 0, open_hi=rank < world - 1)
+        # one plan per image in flight: a plan owns the carry workspace of its image
+        self.plans = [Plan(self.local_extents, dtype, scans, border, **kw) for _ in range(batch if world > 1 else 1)]
+        self.tail_elems = self.plans[0].shard_tail_bytes // 4 if world > 1 else 0
+        self._tails = None
+
+    def run(self, srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]):
+        """Filter `batch` strips (device tensors of the local extents)."""
+        if self.world == 1:
+            for s, d in zip(srcs, dsts):
+                self.plans[0].execute(s, d)
+            return
+        if self._tails is None:
+            dt = torch.float32 if srcs[0].dtype == torch.float32 else torch.int32
+            self._tails = torch.empty((self.batch, self.tail_elems), device=srcs[0].device, dtype=dt)
+        for i, (s, d) in enumerate(zip(srcs, dsts)):
+            self.plans[i].stage1(s, d, self._tails[i])
+        gathered = exchange_tails(self._tails, self.world, self.group)
+        for i, (s, d) in enumerate(zip(srcs, dsts)):
+            self.plans[i].stage2(s, d, gathered[i], self.world, self.rank)
+
+    @property
+    def launches_per_image(self) -> int:
+        n = self.plans[0].num_launches
+        return n + (2 if self.world > 1 else 0)     # strip resolve + the d chain runs twice
+
+    def close(self):
+        for p in self.plans:
+            p.close()
