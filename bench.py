@@ -67,12 +67,17 @@ def measured_peaks():
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q_OLD = Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
         try:
+            probe = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+            if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
+                self.Q = self.Q_OLD
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -164,6 +169,16 @@ def run_reference(args, rank: int):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic_per_launch():
+    """dram read+write bytes per launch of the dominant kernel, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    try:
+        d = json.load(open(path))
+        return float(d["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,7 +202,8 @@ def main():
     import torch
     import torch.distributed as dist
     import recfilter_b200 as rf
-    from recfilter_b200 import Plan, Scan
+    from recfilter_b200 import Scan
+    from recfilter_b200.sharded import ShardedFilter
 
     if not torch.cuda.is_available() or rf.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -197,38 +213,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N = world
     assert N == args.gpus or world == 1, "--gpus must match the torchrun world size"
-    assert H % N == 0
 
     scans = [Scan(*s) for s in scans_c3()]
     B = args.batch
-    rows = H // N
+    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B)
+    rows = flt.local_extents[1]
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     srcs = [torch.rand((rows, W), device="cuda", dtype=torch.float32, generator=gen) for _ in range(B)]
     dsts = [torch.empty_like(s) for s in srcs]
+    launches_per_image = flt.launches_per_image
 
-    if N == 1:
-        plans = [Plan((W, H), "f32", scans, "clamp")]
-        launches_per_image = plans[0].num_launches
-
-        def step():
-            for s, d in zip(srcs, dsts):
-                plans[0].execute(s, d)
-    else:
-        plans = [Plan((W, rows), "f32", scans, "clamp", shard_dim=1, open_lo=rank > 0, open_hi=rank < N - 1)
-                 for _ in range(B)]
-        tail_elems = plans[0].shard_tail_bytes // 4
-        my_tails = torch.empty((B, tail_elems), device="cuda", dtype=torch.float32)
-        all_tails = torch.empty((N, B, tail_elems), device="cuda", dtype=torch.float32)
-        gathered = torch.empty((B, N, tail_elems), device="cuda", dtype=torch.float32)
-        launches_per_image = plans[0].num_launches + 3   # carry chains run twice + strip resolve
-
-        def step():
-            for i in range(B):
-                plans[i].stage1(srcs[i], dsts[i], my_tails[i])
-            dist.all_gather_into_tensor(all_tails, my_tails)
-            gathered.copy_(all_tails.transpose(0, 1))
-            for i in range(B):
-                plans[i].stage2(srcs[i], dsts[i], gathered[i], N, rank)
+    def step():
+        flt.run(srcs, dsts)
 
     def barrier():
         if world > 1:
@@ -258,32 +254,36 @@ def main():
     samples_per_step = B * W * H
     value = args.steps * samples_per_step / (ms * 1e-3) / 1e9
 
-    # ---- per-kernel timing of the dominant kernel (separate loop, events around every launch) ------
-    for p in plans:
+    # ---- per-kernel timing: same steps, same inputs, CUDA events around every launch of the plan's stream ----
+    ksteps = max(2, min(args.steps, 5))
+    for p in flt.plans:
         p.stage_timing(True)
-    for _ in range(3):
+    for _ in range(ksteps):
         step()
     torch.cuda.synchronize()
     stage = {}
-    for p in plans:
+    for p in flt.plans:
         for k, v in p.stage_times().items():
             s = stage.setdefault(k, {"ms": 0.0, "launches": 0})
             s["ms"] += v["ms"]; s["launches"] += v["launches"]
         p.stage_timing(False)
     peak, peak_src = measured_peaks()
     fin = stage["tile_final"]
-    k4_ms = fin["ms"] / max(fin["launches"], 1)
-    alg_bytes = 8.0 * W * rows                       # 4 B read + 4 B written per sample of this rank's strip
-    achieved = alg_bytes / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+    k_ms = fin["ms"] / max(fin["launches"], 1)
+    alg_bytes = 8.0 * W * rows                       # 4 B read + 4 B written per sample of this rank's strip, per launch
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     total_stage_ms = sum(v["ms"] for v in stage.values())
-    roofline = {"bound": "hbm", "kernel": "tile_kernel<float,3,FINAL>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_us": k4_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes,
+    traffic, traffic_src = ncu_traffic_per_launch() if N == 1 else (None, None)
+    roofline = {"bound": "hbm", "kernel": "fused_tile_kernel<float,3,128,P2> (pass 2: re-scan from carries, store)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel_us": k_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": fin["ms"] / total_stage_ms if total_stage_ms else None,
-                "stage_us_per_image": {k: v["ms"] * 1e3 / (3 * B) for k, v in stage.items()},
-                "whole_filter_frac_of_peak": (8.0 * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak / 1.0}
+                "stage_us_per_image": {k: v["ms"] * 1e3 / (ksteps * B) for k, v in stage.items() if v["launches"]},
+                "kernel_timing": f"CUDA events around every launch on the plan's stream, {ksteps} steps after the timed region",
+                "whole_filter_frac_of_peak": (8.0 * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak}
 
-    # ---- end to end through the host-buffer C ABI --------------------------------------------------
+    # ---- end to end: pinned host buffers, H2D + filter + D2H inside the timed region ----------------------
     e2e_steps = max(2, min(args.steps, 5))
     host_in = [torch.empty((rows, W), dtype=torch.float32).pin_memory() for _ in range(B)]
     host_out = [torch.empty((rows, W), dtype=torch.float32).pin_memory() for _ in range(B)]
@@ -293,7 +293,7 @@ def main():
     def e2e_step():
         if N == 1:
             for hi, ho in zip(host_in, host_out):
-                plans[0].realize_ptr(hi.data_ptr(), ho.data_ptr())
+                flt.plans[0].realize_ptr(hi.data_ptr(), ho.data_ptr())      # rf_plan_execute_host: the realize() path
         else:
             for i in range(B):
                 srcs[i].copy_(host_in[i], non_blocking=True)
@@ -316,8 +316,8 @@ def main():
     e2e_value = e2e_steps * samples_per_step / dt / 1e9
     e2e = {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 4 * samples_per_step,
            "d2h_bytes_per_step": 4 * samples_per_step, "steps": e2e_steps,
-           "api": "rf_plan_execute_host (RecFilter::realize path)" if N == 1 else
-                  "pinned H2D + rf_plan_stage1/all_gather/rf_plan_stage2 + D2H"}
+           "api": "rf_plan_execute_host (RecFilter::realize path), pinned host buffers" if N == 1 else
+                  "pinned H2D + rf_plan_stage1 / all_gather / rf_plan_stage2 + D2H"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
@@ -329,7 +329,8 @@ def main():
         cpu = {"value": v_all, "unit": "Gsamples/s", "cores": th, "kind": "port",
                "single_thread_value": v_one,
                "sample": f"one full 8192x8192 image (best of 3) with {th} OpenMP threads; single-thread figure on a "
-                         "2048x8192 strip; oracle/oracle.c serial recurrence loops"}
+                         "2048x8192 strip; oracle/oracle.c serial recurrence loops (the reference's Halide x86 JIT "
+                         "cannot be built here)"}
 
     if rank == 0:
         line = {
@@ -338,13 +339,14 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step": B, "sharding": "none" if N == 1 else f"{N} row strips",
                        "l2": "every image (268 MB) exceeds L2 and a step cycles through %d distinct images" % B,
-                       "tile": 64},
+                       "tile": "128x128 register tiles (fused engine)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,
-            "hbm_roofline_pct": 100.0 * (8.0 * value) / peak,
-            "hbm_roofline_pct_of_8TBs": 100.0 * (8.0 * value) / 8000.0,
+            "hbm_roofline_pct": 100.0 * (8.0 * value) / (peak * N),
+            "hbm_roofline_pct_of_8TBs": 100.0 * (8.0 * value) / (8000.0 * N),
         }
         print(json.dumps(line), flush=True)
+    flt.close()
     if world > 1:
         dist.destroy_process_group()
 
