@@ -139,6 +139,16 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read()
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register, no scoreboard stall at the issue point
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // P1 / P2: the tile kernel.
@@ -158,6 +168,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     // the swizzle is a function of the shared-memory address: boxes must start on a 1024 B boundary
     unsigned char* tile = fsmem_raw + ((1024u - (smem_u32(fsmem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tile + NBOX * BOX_BYTES);
+    CT* cbuf = reinterpret_cast<CT*>(tile + NBOX * BOX_BYTES + 16);      // P2: carries [d scans | x scans][R][TS]
 
     const int tid = threadIdx.x;
     int64_t b = p.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
@@ -176,7 +187,27 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     }
 
     CT v[TS];
-    CT hn[R];                                                          // history of the next scan (prefetched)
+    CT hn[R];                                                          // history of the next scan
+
+    if constexpr (MODE == FMODE_P2) {
+        // every carry this thread will need (column tid, then row tid) starts its way into shared
+        // memory now, behind the tile: no load latency is left inside the scan phases
+        for (int s = 0; s < p.md; ++s) {
+            const bool closed = p.sd.causal[s] ? (bd == 0 && p.d_lo_closed) : (bd == p.nbd - 1 && p.d_hi_closed);
+            if (closed) continue;
+            const int64_t idx0 = ((int64_t)s * R * p.nbd + bd) * p.nly + o * p.Nx + (int64_t)bx * TS + tid;
+#pragma unroll
+            for (int k = 0; k < R; ++k) cp_async4(cbuf + (s * R + k) * TS + tid, p.CY + idx0 + k * (int64_t)p.nbd * p.nly);
+        }
+        for (int s = 0; s < p.mx; ++s) {
+            const bool closed = p.sx.causal[s] ? (bx == 0 && p.x_lo_closed) : (bx == p.nbx - 1 && p.x_hi_closed);
+            if (closed) continue;
+            const int64_t idx0 = ((int64_t)s * R * p.nbx + bx) * p.nlx + o * p.Nd + (int64_t)bd * TS + tid;
+#pragma unroll
+            for (int k = 0; k < R; ++k) cp_async4(cbuf + ((p.md + s) * R + k) * TS + tid, p.CX + idx0 + k * (int64_t)p.nbx * p.nlx);
+        }
+        cp_async_wait_all();           // (the wait retires behind the mbarrier wait of the tile in practice)
+    }
 
     if (p.md > 0) {
         // ---- column phase: thread tid owns column tid ----
@@ -185,13 +216,12 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         auto load_cy = [&](int s) {
             const bool causal = p.sd.causal[s] != 0;
             const bool closed = causal ? (bd == 0 && p.d_lo_closed) : (bd == p.nbd - 1 && p.d_hi_closed);
-            const int64_t idx0 = ((int64_t)s * R * p.nbd + bd) * p.nly + ly;
 #pragma unroll
-            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? p.CY[idx0 + k * kstride] : (CT)0;
+            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? cbuf[(s * R + k) * TS + tid] : (CT)0;
         };
-        load_cy(0);                                                    // in flight while the tile lands
         const uint32_t cbase = smem_u32(tile) + (tid >> 5) * BOX_BYTES + (((tid & 31) >> 2) << 4) + ((tid & 3) << 2);
         mbar_wait(bar, 0);
+        load_cy(0);
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
             uint32_t w;
@@ -234,12 +264,11 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         auto load_cx = [&](int s) {
             const bool causal = p.sx.causal[s] != 0;
             const bool closed = causal ? (bx == 0 && p.x_lo_closed) : (bx == p.nbx - 1 && p.x_hi_closed);
-            const int64_t idx0 = ((int64_t)s * R * p.nbx + bx) * p.nlx + lx;
 #pragma unroll
-            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? p.CX[idx0 + k * kstride] : (CT)0;
+            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? cbuf[((p.md + s) * R + k) * TS + tid] : (CT)0;
         };
-        load_cx(0);
         if (p.md > 0) __syncthreads(); else mbar_wait(bar, 0);
+        load_cx(0);
         const uint32_t rbase = smem_u32(tile) + tid * 128;
         const uint32_t rx = (tid & 7) << 4;
 #pragma unroll
@@ -298,12 +327,13 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// carry chain along one dimension, all scans of that dimension in one launch
-//   tail'  = T[s][j] (+ G_y * A, the cross-dimension residual) + sum_{q<s} M[q->s] * c_q[j]
+// carry chain along one dimension, all scans of that dimension in one launch (fp32 / u32 ring)
+//   tail'  = T[s][j] + sum_{q<s} M[q->s] * c_q[j]
 //   tau[j] = tail' + P[s] * c_s[j];   c_s[next tile in scan order] = tau[j]
-// blockDim = (32 lines, nseg segments of FCHAIN_L tiles).  A thread owns FCHAIN_L memory-adjacent
-// tiles of one line for every scan (so it can re-read the carries of earlier scans it wrote
-// itself); segment tails are exchanged through shared memory.
+// blockDim = (32 lines, nseg segments of L tiles).  A thread owns L memory-adjacent tiles of one
+// line for every scan (so it can re-read the carries of earlier scans it wrote itself); every
+// global load of a scan is independent of the recurrence and issued up front, the tables live
+// in shared memory, segment tails are exchanged through shared memory.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int ftile_variant(int j, int nb)
 {
@@ -313,135 +343,162 @@ __device__ __forceinline__ int ftile_variant(int j, int nb)
     return V_INTERIOR;
 }
 
-template <typename TT, int R>
-__device__ __forceinline__ void fmatvec_acc(TT (&y)[R], const TT* __restrict__ m, const TT (&x)[R])
+template <typename CT, int R>
+__device__ __forceinline__ void fmatvec_acc(CT (&y)[R], const CT* m, const CT (&x)[R])
 {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        TT acc = y[k];
+        CT acc = y[k];
 #pragma unroll
-        for (int kk = 0; kk < R; ++kk) acc = fmadd(__ldg(m + k * R + kk), x[kk], acc);
+        for (int kk = 0; kk < R; ++kk) acc = fmadd(m[k * R + kk], x[kk], acc);
         y[k] = acc;
     }
 }
 
+/*
+ * Difference basis.  A history is R consecutive outputs of a (usually low-pass) filter: nearly
+ * equal numbers, multiplied in the carry algebra by matrices whose rows are large and
+ * alternating -- in fp32 the products cancel catastrophically.  The algebra therefore runs on
+ * backward differences  (c0, c0-c1, (c0-c1)-(c1-c2), ...)  = D c.  Differences of neighbouring
+ * fp32 values are exact (or nearly), the conjugated matrices D M D^-1 (built on the host in
+ * fp64, plan.cu) have no cancelling rows, and for integer rings D is unimodular, so the
+ * summed-area tables stay bit exact.
+ */
 template <typename CT, int R>
-__global__ void __launch_bounds__(32 * 16)
+__device__ __forceinline__ void fdiff_fwd(CT (&c)[R])
+{
+#pragma unroll
+    for (int m = 1; m < R; ++m)
+#pragma unroll
+        for (int k = R - 1; k >= m; --k) c[k] = c[k - 1] - c[k];
+}
+template <typename CT, int R>
+__device__ __forceinline__ void fdiff_inv(CT (&c)[R])
+{
+#pragma unroll
+    for (int m = R - 1; m >= 1; --m)
+#pragma unroll
+        for (int k = m; k < R; ++k) c[k] = c[k - 1] - c[k];
+}
+
+template <typename CT, int R, int L>
+__global__ void __launch_bounds__(32 * 16, (L <= 4 ? 2 : 1))
 fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 {
-    typedef typename TabType<CT>::type TT;
     extern __shared__ __align__(16) unsigned char fchain_smem[];
-    TT* segtail = reinterpret_cast<TT*>(fchain_smem);       // [nseg][R][32]
+    constexpr int RR = R * R;
+    CT* sP      = reinterpret_cast<CT*>(fchain_smem);          // [V][S][R][R]
+    CT* sM      = sP + V_COUNT * p.S * RR;                      // [V][S][S][R][R]
+    CT* sPseg   = sM + V_COUNT * p.S * p.S * RR;                // [S][nseg][R][R]
+    CT* segtail = sPseg + p.S * p.nseg * RR;                    // [nseg][R][32]
 
     const int lane = threadIdx.x, g = threadIdx.y;
+    {
+        const int tid = g * 32 + lane, nthr = 32 * blockDim.y;
+        for (int i = tid; i < V_COUNT * p.S * RR; i += nthr) sP[i] = p.P[i];
+        for (int i = tid; i < V_COUNT * p.S * p.S * RR; i += nthr) sM[i] = p.M[i];
+        for (int i = tid; i < p.S * p.nseg * RR; i += nthr) sPseg[i] = p.Pseg[i];
+    }
     const int64_t l = (int64_t)blockIdx.x * 32 + lane;
     const bool valid = l < p.nl;
     const int64_t lc = valid ? l : p.nl - 1;                 // clamp: keep the barriers uniform
-    const int j0 = g * FCHAIN_L;
-    const int j1 = min(p.nb, j0 + FCHAIN_L);
+    const int j0 = g * L;
+    const int j1 = min(p.nb, j0 + L);
     const int cnt = j1 - j0;
     const int64_t plane = (int64_t)p.nb * p.nl;
-
-    // cross-dimension residual: row of G for this line (x chain of a fused pass)
-    TT gy[FMAX_SCANS][R];
-    int64_t a_base = 0;
-    if (p.A) {
-        const int64_t o = lc / p.Nd;
-        const int64_t rem = lc - o * p.Nd;
-        const int bd = (int)(rem / p.TS), i = (int)(rem - (int64_t)bd * p.TS);
-        const int vd = ftile_variant(bd, p.nbd);
-#pragma unroll
-        for (int sd = 0; sd < FMAX_SCANS; ++sd)
-#pragma unroll
-            for (int k = 0; k < R; ++k)
-                gy[sd][k] = sd < p.Sd ? __ldg(p.G + (((int64_t)vd * p.Sd + sd) * p.TS + i) * R + k) : (TT)0;
-        a_base = (o * p.nbd + bd) * (int64_t)p.nb;           // tile (o, bd, bx=0)
-    }
+    __syncthreads();
 
     for (int s = 0; s < p.S; ++s) {
         const bool causal = p.causal[s] != 0;
         const int gs = causal ? g : p.nseg - 1 - g;          // segment index in scan order
-        TT cl[FCHAIN_L][R];
-        TT tau[R];
+        CT tt[L][R];
+        CT cl[L][R];
+        CT tau[R];
+        // ---- every load of this scan, up front ----
 #pragma unroll
         for (int k = 0; k < R; ++k)
-            tau[k] = (gs == 0 && p.ext) ? (TT)p.ext[((int64_t)s * R + k) * p.nl + lc] : (TT)0;
-
+            tau[k] = (gs == 0 && p.ext) ? p.ext[((int64_t)s * R + k) * p.nl + lc] : (CT)0;
+        fdiff_fwd<CT, R>(tau);
 #pragma unroll
-        for (int t = 0; t < FCHAIN_L; ++t) {
+        for (int t = 0; t < L; ++t) {
+            const int j = causal ? j0 + t : j1 - 1 - t;
+            const int64_t base = (int64_t)j * p.nl + lc;
+#pragma unroll
+            for (int k = 0; k < R; ++k) tt[t][k] = (t < cnt) ? p.T[((int64_t)s * R + k) * plane + base] : (CT)0;
+            fdiff_fwd<CT, R>(tt[t]);
+        }
+        // ---- same-dimension residual of the earlier scans (their carries are complete) ----
+        for (int q = 0; q < s; ++q) {
+#pragma unroll
+            for (int t = 0; t < L; ++t) {
+                if (t < cnt) {
+                    const int j = causal ? j0 + t : j1 - 1 - t;
+                    const int var = ftile_variant(j, p.nb);
+                    const int64_t base = (int64_t)j * p.nl + lc;
+                    CT cq[R];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) cq[k] = p.C[((int64_t)q * R + k) * plane + base];
+                    fdiff_fwd<CT, R>(cq);
+                    fmatvec_acc<CT, R>(tt[t], sM + ((var * p.S + q) * p.S + s) * RR, cq);
+                }
+            }
+        }
+        // ---- the recurrence over this thread's tiles ----
+#pragma unroll
+        for (int t = 0; t < L; ++t) {
             if (t < cnt) {
                 const int j = causal ? j0 + t : j1 - 1 - t;
                 const int var = ftile_variant(j, p.nb);
-                const int64_t base = (int64_t)j * p.nl + lc;
-                TT tt[R];
 #pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    cl[t][k] = tau[k];
-                    tt[k] = (TT)p.T[((int64_t)s * R + k) * plane + base];
-                }
-                if (p.A) {
-                    const TT* At = p.A + (((a_base + j) * p.Sd) * p.S + s) * (R * R);
-                    for (int sd = 0; sd < p.Sd; ++sd) {
-                        const TT* Am = At + (int64_t)sd * p.S * (R * R);
+                for (int k = 0; k < R; ++k) cl[t][k] = tau[k];
+                fmatvec_acc<CT, R>(tt[t], sP + (var * p.S + s) * RR, tau);
 #pragma unroll
-                        for (int kx = 0; kx < R; ++kx) {
-                            TT acc = tt[kx];
-#pragma unroll
-                            for (int k = 0; k < R; ++k) acc = fmadd(gy[sd][k], __ldg(Am + k * R + kx), acc);
-                            tt[kx] = acc;
-                        }
-                    }
-                }
-                for (int q = 0; q < s; ++q) {
-                    TT cq[R];
-#pragma unroll
-                    for (int k = 0; k < R; ++k) cq[k] = (TT)p.C[((int64_t)q * R + k) * plane + base];
-                    fmatvec_acc<TT, R>(tt, p.M + (((int64_t)var * p.S + q) * p.S + s) * R * R, cq);
-                }
-                fmatvec_acc<TT, R>(tt, p.P + ((int64_t)var * p.S + s) * R * R, tau);
-#pragma unroll
-                for (int k = 0; k < R; ++k) tau[k] = tt[k];
+                for (int k = 0; k < R; ++k) tau[k] = tt[t][k];
             }
         }
-        // ---- exchange segment tails ----
+        // ---- exchange segment tails, prefix over the earlier segments ----
 #pragma unroll
         for (int k = 0; k < R; ++k) segtail[(gs * R + k) * 32 + lane] = tau[k];
         __syncthreads();
-        TT u[R];
+        CT u[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) u[k] = (TT)0;
+        for (int k = 0; k < R; ++k) u[k] = (CT)0;
         for (int g2 = 0; g2 < gs; ++g2) {
-            TT nu[R];
+            CT nu[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) nu[k] = segtail[(g2 * R + k) * 32 + lane];
-            fmatvec_acc<TT, R>(nu, p.Pseg + ((int64_t)s * p.nseg + g2) * R * R, u);
+            fmatvec_acc<CT, R>(nu, sPseg + (s * p.nseg + g2) * RR, u);
 #pragma unroll
             for (int k = 0; k < R; ++k) u[k] = nu[k];
         }
         if (p.tail_out && gs == p.nseg - 1 && valid) {
-            TT fin[R];
+            CT fin[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) fin[k] = tau[k];
-            fmatvec_acc<TT, R>(fin, p.Pseg + ((int64_t)s * p.nseg + gs) * R * R, u);
+            fmatvec_acc<CT, R>(fin, sPseg + (s * p.nseg + gs) * RR, u);
+            fdiff_inv<CT, R>(fin);
 #pragma unroll
-            for (int k = 0; k < R; ++k) p.tail_out[((int64_t)s * R + k) * p.nl + l] = (CT)fin[k];
+            for (int k = 0; k < R; ++k) p.tail_out[((int64_t)s * R + k) * p.nl + l] = fin[k];
         }
         // ---- add the propagated segment carry, store the carries ----
 #pragma unroll
-        for (int t = 0; t < FCHAIN_L; ++t) {
+        for (int t = 0; t < L; ++t) {
             if (t < cnt) {
                 const int j = causal ? j0 + t : j1 - 1 - t;
                 const int var = ftile_variant(j, p.nb);
                 const int64_t base = (int64_t)j * p.nl + lc;
                 if (valid) {
+                    CT c[R];
 #pragma unroll
-                    for (int k = 0; k < R; ++k)
-                        p.C[((int64_t)s * R + k) * plane + base] = (CT)(cl[t][k] + u[k]);
+                    for (int k = 0; k < R; ++k) c[k] = cl[t][k] + u[k];
+                    fdiff_inv<CT, R>(c);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) p.C[((int64_t)s * R + k) * plane + base] = c[k];
                 }
-                TT nu[R];
+                CT nu[R];
 #pragma unroll
-                for (int k = 0; k < R; ++k) nu[k] = (TT)0;
-                fmatvec_acc<TT, R>(nu, p.P + ((int64_t)var * p.S + s) * R * R, u);
+                for (int k = 0; k < R; ++k) nu[k] = (CT)0;
+                fmatvec_acc<CT, R>(nu, sP + (var * p.S + s) * RR, u);
 #pragma unroll
                 for (int k = 0; k < R; ++k) u[k] = nu[k];
             }
@@ -451,18 +508,18 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// cross-dimension residual, part 1:  A[tile][sd][sx] = sum over the tile's columns of
-//   CY_sd[k][col] * L_sx[kx][col]      (R x R per scan pair; one warp per tile)
-// The completed d carries change the d-filtered tile by G_y * CY (rows x cols); the x tails P1
-// computed on the incomplete tile therefore miss  (G_y * CY) * L_x^T = G_y * A
-// (/root/reference/lib/split.cpp:1215-1633).
+// cross-dimension residual (/root/reference/lib/split.cpp:1215-1633), one warp per tile.
+// The completed d carries change the d-filtered tile by G_d * CY (rows x cols, rank R per d
+// scan); the x tails P1 took from the incomplete tile therefore miss (G_d * CY) * L_x^T:
+//   A[sd][sx] = CY_sd (R x TS) * L_sx^T (TS x R)          reduced over the tile's columns
+//   TX[sx][kx][row] += sum_sd sum_k G[sd][row][k] * A[sd][sx][k][kx]
+// After this kernel the x chain is a plain chain.
 // ---------------------------------------------------------------------------------------------
 template <typename CT, int R, int TS>
 __global__ void __launch_bounds__(128)
 fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 {
-    typedef typename TabType<CT>::type TT;
-    constexpr int CPL = TS / 32;                 // columns per lane
+    constexpr int CPL = TS / 32;                 // columns (and rows) per lane
     const int lane = threadIdx.x & 31;
     const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -471,48 +528,80 @@ fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
     const int bx = (int)(b % p.nbx); b /= p.nbx;
     const int bd = (int)(b % p.nbd);
     const int64_t o = b / p.nbd;
-    const int vx = ftile_variant(bx, p.nbx);
+    const int vx = ftile_variant(bx, p.nbx), vd = ftile_variant(bd, p.nbd);
     const int64_t ly0 = o * p.Nx + (int64_t)bx * TS + lane;
-    const int64_t kstride = (int64_t)p.nbd * p.nly;
+    const int64_t lx0 = o * p.Nd + (int64_t)bd * TS + lane;
+    const int64_t kstride_y = (int64_t)p.nbd * p.nly;
 
-    for (int sd = 0; sd < p.Sd; ++sd) {
-        TT cy[R][CPL];
+    // the d carries of this tile's columns, every d scan (FMAX_SCANS * R * CPL registers at most)
+    CT cy[FMAX_SCANS][R][CPL];
+#pragma unroll
+    for (int sd = 0; sd < FMAX_SCANS; ++sd)
 #pragma unroll
         for (int k = 0; k < R; ++k)
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
-                cy[k][c] = (TT)p.CY[((int64_t)sd * R * p.nbd + bd) * p.nly + k * kstride + ly0 + c * 32];
-        for (int q = 0; q < p.Sx; ++q) {
-            TT acc[R][R];
+                cy[sd][k][c] = sd < p.Sd ? p.CY[((int64_t)sd * R * p.nbd + bd) * p.nly + k * kstride_y + ly0 + c * 32] : (CT)0;
+    // difference basis along k (G is stored as G * D^-1)
 #pragma unroll
-            for (int k = 0; k < R; ++k)
+    for (int sd = 0; sd < FMAX_SCANS; ++sd)
 #pragma unroll
-                for (int kx = 0; kx < R; ++kx) acc[k][kx] = (TT)0;
+        for (int c = 0; c < CPL; ++c) {
+            CT h[R];
 #pragma unroll
-            for (int kx = 0; kx < R; ++kx)
+            for (int k = 0; k < R; ++k) h[k] = cy[sd][k][c];
+            fdiff_fwd<CT, R>(h);
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const TT lv = __ldg(p.L + (((int64_t)vx * p.Sx + q) * R + kx) * TS + c * 32 + lane);
+            for (int k = 0; k < R; ++k) cy[sd][k][c] = h[k];
+        }
+
+    for (int q = 0; q < p.Sx; ++q) {
+        CT lv[R][CPL];
 #pragma unroll
-                    for (int k = 0; k < R; ++k) acc[k][kx] = fmadd(cy[k][c], lv, acc[k][kx]);
-                }
+        for (int kx = 0; kx < R; ++kx)
 #pragma unroll
-            for (int k = 0; k < R; ++k)
+            for (int c = 0; c < CPL; ++c)
+                lv[kx][c] = __ldg(p.L + (((int64_t)vx * p.Sx + q) * R + kx) * TS + c * 32 + lane);
+        CT corr[R][CPL];
 #pragma unroll
-                for (int kx = 0; kx < R; ++kx) {
-                    TT x = acc[k][kx];
+        for (int kx = 0; kx < R; ++kx)
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, off);
-                    acc[k][kx] = x;
-                }
-            if (lane == 0) {
-                TT* dst = p.A + ((w * p.Sd + sd) * p.Sx + q) * (R * R);
+            for (int c = 0; c < CPL; ++c) corr[kx][c] = (CT)0;
+#pragma unroll
+        for (int sd = 0; sd < FMAX_SCANS; ++sd) {
+            if (sd < p.Sd) {
+                CT acc[R][R];
 #pragma unroll
                 for (int k = 0; k < R; ++k)
 #pragma unroll
-                    for (int kx = 0; kx < R; ++kx) dst[k * R + kx] = acc[k][kx];
+                    for (int kx = 0; kx < R; ++kx) {
+                        CT x = (CT)0;
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) x = fmadd(cy[sd][k][c], lv[kx][c], x);
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, off);
+                        acc[k][kx] = x;                      // every lane holds A[sd][q][k][kx]
+                    }
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    CT gr[R];
+#pragma unroll
+                    for (int k = 0; k < R; ++k)
+                        gr[k] = __ldg(p.G + (((int64_t)vd * p.Sd + sd) * TS + c * 32 + lane) * R + k);
+#pragma unroll
+                    for (int kx = 0; kx < R; ++kx)
+#pragma unroll
+                        for (int k = 0; k < R; ++k) corr[kx][c] = fmadd(gr[k], acc[k][kx], corr[kx][c]);
+                }
             }
         }
+#pragma unroll
+        for (int kx = 0; kx < R; ++kx)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                CT* dst = p.TX + (((int64_t)q * R + kx) * p.nbx + bx) * p.nlx + lx0 + c * 32;
+                *dst = *dst + corr[kx][c];
+            }
     }
 }
 

@@ -19,13 +19,15 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     const int64_t nblocks = (int64_t)p.nbx * p.nbd * p.No;
     if (nblocks <= 0) return cudaSuccess;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const size_t smem = fused_tile_smem_bytes(TS);
+    const size_t smem = fused_tile_smem_bytes(TS, mode == FMODE_P2 ? (p.mx + p.md) * R * TS : 0);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e;
-        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_tile_smem_bytes(TS));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)fused_tile_smem_bytes(TS, 2 * FMAX_SCANS * R * TS));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -59,8 +61,10 @@ static cudaError_t launch_fchain_T(const FChainParams<CT, R>& p, cudaStream_t st
     if (p.nseg < 1 || p.nseg > 16) return cudaErrorInvalidConfiguration;
     const dim3 block(32, p.nseg);
     const unsigned grid = (unsigned)((p.nl + 31) / 32);
-    const size_t smem = (size_t)p.nseg * R * 32 * sizeof(typename TabType<CT>::type);
-    fchain_kernel<CT, R><<<grid, block, smem, st>>>(p);
+    const size_t smem = fchain_smem_bytes(p.S, p.nseg, R);
+    if (p.L == 4)             fchain_kernel<CT, R, 4><<<grid, block, smem, st>>>(p);
+    else if (p.L == FCHAIN_L) fchain_kernel<CT, R, FCHAIN_L><<<grid, block, smem, st>>>(p);
+    else return cudaErrorInvalidConfiguration;
     return cudaGetLastError();
 }
 

@@ -36,35 +36,39 @@ struct FusedParams {
     FusedScanTab<CT, R> sx, sd;
 };
 
+// The carry algebra of the fused path runs in the compute type (fp32 / the u32 ring): the tables
+// are generated on the host in fp64 and rounded once.
 template <typename CT, int R>
 struct FChainParams {
-    typedef typename TabType<CT>::type TT;
     const CT* T; CT* C;           // [s][k][j][l]
     int64_t nl; int nb; int S;
-    int nseg;                     // segments of FCHAIN_L tiles (threadIdx.y)
+    int nseg;                     // segments of L tiles (threadIdx.y)
+    int L;                        // tiles per thread (4 or FCHAIN_L)
     int causal[FMAX_SCANS];
-    const TT* P;                  // [V][S][R][R]
-    const TT* M;                  // [V][S][S][R][R]   (q -> s)
-    const TT* Pseg;               // [S][nseg][R][R]   product over a segment, segments in scan order
+    const CT* P;                  // [V][S][R][R]
+    const CT* M;                  // [V][S][S][R][R]   (q -> s)
+    const CT* Pseg;               // [S][nseg][R][R]   product over a segment, segments in scan order
     const CT* ext;                // [s][k][l] carry entering the first tile (shard cut) or null
     CT* tail_out;                 // [s][k][l] completed tail leaving the last tile or null
-    // cross-dimension residual (x chain of a fused pass), null otherwise
-    const TT* A;                  // [o][bd][bx][sd][sx][R][R]
-    const TT* G;                  // [V][Sd][TS][R]
-    int Sd, TS, nbd; int64_t Nd;
 };
 
 template <typename CT, int R>
 struct FCrossParams {
-    typedef typename TabType<CT>::type TT;
-    const CT* CY;                 // [sd][k][bd][ly]
-    const TT* L;                  // [V][Sx][R][TS]
-    TT* A;                        // [o][bd][bx][sd][sx][R][R]
-    int64_t Nx, No; int nbx, nbd; int Sx, Sd; int64_t nly;
+    const CT* CY;                 // [sd][k][bd][ly]   completed d carries
+    CT* TX;                       // [sx][k][bx][lx]   x tails, corrected in place
+    const CT* L;                  // [V][Sx][R][TS]
+    const CT* G;                  // [V][Sd][TS][R]
+    int64_t Nx, Nd, No; int nbx, nbd; int Sx, Sd; int64_t nly, nlx;
 };
 
+inline size_t fchain_smem_bytes(int S, int nseg, int R)
+{
+    return ((size_t)V_COUNT * S * R * R + (size_t)V_COUNT * S * S * R * R + (size_t)S * nseg * R * R + (size_t)nseg * R * 32) * 4;
+}
+
 // dynamic shared memory of one tile CTA: the swizzled boxes, alignment slack, the mbarrier
-inline size_t fused_tile_smem_bytes(int ts) { return (size_t)ts * ts * 4 + 1024 + 16; }
+// (pass 2 adds the staged carries of the tile: nscans * R * ts words)
+inline size_t fused_tile_smem_bytes(int ts, int carry_words = 0) { return (size_t)ts * ts * 4 + 1024 + 16 + (size_t)carry_words * 4; }
 
 // TMA descriptor of a dense [rows][Nx] matrix of 4-byte elements, box = 32 columns x ts rows, 128 B swizzle
 // (defined once in plan.cu; resolves cuTensorMapEncodeTiled through the runtime, no libcuda link)

@@ -665,14 +665,15 @@ struct Pass : PassBase {
 template <typename CT, int R>
 struct FusedPass : PassBase {
     using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
-    using TT = typename TabType<CT>::type;
+    using TT = CT;                  // fp32 / u32 carry algebra, tables rounded once from the fp64 host build
     FusedParams<CT, R> fp;
     int ts = 128;
     DimGeom gx, gd;
     std::vector<HostScan> sx, sd;
     bool clamp = false;
     int nsegx = 1, nsegd = 1;
-    DevBuf TX, CX, TY, CY, dA;
+    int Lx = FCHAIN_L, Ld = FCHAIN_L;            // tiles per chain thread
+    DevBuf TX, CX, TY, CY;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
     DevBuf dExt, dTailOut;
     DimTables<HT> tx_tab, td_tab;
@@ -687,7 +688,7 @@ struct FusedPass : PassBase {
 
     size_t workspace() const override
     {
-        return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dA.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
+        return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
                dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes;
     }
     int launches() const override
@@ -697,15 +698,58 @@ struct FusedPass : PassBase {
         return n;
     }
 
+    // difference basis of the fused carry algebra (fdiff_fwd / fdiff_inv in fused.cuh)
+    static void diff_fwd(HT* c) { for (int m = 1; m < R; ++m) for (int k = R - 1; k >= m; --k) c[k] = c[k - 1] - c[k]; }
+    static void diff_inv(HT* c) { for (int m = R - 1; m >= 1; --m) for (int k = m; k < R; ++k) c[k] = c[k - 1] - c[k]; }
+    // M <- D M D^-1 for every R x R block of `mats`;  G <- G D^-1 for every row of `rows` ([n][R])
+    static void conjugate_blocks(std::vector<HT>& mats)
+    {
+        for (size_t b = 0; b + (size_t)R * R <= mats.size(); b += (size_t)R * R) {
+            HT out[R * R];
+            for (int j = 0; j < R; ++j) {
+                HT v[R], w[R];
+                for (int k = 0; k < R; ++k) v[k] = (HT)(k == j ? 1 : 0);
+                diff_inv(v);
+                for (int i = 0; i < R; ++i) {
+                    HT acc = (HT)0;
+                    for (int k = 0; k < R; ++k) acc = acc + mats[b + i * R + k] * v[k];
+                    w[i] = acc;
+                }
+                diff_fwd(w);
+                for (int i = 0; i < R; ++i) out[i * R + j] = w[i];
+            }
+            std::copy(out, out + R * R, mats.begin() + b);
+        }
+    }
+    static void right_multiply_rows(std::vector<HT>& rows)
+    {
+        HT dinv[R * R];                                   // column j = D^-1 e_j
+        for (int j = 0; j < R; ++j) {
+            HT v[R];
+            for (int k = 0; k < R; ++k) v[k] = (HT)(k == j ? 1 : 0);
+            diff_inv(v);
+            for (int k = 0; k < R; ++k) dinv[k * R + j] = v[k];
+        }
+        for (size_t b = 0; b + (size_t)R <= rows.size(); b += (size_t)R) {
+            HT out[R];
+            for (int j = 0; j < R; ++j) {
+                HT acc = (HT)0;
+                for (int k = 0; k < R; ++k) acc = acc + rows[b + k] * dinv[k * R + j];
+                out[j] = acc;
+            }
+            std::copy(out, out + R, rows.begin() + b);
+        }
+    }
+
     // product of the per-tile transition matrices over each segment of FCHAIN_L tiles, segments in scan order
-    static std::vector<HT> build_fseg(const DimTables<HT>& tb, const std::vector<HostScan>& scans, int nb, int nseg)
+    static std::vector<HT> build_fseg(const DimTables<HT>& tb, const std::vector<HostScan>& scans, int nb, int nseg, int L)
     {
         const int S = (int)scans.size();
         std::vector<HT> out((size_t)S * nseg * R * R, (HT)0), tmp;
         for (int s = 0; s < S; ++s)
             for (int gs = 0; gs < nseg; ++gs) {
                 const int g = scans[s].causal ? gs : nseg - 1 - gs;          // memory segment
-                const int j0 = g * FCHAIN_L, j1 = std::min(nb, j0 + FCHAIN_L);
+                const int j0 = g * L, j1 = std::min(nb, j0 + L);
                 std::vector<HT> acc((size_t)R * R, (HT)0);
                 for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
                 for (int t = 0; t < j1 - j0; ++t) {
@@ -742,25 +786,29 @@ struct FusedPass : PassBase {
         };
         fill(fp.sx, sx); fill(fp.sd, sd);
         fp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
-        nsegx = (gx.nb + FCHAIN_L - 1) / FCHAIN_L;
-        nsegd = (gd.nb + FCHAIN_L - 1) / FCHAIN_L;
+        Lx = gx.nb <= 64 ? 4 : FCHAIN_L;
+        Ld = gd.nb <= 64 ? 4 : FCHAIN_L;
+        nsegx = (gx.nb + Lx - 1) / Lx;
+        nsegd = (gd.nb + Ld - 1) / Ld;
 
         if (fp.mx > 0) {
             build_dim_tables<HT>(tx_tab, sx, gx, R, clamp, 0, 0, true, true, ts);
+            conjugate_blocks(tx_tab.P); conjugate_blocks(tx_tab.M);
             CUDA_TRY((upload<HT, TT>(dPx, tx_tab.P)));
             CUDA_TRY((upload<HT, TT>(dMx, tx_tab.M)));
             CUDA_TRY((upload<HT, TT>(dL, tx_tab.L)));
-            CUDA_TRY((upload<HT, TT>(dPsegx, build_fseg(tx_tab, sx, gx.nb, nsegx))));
+            CUDA_TRY((upload<HT, TT>(dPsegx, build_fseg(tx_tab, sx, gx.nb, nsegx, Lx))));
             const size_t n = (size_t)fp.mx * R * gx.nb * fp.nlx * sizeof(CT);
             CUDA_TRY(TX.alloc(n)); CUDA_TRY(CX.alloc(n));
             CUDA_TRY(cudaMemset(CX.p, 0, n));
         }
         if (fp.md > 0) {
             build_dim_tables<HT>(td_tab, sd, gd, R, clamp, 0, 0, true, true, ts);
+            conjugate_blocks(td_tab.P); conjugate_blocks(td_tab.M); right_multiply_rows(td_tab.G);
             CUDA_TRY((upload<HT, TT>(dPd, td_tab.P)));
             CUDA_TRY((upload<HT, TT>(dMd, td_tab.M)));
             CUDA_TRY((upload<HT, TT>(dG, td_tab.G)));
-            CUDA_TRY((upload<HT, TT>(dPsegd, build_fseg(td_tab, sd, gd.nb, nsegd))));
+            CUDA_TRY((upload<HT, TT>(dPsegd, build_fseg(td_tab, sd, gd.nb, nsegd, Ld))));
             const size_t n = (size_t)fp.md * R * gd.nb * fp.nly * sizeof(CT);
             CUDA_TRY(TY.alloc(n)); CUDA_TRY(CY.alloc(n));
             CUDA_TRY(cudaMemset(CY.p, 0, n));
@@ -773,8 +821,6 @@ struct FusedPass : PassBase {
                 if (rc) return rc;
             }
         }
-        if (fp.mx > 0 && fp.md > 0)
-            CUDA_TRY(dA.alloc((size_t)gx.nb * gd.nb * No * fp.md * fp.mx * R * R * sizeof(TT)));
         fp.TX = (CT*)TX.p; fp.CX = (const CT*)CX.p; fp.TY = (CT*)TY.p; fp.CY = (const CT*)CY.p;
         return RF_OK;
     }
@@ -800,16 +846,13 @@ struct FusedPass : PassBase {
         cp.nl = xdim ? fp.nlx : fp.nly;
         cp.nb = g.nb; cp.S = g.nscans;
         cp.nseg = xdim ? nsegx : nsegd;
+        cp.L = xdim ? Lx : Ld;
         for (int s = 0; s < g.nscans; ++s) cp.causal[s] = scans[s].causal;
         cp.P = (const TT*)(xdim ? dPx.p : dPd.p);
         cp.M = (const TT*)(xdim ? dMx.p : dMd.p);
         cp.Pseg = (const TT*)(xdim ? dPsegx.p : dPsegd.p);
         cp.ext = xdim ? nullptr : (const CT*)ext_d;
         cp.tail_out = xdim ? nullptr : (CT*)tail_out_d;
-        if (xdim && cross_needed()) {
-            cp.A = (const TT*)dA.p; cp.G = (const TT*)dG.p;
-            cp.Sd = fp.md; cp.TS = ts; cp.nbd = gd.nb; cp.Nd = fp.Nd;
-        }
         cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
         CUDA_TRY((FLaunch<CT, R>::chain(cp, st)));
         if (timer) timer->end(st, ev);
@@ -824,8 +867,9 @@ struct FusedPass : PassBase {
         if (cross_needed()) {
             FCrossParams<CT, R> cr;
             std::memset(&cr, 0, sizeof(cr));
-            cr.CY = (const CT*)CY.p; cr.L = (const TT*)dL.p; cr.A = (TT*)dA.p;
-            cr.Nx = fp.Nx; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md; cr.nly = fp.nly;
+            cr.CY = (const CT*)CY.p; cr.TX = (CT*)TX.p; cr.L = (const TT*)dL.p; cr.G = (const TT*)dG.p;
+            cr.Nx = fp.Nx; cr.Nd = fp.Nd; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md;
+            cr.nly = fp.nly; cr.nlx = fp.nlx;
             cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
             CUDA_TRY((FLaunch<CT, R>::cross(cr, ts, st)));
             if (timer) timer->end(st, ev);

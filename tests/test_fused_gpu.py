@@ -54,7 +54,7 @@ def test_c3_gaussian(oracle, shape, border):
     a = rand_image(shape, np.float32, 300)
     out = check_float(oracle, a, C3, border)
     gen = run(a, C3, border, engine="generic")
-    assert rel_err(out, gen) < 8e-6
+    assert rel_err(out, gen) < 2 * TOL      # two independent fp32 evaluations, each within TOL of the truth
 
 
 def test_c3_full_size_8192(oracle):
@@ -206,7 +206,7 @@ def test_strip_sharded_gaussian(oracle, engine, nshards):
         truth = oracle.apply_filter(a.astype(np.float64), C3, border, threads=8)
         assert rel_err(out, truth) <= TOL
         whole = run(a, C3, border, engine=engine)
-        assert rel_err(out, whole) < 4e-6
+        assert rel_err(out, whole) < TOL        # different tile cuts: two independent fp32 evaluations
 
 
 @pytest.mark.parametrize("engine", ["fused", "generic"])
