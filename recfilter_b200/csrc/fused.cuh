@@ -381,81 +381,180 @@ __device__ __forceinline__ void fdiff_inv(CT (&c)[R])
         for (int k = m; k < R; ++k) c[k] = c[k - 1] - c[k];
 }
 
-template <typename CT, int R, int L>
-__global__ void __launch_bounds__(32 * 16, (L <= 4 ? 2 : 1))
+/*
+ * fchain_kernel -- carries of every scan of one dimension, one launch.
+ *
+ * The kernel is a chain of dependent steps executed once per warp by few warps, so it is bound
+ * by instruction issue: it is written for a SMALL instruction footprint and few instructions
+ * per tile (a fully unrolled, register-resident version spent most of its time in
+ * instruction-cache misses).  The loop over tiles stays rolled and the per-tile data of a thread
+ * lives in shared memory, R consecutive words per (tile, thread) so that every access is a
+ * pointer plus an immediate:
+ *   sT  this scan's tails, brought in by cp.async (no registers, no scoreboard stall)
+ *   sC  the completed carries of every scan (difference basis), re-used by the same-dimension
+ *       residual of the later scans and by the second sweep
+ *   sA  (x chain) the A matrices of the block's tile row, see fcrossA_kernel.
+ * The matrices of the current tile variant are held in registers and reloaded only when the
+ * variant changes (first / last tile of the line).  Offsets are 32-bit (checked by the planner).
+ */
+template <typename CT, int R>
+__device__ __forceinline__ void fload_mat(CT (&m)[R * R], const CT* src)
+{
+#pragma unroll
+    for (int i = 0; i < R * R; ++i) m[i] = src[i];
+}
+template <typename CT, int R>
+__device__ __forceinline__ void fmatvec_acc_reg(CT (&y)[R], const CT (&m)[R * R], const CT (&x)[R])
+{
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        CT acc = y[k];
+#pragma unroll
+        for (int kk = 0; kk < R; ++kk) acc = fmadd(m[k * R + kk], x[kk], acc);
+        y[k] = acc;
+    }
+}
+
+template <typename CT, int R, int S>
+__global__ void __launch_bounds__(32 * 16, 1)
 fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 {
     extern __shared__ __align__(16) unsigned char fchain_smem[];
     constexpr int RR = R * R;
-    CT* sP      = reinterpret_cast<CT*>(fchain_smem);          // [V][S][R][R]
-    CT* sM      = sP + V_COUNT * p.S * RR;                      // [V][S][S][R][R]
-    CT* sPseg   = sM + V_COUNT * p.S * p.S * RR;                // [S][nseg][R][R]
-    CT* segtail = sPseg + p.S * p.nseg * RR;                    // [nseg][R][32]
-
+    constexpr int NQ = S > 1 ? S - 1 : 1;
+    const int L = p.L, nseg = p.nseg;
     const int lane = threadIdx.x, g = threadIdx.y;
-    {
-        const int tid = g * 32 + lane, nthr = 32 * blockDim.y;
-        for (int i = tid; i < V_COUNT * p.S * RR; i += nthr) sP[i] = p.P[i];
-        for (int i = tid; i < V_COUNT * p.S * p.S * RR; i += nthr) sM[i] = p.M[i];
-        for (int i = tid; i < p.S * p.nseg * RR; i += nthr) sPseg[i] = p.Pseg[i];
-    }
+    const int nthr = 32 * nseg, tid = g * 32 + lane;
+    CT* sA      = reinterpret_cast<CT*>(fchain_smem);          // [nb][S][R][sdk]  (16-byte aligned rows)
+    CT* sP      = sA + (p.A ? (size_t)p.nb * S * R * p.sdk : 0); // [V][S][R][R]
+    CT* sM      = sP + V_COUNT * S * RR;                        // [V][S][S][R][R]
+    CT* sPseg   = sM + V_COUNT * S * S * RR;                    // [S][nseg][R][R]
+    CT* segtail = sPseg + S * nseg * RR;                        // [nseg][R][32]
+    CT* sT      = segtail + nseg * R * 32;                      // [L][nthr][R]
+    CT* sC      = sT + (size_t)L * R * nthr;                    // [S][L][nthr][R]
+
     const int64_t l = (int64_t)blockIdx.x * 32 + lane;
     const bool valid = l < p.nl;
     const int64_t lc = valid ? l : p.nl - 1;                 // clamp: keep the barriers uniform
     const int j0 = g * L;
-    const int j1 = min(p.nb, j0 + L);
-    const int cnt = j1 - j0;
-    const int64_t plane = (int64_t)p.nb * p.nl;
+    const int cnt = min(p.nb, j0 + L) - j0;                  // tiles of this thread (>= 1)
+    const uint32_t nl32 = (uint32_t)p.nl, plane32 = (uint32_t)p.nb * nl32;
+    const int slot = nthr * R;                               // words per tile slot
+    CT* const myT = sT + tid * R;
+    CT* const myC = sC + tid * R;
+    const CT* const Tl = p.T + lc;
+    CT* const Cl = p.C + lc;
+
+    auto fetch_tails = [&](int s) {                          // tails of scan s -> sT, asynchronously
+        uint32_t off = (uint32_t)s * R * plane32 + (uint32_t)j0 * nl32;
+        CT* dst = myT;
+        for (int m = 0; m < cnt; ++m, off += nl32, dst += slot)
+#pragma unroll
+            for (int k = 0; k < R; ++k) cp_async4(dst + k, Tl + (off + k * plane32));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // x chain with the cross-dimension residual folded in: this line is row `row` of tile row bd
+    CT grow[FMAX_SCANS * R];
+#pragma unroll
+    for (int n = 0; n < FMAX_SCANS * R; ++n) grow[n] = (CT)0;
+    const int sdk4 = p.A ? (p.sdk >> 2) : 0;
+    if (p.A) {
+        const int64_t o = lc / p.Nd;
+        const int rem = (int)(lc - o * p.Nd);
+        const int bd = rem / p.ts, row = rem - bd * p.ts;
+        const int vd = ftile_variant(bd, p.nbd);
+        // every line of the block lies in the same tile row: stage its A matrices (16 bytes per copy)
+        const int64_t o0 = ((int64_t)blockIdx.x * 32) / p.Nd;
+        const int bd0 = (int)((((int64_t)blockIdx.x * 32) - o0 * p.Nd) / p.ts);
+        const CT* Arow = p.A + (o0 * p.nbd + bd0) * (int64_t)p.nb * S * R * p.sdk;
+        const int n16 = p.nb * S * R * sdk4;
+        for (int i = tid; i < n16; i += nthr)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(sA + i * 4)), "l"(Arow + (int64_t)i * 4) : "memory");
+#pragma unroll
+        for (int n = 0; n < FMAX_SCANS * R; ++n)
+            if (n < p.Sd * R) grow[n] = __ldg(p.G + (((int64_t)vd * p.Sd + n / R) * p.ts + row) * R + n % R);
+    }
+    fetch_tails(0);
+    for (int i = tid; i < V_COUNT * S * RR; i += nthr) sP[i] = p.P[i];
+    for (int i = tid; i < V_COUNT * S * S * RR; i += nthr) sM[i] = p.M[i];
+    for (int i = tid; i < S * nseg * RR; i += nthr) sPseg[i] = p.Pseg[i];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    for (int s = 0; s < p.S; ++s) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
         const bool causal = p.causal[s] != 0;
-        const int gs = causal ? g : p.nseg - 1 - g;          // segment index in scan order
-        CT tt[L][R];
-        CT cl[L][R];
+        const int gs = causal ? g : nseg - 1 - g;            // segment index in scan order
+        const int m0 = causal ? 0 : cnt - 1, dm = causal ? 1 : -1;
+        const int dslot = dm * slot;
         CT tau[R];
-        // ---- every load of this scan, up front ----
 #pragma unroll
         for (int k = 0; k < R; ++k)
             tau[k] = (gs == 0 && p.ext) ? p.ext[((int64_t)s * R + k) * p.nl + lc] : (CT)0;
         fdiff_fwd<CT, R>(tau);
-#pragma unroll
-        for (int t = 0; t < L; ++t) {
-            const int j = causal ? j0 + t : j1 - 1 - t;
-            const int64_t base = (int64_t)j * p.nl + lc;
-#pragma unroll
-            for (int k = 0; k < R; ++k) tt[t][k] = (t < cnt) ? p.T[((int64_t)s * R + k) * plane + base] : (CT)0;
-            fdiff_fwd<CT, R>(tt[t]);
-        }
-        // ---- same-dimension residual of the earlier scans (their carries are complete) ----
-        for (int q = 0; q < s; ++q) {
-#pragma unroll
-            for (int t = 0; t < L; ++t) {
-                if (t < cnt) {
-                    const int j = causal ? j0 + t : j1 - 1 - t;
-                    const int var = ftile_variant(j, p.nb);
-                    const int64_t base = (int64_t)j * p.nl + lc;
-                    CT cq[R];
-#pragma unroll
-                    for (int k = 0; k < R; ++k) cq[k] = p.C[((int64_t)q * R + k) * plane + base];
-                    fdiff_fwd<CT, R>(cq);
-                    fmatvec_acc<CT, R>(tt[t], sM + ((var * p.S + q) * p.S + s) * RR, cq);
-                }
-            }
-        }
-        // ---- the recurrence over this thread's tiles ----
-#pragma unroll
-        for (int t = 0; t < L; ++t) {
-            if (t < cnt) {
-                const int j = causal ? j0 + t : j1 - 1 - t;
+        if (s > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+        CT Pm[RR];
+        CT Mm[NQ][RR];
+        int cur = -1;
+        // ---- first sweep, scan order: provisional carries (zero carry into the segment) ----
+        {
+            int j = j0 + m0;
+            const CT* tp = myT + m0 * slot;
+            CT* cp = myC + (s * L + m0) * slot;
+            const CT* ap = sA + ((size_t)j * S + s) * R * p.sdk;
+            const int da = dm * S * R * p.sdk;
+            for (int t = 0; t < cnt; ++t, j += dm, tp += dslot, cp += dslot, ap += da) {
                 const int var = ftile_variant(j, p.nb);
+                if (var != cur) {                             // warp-uniform, at most three times per sweep
+                    cur = var;
+                    fload_mat<CT, R>(Pm, sP + (var * S + s) * RR);
 #pragma unroll
-                for (int k = 0; k < R; ++k) cl[t][k] = tau[k];
-                fmatvec_acc<CT, R>(tt[t], sP + (var * p.S + s) * RR, tau);
+                    for (int q = 0; q < NQ; ++q)
+                        if (q < s) fload_mat<CT, R>(Mm[q], sM + ((var * S + q) * S + s) * RR);
+                }
+                CT x[R];
 #pragma unroll
-                for (int k = 0; k < R; ++k) tau[k] = tt[t][k];
+                for (int k = 0; k < R; ++k) x[k] = tp[k];
+                if (p.A) {                                    // tail += G_row * A[tile]
+#pragma unroll
+                    for (int kx = 0; kx < R; ++kx) {
+                        CT acc = x[kx];
+#pragma unroll
+                        for (int i4 = 0; i4 < (FMAX_SCANS * R + 3) / 4; ++i4) {
+                            if (i4 < sdk4) {
+                                const uint4 qv = *reinterpret_cast<const uint4*>(ap + kx * p.sdk + i4 * 4);
+                                const CT a4[4] = { *reinterpret_cast<const CT*>(&qv.x), *reinterpret_cast<const CT*>(&qv.y),
+                                                   *reinterpret_cast<const CT*>(&qv.z), *reinterpret_cast<const CT*>(&qv.w) };
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (i4 * 4 + e < FMAX_SCANS * R) acc = fmadd(grow[(i4 * 4 + e) % (FMAX_SCANS * R)], a4[e], acc);
+                            }
+                        }
+                        x[kx] = acc;
+                    }
+                }
+                fdiff_fwd<CT, R>(x);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {                // same-dimension residual of the earlier scans
+                    if (q < s) {
+                        CT c[R];
+                        const CT* cqp = cp - (s - q) * L * slot;
+#pragma unroll
+                        for (int k = 0; k < R; ++k) c[k] = cqp[k];
+                        fmatvec_acc_reg<CT, R>(x, Mm[q], c);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < R; ++k) cp[k] = tau[k];
+                fmatvec_acc_reg<CT, R>(x, Pm, tau);
+#pragma unroll
+                for (int k = 0; k < R; ++k) tau[k] = x[k];
             }
         }
+        if (s + 1 < S) fetch_tails(s + 1);                   // sT entries of this thread are consumed
+
         // ---- exchange segment tails, prefix over the earlier segments ----
 #pragma unroll
         for (int k = 0; k < R; ++k) segtail[(gs * R + k) * 32 + lane] = tau[k];
@@ -467,38 +566,41 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
             CT nu[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) nu[k] = segtail[(g2 * R + k) * 32 + lane];
-            fmatvec_acc<CT, R>(nu, sPseg + (s * p.nseg + g2) * RR, u);
+            fmatvec_acc<CT, R>(nu, sPseg + (s * nseg + g2) * RR, u);
 #pragma unroll
             for (int k = 0; k < R; ++k) u[k] = nu[k];
         }
-        if (p.tail_out && gs == p.nseg - 1 && valid) {
+        if (p.tail_out && gs == nseg - 1 && valid) {
             CT fin[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) fin[k] = tau[k];
-            fmatvec_acc<CT, R>(fin, sPseg + (s * p.nseg + gs) * RR, u);
+            fmatvec_acc<CT, R>(fin, sPseg + (s * nseg + gs) * RR, u);
             fdiff_inv<CT, R>(fin);
 #pragma unroll
             for (int k = 0; k < R; ++k) p.tail_out[((int64_t)s * R + k) * p.nl + l] = fin[k];
         }
-        // ---- add the propagated segment carry, store the carries ----
-#pragma unroll
-        for (int t = 0; t < L; ++t) {
-            if (t < cnt) {
-                const int j = causal ? j0 + t : j1 - 1 - t;
+        // ---- second sweep: add the propagated segment carry, store the carries ----
+        {
+            int j = j0 + m0;
+            CT* cp = myC + (s * L + m0) * slot;
+            uint32_t off = (uint32_t)s * R * plane32 + (uint32_t)j * nl32;
+            const uint32_t doff = (uint32_t)dm * nl32;
+            cur = -1;
+            for (int t = 0; t < cnt; ++t, j += dm, cp += dslot, off += doff) {
                 const int var = ftile_variant(j, p.nb);
-                const int64_t base = (int64_t)j * p.nl + lc;
+                if (var != cur) { cur = var; fload_mat<CT, R>(Pm, sP + (var * S + s) * RR); }
+                CT c[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) { c[k] = cp[k] + u[k]; cp[k] = c[k]; }
+                fdiff_inv<CT, R>(c);
                 if (valid) {
-                    CT c[R];
 #pragma unroll
-                    for (int k = 0; k < R; ++k) c[k] = cl[t][k] + u[k];
-                    fdiff_inv<CT, R>(c);
-#pragma unroll
-                    for (int k = 0; k < R; ++k) p.C[((int64_t)s * R + k) * plane + base] = c[k];
+                    for (int k = 0; k < R; ++k) Cl[off + k * plane32] = c[k];
                 }
                 CT nu[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) nu[k] = (CT)0;
-                fmatvec_acc<CT, R>(nu, sP + (var * p.S + s) * RR, u);
+                fmatvec_acc_reg<CT, R>(nu, Pm, u);
 #pragma unroll
                 for (int k = 0; k < R; ++k) u[k] = nu[k];
             }
@@ -508,18 +610,18 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// cross-dimension residual (/root/reference/lib/split.cpp:1215-1633), one warp per tile.
+// cross-dimension residual (/root/reference/lib/split.cpp:1215-1633), part 1: one warp per tile.
 // The completed d carries change the d-filtered tile by G_d * CY (rows x cols, rank R per d
 // scan); the x tails P1 took from the incomplete tile therefore miss (G_d * CY) * L_x^T:
-//   A[sd][sx] = CY_sd (R x TS) * L_sx^T (TS x R)          reduced over the tile's columns
-//   TX[sx][kx][row] += sum_sd sum_k G[sd][row][k] * A[sd][sx][k][kx]
-// After this kernel the x chain is a plain chain.
+//   A[tile][sx][kx][sd*R+k] = sum over the tile's columns of CY_sd[k][col] * L_sx[kx][col]
+// Part 2 (TX[sx][kx][row] += sum_sd sum_k G[sd][row][k] * A[..]) is applied by the x chain while
+// it loads its tails, so the x tails are never rewritten in memory.
 // ---------------------------------------------------------------------------------------------
 template <typename CT, int R, int TS>
 __global__ void __launch_bounds__(128)
-fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
+fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 {
-    constexpr int CPL = TS / 32;                 // columns (and rows) per lane
+    constexpr int CPL = TS / 32;                 // columns per lane
     const int lane = threadIdx.x & 31;
     const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -528,12 +630,11 @@ fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
     const int bx = (int)(b % p.nbx); b /= p.nbx;
     const int bd = (int)(b % p.nbd);
     const int64_t o = b / p.nbd;
-    const int vx = ftile_variant(bx, p.nbx), vd = ftile_variant(bd, p.nbd);
+    const int vx = ftile_variant(bx, p.nbx);
     const int64_t ly0 = o * p.Nx + (int64_t)bx * TS + lane;
-    const int64_t lx0 = o * p.Nd + (int64_t)bd * TS + lane;
     const int64_t kstride_y = (int64_t)p.nbd * p.nly;
 
-    // the d carries of this tile's columns, every d scan (FMAX_SCANS * R * CPL registers at most)
+    // the d carries of this tile's columns, every d scan, in the difference basis (G is stored as G * D^-1)
     CT cy[FMAX_SCANS][R][CPL];
 #pragma unroll
     for (int sd = 0; sd < FMAX_SCANS; ++sd)
@@ -542,7 +643,6 @@ fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
                 cy[sd][k][c] = sd < p.Sd ? p.CY[((int64_t)sd * R * p.nbd + bd) * p.nly + k * kstride_y + ly0 + c * 32] : (CT)0;
-    // difference basis along k (G is stored as G * D^-1)
 #pragma unroll
     for (int sd = 0; sd < FMAX_SCANS; ++sd)
 #pragma unroll
@@ -555,6 +655,7 @@ fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
             for (int k = 0; k < R; ++k) cy[sd][k][c] = h[k];
         }
 
+    CT* Aout = p.A + w * ((int64_t)p.Sx * R * p.sdk);
     for (int q = 0; q < p.Sx; ++q) {
         CT lv[R][CPL];
 #pragma unroll
@@ -562,46 +663,25 @@ fcross_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
                 lv[kx][c] = __ldg(p.L + (((int64_t)vx * p.Sx + q) * R + kx) * TS + c * 32 + lane);
-        CT corr[R][CPL];
 #pragma unroll
-        for (int kx = 0; kx < R; ++kx)
+        for (int kx = 0; kx < R; ++kx) {
+            CT mine = (CT)0;                                 // lane n keeps entry n = sd * R + k
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) corr[kx][c] = (CT)0;
+            for (int sd = 0; sd < FMAX_SCANS; ++sd) {
+                if (sd < p.Sd) {
 #pragma unroll
-        for (int sd = 0; sd < FMAX_SCANS; ++sd) {
-            if (sd < p.Sd) {
-                CT acc[R][R];
-#pragma unroll
-                for (int k = 0; k < R; ++k)
-#pragma unroll
-                    for (int kx = 0; kx < R; ++kx) {
+                    for (int k = 0; k < R; ++k) {
                         CT x = (CT)0;
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) x = fmadd(cy[sd][k][c], lv[kx][c], x);
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, off);
-                        acc[k][kx] = x;                      // every lane holds A[sd][q][k][kx]
+                        if (lane == sd * R + k) mine = x;
                     }
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    CT gr[R];
-#pragma unroll
-                    for (int k = 0; k < R; ++k)
-                        gr[k] = __ldg(p.G + (((int64_t)vd * p.Sd + sd) * TS + c * 32 + lane) * R + k);
-#pragma unroll
-                    for (int kx = 0; kx < R; ++kx)
-#pragma unroll
-                        for (int k = 0; k < R; ++k) corr[kx][c] = fmadd(gr[k], acc[k][kx], corr[kx][c]);
                 }
             }
+            if (lane < p.sdk) Aout[((int64_t)q * R + kx) * p.sdk + lane] = mine;
         }
-#pragma unroll
-        for (int kx = 0; kx < R; ++kx)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                CT* dst = p.TX + (((int64_t)q * R + kx) * p.nbx + bx) * p.nlx + lx0 + c * 32;
-                *dst = *dst + corr[kx][c];
-            }
     }
 }
 

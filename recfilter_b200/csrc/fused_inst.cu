@@ -54,18 +54,35 @@ static cudaError_t launch_fused_tile_T(const FusedParams<CT, R>& p, const void* 
     return cudaErrorInvalidValue;
 }
 
+template <typename CT, int R, int S>
+static cudaError_t launch_fchain_S(const FChainParams<CT, R>& p, unsigned grid, dim3 block, size_t smem, cudaStream_t st)
+{
+    static size_t attr_bytes = 0;
+    if (smem > 48u * 1024u && smem > attr_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(fchain_kernel<CT, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_bytes = smem;
+    }
+    fchain_kernel<CT, R, S><<<grid, block, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <typename CT, int R>
 static cudaError_t launch_fchain_T(const FChainParams<CT, R>& p, cudaStream_t st)
 {
     if (p.nl <= 0 || p.nb <= 0) return cudaSuccess;
-    if (p.nseg < 1 || p.nseg > 16) return cudaErrorInvalidConfiguration;
+    if (p.nseg < 1 || p.nseg > 16 || p.S < 1 || p.S > FMAX_SCANS || p.L < 1) return cudaErrorInvalidConfiguration;
     const dim3 block(32, p.nseg);
     const unsigned grid = (unsigned)((p.nl + 31) / 32);
-    const size_t smem = fchain_smem_bytes(p.S, p.nseg, R);
-    if (p.L == 4)             fchain_kernel<CT, R, 4><<<grid, block, smem, st>>>(p);
-    else if (p.L == FCHAIN_L) fchain_kernel<CT, R, FCHAIN_L><<<grid, block, smem, st>>>(p);
-    else return cudaErrorInvalidConfiguration;
-    return cudaGetLastError();
+    const size_t smem = fchain_smem_bytes(p.S, p.nseg, R, p.L, p.nb, p.A ? p.sdk : 0);
+    if (smem > 227u * 1024u) return cudaErrorInvalidConfiguration;
+    if ((int64_t)p.S * R * p.nb * p.nl > 0x7fffffffLL) return cudaErrorInvalidConfiguration;   // 32-bit offsets
+    switch (p.S) {
+    case 1: return launch_fchain_S<CT, R, 1>(p, grid, block, smem, st);
+    case 2: return launch_fchain_S<CT, R, 2>(p, grid, block, smem, st);
+    case 3: return launch_fchain_S<CT, R, 3>(p, grid, block, smem, st);
+    default: return launch_fchain_S<CT, R, 4>(p, grid, block, smem, st);
+    }
 }
 
 template <typename CT, int R>
@@ -74,8 +91,8 @@ static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& p, int ts, cudaStr
     const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
     if (ntiles <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((ntiles + 3) / 4);
-    if (ts == 128)     fcross_kernel<CT, R, 128><<<grid, 128, 0, st>>>(p);
-    else if (ts == 64) fcross_kernel<CT, R, 64><<<grid, 128, 0, st>>>(p);
+    if (ts == 128)     fcrossA_kernel<CT, R, 128><<<grid, 128, 0, st>>>(p);
+    else if (ts == 64) fcrossA_kernel<CT, R, 64><<<grid, 128, 0, st>>>(p);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

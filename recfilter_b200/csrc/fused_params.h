@@ -50,20 +50,26 @@ struct FChainParams {
     const CT* Pseg;               // [S][nseg][R][R]   product over a segment, segments in scan order
     const CT* ext;                // [s][k][l] carry entering the first tile (shard cut) or null
     CT* tail_out;                 // [s][k][l] completed tail leaving the last tile or null
+    // x chain only: cross-dimension residual applied while the tails are loaded (null: plain chain)
+    const CT* A;                  // [tile][s][kx][sdk]  from fcrossA_kernel
+    const CT* G;                  // [V][Sd][ts][R]      d response to a unit carry (times D^-1)
+    int64_t Nd; int nbd; int Sd; int ts; int sdk;
 };
 
 template <typename CT, int R>
 struct FCrossParams {
     const CT* CY;                 // [sd][k][bd][ly]   completed d carries
-    CT* TX;                       // [sx][k][bx][lx]   x tails, corrected in place
+    CT* A;                        // [tile][sx][kx][sdk]  sdk = Sd * R rounded up to a multiple of 4
     const CT* L;                  // [V][Sx][R][TS]
-    const CT* G;                  // [V][Sd][TS][R]
-    int64_t Nx, Nd, No; int nbx, nbd; int Sx, Sd; int64_t nly, nlx;
+    int64_t Nx, Nd, No; int nbx, nbd; int Sx, Sd; int sdk; int64_t nly, nlx;
 };
 
-inline size_t fchain_smem_bytes(int S, int nseg, int R)
+// dynamic shared memory of one chain block (layout in fchain_kernel)
+inline size_t fchain_smem_bytes(int S, int nseg, int R, int L, int nb, int sdk_if_cross)
 {
-    return ((size_t)V_COUNT * S * R * R + (size_t)V_COUNT * S * S * R * R + (size_t)S * nseg * R * R + (size_t)nseg * R * 32) * 4;
+    const size_t nthr = 32u * (size_t)nseg;
+    return ((size_t)nb * S * R * sdk_if_cross + (size_t)V_COUNT * S * R * R + (size_t)V_COUNT * S * S * R * R +
+            (size_t)S * nseg * R * R + (size_t)nseg * R * 32 + (size_t)L * R * nthr + (size_t)S * L * R * nthr) * 4;
 }
 
 // dynamic shared memory of one tile CTA: the swizzled boxes, alignment slack, the mbarrier

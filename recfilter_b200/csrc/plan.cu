@@ -658,6 +658,29 @@ struct Pass : PassBase {
     }
 };
 
+// tiles per chain thread: long segments cost fewer instructions per line, short ones expose more
+// threads (and need less shared memory when a dimension has many scans)
+static int fchain_pick_L(int nb, int S)
+{
+    if (const char* e = getenv("RFB_CHAIN_L")) { const int v = atoi(e); if ((v == 4 || v == FCHAIN_L) && nb <= 16 * v) return v; }
+    return (nb <= 32 || (S > 2 && nb <= 64)) ? 4 : FCHAIN_L;
+}
+// does the carry chain of a fused pass fit the shared memory of one CTA?
+static bool fchain_fits(int R, int Sx, int Sd, int nbx, int nbd)
+{
+    const size_t limit = 227u * 1024u;
+    if (Sd > 0) {
+        const int L = fchain_pick_L(nbd, Sd);
+        if (fchain_smem_bytes(Sd, (nbd + L - 1) / L, R, L, nbd, 0) > limit) return false;
+    }
+    if (Sx > 0) {
+        const int L = fchain_pick_L(nbx, Sx);
+        const int sdk = Sd > 0 ? ((Sd * R + 3) / 4) * 4 : 0;
+        if (fchain_smem_bytes(Sx, (nbx + L - 1) / L, R, L, nbx, sdk) > limit) return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused fast path (kernels in fused.cuh): full TS x TS tiles, unit-feed-forward scans,
 // d scans before x scans, one carry-chain launch per dimension
@@ -673,11 +696,12 @@ struct FusedPass : PassBase {
     bool clamp = false;
     int nsegx = 1, nsegd = 1;
     int Lx = FCHAIN_L, Ld = FCHAIN_L;            // tiles per chain thread
-    DevBuf TX, CX, TY, CY;
+    DevBuf TX, CX, TY, CY, dA;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
     DevBuf dExt, dTailOut;
     DimTables<HT> tx_tab, td_tab;
     std::unique_ptr<ShardResolver<CT, R>> resolver;
+    int sdk() const { return ((fp.md * R + 3) / 4) * 4; }     // entries of one A row, padded for 128-bit loads
 
     bool x_needs() const { return gx.nscans > 0 && gx.nb > 1; }
     bool d_needs() const { return gd.nscans > 0 && (gd.nb > 1 || !gd.lo_closed || !gd.hi_closed); }
@@ -688,7 +712,7 @@ struct FusedPass : PassBase {
 
     size_t workspace() const override
     {
-        return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
+        return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dA.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
                dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes;
     }
     int launches() const override
@@ -786,8 +810,8 @@ struct FusedPass : PassBase {
         };
         fill(fp.sx, sx); fill(fp.sd, sd);
         fp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
-        Lx = gx.nb <= 64 ? 4 : FCHAIN_L;
-        Ld = gd.nb <= 64 ? 4 : FCHAIN_L;
+        Lx = fchain_pick_L(gx.nb, fp.mx);
+        Ld = fchain_pick_L(gd.nb, fp.md);
         nsegx = (gx.nb + Lx - 1) / Lx;
         nsegd = (gd.nb + Ld - 1) / Ld;
 
@@ -821,6 +845,11 @@ struct FusedPass : PassBase {
                 if (rc) return rc;
             }
         }
+        if (cross_needed()) {
+            const size_t n = (size_t)gx.nb * gd.nb * No * fp.mx * R * sdk() * sizeof(CT);
+            CUDA_TRY(dA.alloc(n));
+            CUDA_TRY(cudaMemset(dA.p, 0, n));
+        }
         fp.TX = (CT*)TX.p; fp.CX = (const CT*)CX.p; fp.TY = (CT*)TY.p; fp.CY = (const CT*)CY.p;
         return RF_OK;
     }
@@ -853,6 +882,10 @@ struct FusedPass : PassBase {
         cp.Pseg = (const TT*)(xdim ? dPsegx.p : dPsegd.p);
         cp.ext = xdim ? nullptr : (const CT*)ext_d;
         cp.tail_out = xdim ? nullptr : (CT*)tail_out_d;
+        if (xdim && cross_needed()) {
+            cp.A = (const CT*)dA.p; cp.G = (const TT*)dG.p;
+            cp.Nd = fp.Nd; cp.nbd = gd.nb; cp.Sd = fp.md; cp.ts = ts; cp.sdk = sdk();
+        }
         cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
         CUDA_TRY((FLaunch<CT, R>::chain(cp, st)));
         if (timer) timer->end(st, ev);
@@ -867,8 +900,9 @@ struct FusedPass : PassBase {
         if (cross_needed()) {
             FCrossParams<CT, R> cr;
             std::memset(&cr, 0, sizeof(cr));
-            cr.CY = (const CT*)CY.p; cr.TX = (CT*)TX.p; cr.L = (const TT*)dL.p; cr.G = (const TT*)dG.p;
+            cr.CY = (const CT*)CY.p; cr.A = (CT*)dA.p; cr.L = (const TT*)dL.p;
             cr.Nx = fp.Nx; cr.Nd = fp.Nd; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md;
+            cr.sdk = sdk();
             cr.nly = fp.nly; cr.nlx = fp.nlx;
             cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
             CUDA_TRY((FLaunch<CT, R>::cross(cr, ts, st)));
@@ -1035,6 +1069,8 @@ static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx,
         if (!sx.empty() && nbx > 16 * FCHAIN_L) continue;
         if (!sd.empty() && nbd > 16 * FCHAIN_L) continue;
         if (nbx * nbd * No > 0x7fffffffLL) continue;
+        if (!fchain_fits(plan->R, (int)sx.size(), (int)sd.size(), (int)nbx, (int)nbd)) continue;
+        if ((int64_t)std::max(sx.size(), sd.size()) * plan->R * std::max(nbx * Nd, nbd * Nx) * No > 0x7fffffffLL) continue;   // 32-bit carry offsets
         if (!force && ts == 128 && nbx * nbd * No < 2 * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
             (sx.empty() || Nx / 64 <= 16 * FCHAIN_L) && (sd.empty() || Nd / 64 <= 16 * FCHAIN_L))
             continue;                       // small problem: smaller tiles fill the machine better
