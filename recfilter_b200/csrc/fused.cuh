@@ -97,6 +97,15 @@ __device__ __forceinline__ void scan_line(CT (&v)[N], CT (&h)[R], const CT (&a)[
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): the kernels of a pass are launched back to back with
+// cudaLaunchAttributeProgrammaticStreamSerialization; a kernel lets its successor start launching
+// right away (its CTAs fill the SMs as ours retire and run their prologue) and itself waits for
+// the complete, flushed predecessor before it touches anything the predecessor wrote.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait()              { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG / UTMASTG / SYNCS)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,8 +187,10 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     const int x0 = bx * TS;
     const int y0 = (int)(o * p.Nd + (int64_t)bd * TS);                  // row of the [No*Nd][Nx] matrix
 
+    pdl_launch_dependents();
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
+    pdl_wait();                                   // the input (and, for P2, the carries) may come from the previous kernel
     if (tid == 0) {
         mbar_expect_tx(bar, NBOX * BOX_BYTES);
 #pragma unroll
@@ -454,6 +465,11 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // static tables first (they do not depend on the previous kernel) ...
+    pdl_launch_dependents();
+    for (int i = tid; i < V_COUNT * S * RR; i += nthr) sP[i] = p.P[i];
+    for (int i = tid; i < V_COUNT * S * S * RR; i += nthr) sM[i] = p.M[i];
+    for (int i = tid; i < S * nseg * RR; i += nthr) sPseg[i] = p.Pseg[i];
     // x chain with the cross-dimension residual folded in: this line is row `row` of tile row bd
     CT grow[FMAX_SCANS * R];
 #pragma unroll
@@ -464,6 +480,13 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
         const int rem = (int)(lc - o * p.Nd);
         const int bd = rem / p.ts, row = rem - bd * p.ts;
         const int vd = ftile_variant(bd, p.nbd);
+#pragma unroll
+        for (int n = 0; n < FMAX_SCANS * R; ++n)
+            if (n < p.Sd * R) grow[n] = __ldg(p.G + (((int64_t)vd * p.Sd + n / R) * p.ts + row) * R + n % R);
+    }
+    // ... then everything the previous kernel produced
+    pdl_wait();
+    if (p.A) {
         // every line of the block lies in the same tile row: stage its A matrices (16 bytes per copy)
         const int64_t o0 = ((int64_t)blockIdx.x * 32) / p.Nd;
         const int bd0 = (int)((((int64_t)blockIdx.x * 32) - o0 * p.Nd) / p.ts);
@@ -471,14 +494,8 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
         const int n16 = p.nb * S * R * sdk4;
         for (int i = tid; i < n16; i += nthr)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(sA + i * 4)), "l"(Arow + (int64_t)i * 4) : "memory");
-#pragma unroll
-        for (int n = 0; n < FMAX_SCANS * R; ++n)
-            if (n < p.Sd * R) grow[n] = __ldg(p.G + (((int64_t)vd * p.Sd + n / R) * p.ts + row) * R + n % R);
     }
     fetch_tails(0);
-    for (int i = tid; i < V_COUNT * S * RR; i += nthr) sP[i] = p.P[i];
-    for (int i = tid; i < V_COUNT * S * S * RR; i += nthr) sM[i] = p.M[i];
-    for (int i = tid; i < S * nseg * RR; i += nthr) sPseg[i] = p.Pseg[i];
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
@@ -625,6 +642,8 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
     const int lane = threadIdx.x & 31;
     const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
     const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
     if (w >= ntiles) return;
     int64_t b = w;
     const int bx = (int)(b % p.nbx); b /= p.nbx;

@@ -4,6 +4,9 @@
  * parallel.
  */
 #include <type_traits>
+#include <utility>
+#include <cstring>
+#include <cstdlib>
 #include "fused.cuh"
 
 #ifndef RFB_R
@@ -11,6 +14,21 @@
 #endif
 
 namespace rfb {
+
+// launch with programmatic stream serialization (PDL, see fused.cuh); RFB_NO_PDL=1 turns it off
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    static const bool use_pdl = !(getenv("RFB_NO_PDL") && atoi(getenv("RFB_NO_PDL")) != 0);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 template <typename CT, int R, int TS>
 static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void* in, void* out, int mode,
@@ -36,13 +54,12 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     cudaError_t e = make_tile_map(&tm_in, in, p.Nx, p.No * p.Nd, TS, is_float);
     if (e != cudaSuccess) return e;
     if (mode == FMODE_P1) {
-        fused_tile_kernel<CT, R, TS, FMODE_P1><<<(unsigned)nblocks, TS, smem, st>>>(p, tm_in, tm_in);
+        return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P1>, dim3((unsigned)nblocks), dim3(TS), smem, st, p, tm_in, tm_in);
     } else {
         e = make_tile_map(&tm_out, out, p.Nx, p.No * p.Nd, TS, is_float);
         if (e != cudaSuccess) return e;
-        fused_tile_kernel<CT, R, TS, FMODE_P2><<<(unsigned)nblocks, TS, smem, st>>>(p, tm_in, tm_out);
+        return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P2>, dim3((unsigned)nblocks), dim3(TS), smem, st, p, tm_in, tm_out);
     }
-    return cudaGetLastError();
 }
 
 template <typename CT, int R>
@@ -63,8 +80,7 @@ static cudaError_t launch_fchain_S(const FChainParams<CT, R>& p, unsigned grid, 
         if (e != cudaSuccess) return e;
         attr_bytes = smem;
     }
-    fchain_kernel<CT, R, S><<<grid, block, smem, st>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(fchain_kernel<CT, R, S>, dim3(grid), block, smem, st, p);
 }
 
 template <typename CT, int R>
@@ -91,10 +107,9 @@ static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& p, int ts, cudaStr
     const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
     if (ntiles <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((ntiles + 3) / 4);
-    if (ts == 128)     fcrossA_kernel<CT, R, 128><<<grid, 128, 0, st>>>(p);
-    else if (ts == 64) fcrossA_kernel<CT, R, 64><<<grid, 128, 0, st>>>(p);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (ts == 128) return launch_pdl(fcrossA_kernel<CT, R, 128>, dim3(grid), dim3(128), 0, st, p);
+    if (ts == 64)  return launch_pdl(fcrossA_kernel<CT, R, 64>, dim3(grid), dim3(128), 0, st, p);
+    return cudaErrorInvalidValue;
 }
 
 #define RFB_CAT_(a, b) a##b
