@@ -65,54 +65,60 @@ def measured_peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    Q_OLD = Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
+    """SM clock and throttle reasons, polled through NVML every few ms while the timed region runs
+    (the region lasts tens of ms: `nvidia-smi -lms` would not produce a sample in time)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.thread, self.samples, self.reasons, self.stop_flag = index, None, [], set(), False
+        self.max_mhz, self.err = None, None
 
     def start(self):
         try:
-            probe = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
-            if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
-                self.Q = self.Q_OLD
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    idx = self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:          # noqa: BLE001
+            self.err = f"{type(e).__name__}: {e}"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:       # noqa: BLE001  (older binding name)
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:      # noqa: BLE001
+                self.err = f"{type(e).__name__}: {e}"
+                return
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": [],
+                    "error": self.err or "no samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(self.reasons), "source": "NVML polled every 2 ms during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,7 +188,7 @@ def ncu_traffic_per_launch():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -292,8 +298,8 @@ def main():
 
     def e2e_step():
         if N == 1:
-            for hi, ho in zip(host_in, host_out):
-                flt.plans[0].realize_ptr(hi.data_ptr(), ho.data_ptr())      # rf_plan_execute_host: the realize() path
+            # rf_plan_execute_host_batch: the realize() path for a batch of frames, copies pipelined with the kernels
+            flt.plans[0].realize_batch_ptr([h.data_ptr() for h in host_in], [h.data_ptr() for h in host_out])
         else:
             for i in range(B):
                 srcs[i].copy_(host_in[i], non_blocking=True)
@@ -316,7 +322,8 @@ def main():
     e2e_value = e2e_steps * samples_per_step / dt / 1e9
     e2e = {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 4 * samples_per_step,
            "d2h_bytes_per_step": 4 * samples_per_step, "steps": e2e_steps,
-           "api": "rf_plan_execute_host (RecFilter::realize path), pinned host buffers" if N == 1 else
+           "api": "rf_plan_execute_host_batch (RecFilter::realize path, one call per step of %d images; H2D / kernels / D2H "
+                  "pipelined over 3 device buffers), pinned host buffers" % B if N == 1 else
                   "pinned H2D + rf_plan_stage1 / all_gather / rf_plan_stage2 + D2H"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------

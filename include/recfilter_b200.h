@@ -129,6 +129,16 @@ int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stre
 /* Host buffers: H2D + execute + D2H, synchronous (the realize() path). */
 int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host);
 
+/*
+ * n independent images/signals of the plan's shape in host memory (the app loops that call
+ * realize() once per frame, e.g. /root/reference/lib/recfilter.cpp:991-1016 with a fresh input):
+ * upload, filter and download are pipelined over three device buffers, so the H2D copy of image
+ * i+1 and the D2H copy of image i-1 overlap the kernels of image i.  Pinned host memory
+ * (rf_malloc_host) is needed for the copies to overlap; pageable memory works but serialises.
+ * Synchronous: all outputs are complete on return.
+ */
+int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host, void* const* out_host);
+
 /* Time `iters` executions on device-resident data with CUDA events (ms per iteration). */
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter);
 

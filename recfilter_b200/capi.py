@@ -91,6 +91,7 @@ def lib():
     L.rf_plan_describe.argtypes = [vp, C.c_char_p, sz]
     L.rf_plan_execute.argtypes = [vp, vp, vp, vp]
     L.rf_plan_execute_host.argtypes = [vp, vp, vp]
+    L.rf_plan_execute_host_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.rf_plan_profile.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_float)]
     L.rf_plan_shard_tail_bytes.argtypes = [vp]
     L.rf_plan_shard_tail_bytes.restype = sz
@@ -259,6 +260,25 @@ class Plan:
     def realize_ptr(self, in_host_ptr: int, out_host_ptr: int):
         _check(lib().rf_plan_execute_host(self._h, C.c_void_p(in_host_ptr), C.c_void_p(out_host_ptr)),
                "rf_plan_execute_host")
+
+    def realize_batch_ptr(self, in_host_ptrs, out_host_ptrs):
+        """n images in host memory (pinned for overlap): pipelined H2D / filter / D2H, rf_plan_execute_host_batch."""
+        n = len(in_host_ptrs)
+        if n != len(out_host_ptrs):
+            raise RecFilterError("realize_batch_ptr: input and output lists differ in length")
+        ins = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in in_host_ptrs])
+        outs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in out_host_ptrs])
+        _check(lib().rf_plan_execute_host_batch(self._h, n, ins, outs), "rf_plan_execute_host_batch")
+
+    def realize_batch(self, arrays):
+        """List of host arrays in, list of host arrays out (see realize_batch_ptr)."""
+        ins = [np.ascontiguousarray(a, dtype=self.np_dtype) for a in arrays]
+        for a in ins:
+            if a.size != self.size:
+                raise RecFilterError(f"array has {a.size} samples, plan expects {self.size}")
+        outs = [np.empty_like(a) for a in ins]
+        self.realize_batch_ptr([a.ctypes.data for a in ins], [o.ctypes.data for o in outs])
+        return outs
 
     def profile(self, src, dst, iters: int) -> float:
         ms = C.c_float()

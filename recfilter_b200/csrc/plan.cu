@@ -973,6 +973,21 @@ struct rf_plan {
     std::string text;
     DevBuf stage;            // 32-bit staging for 8/16-bit integer filters
     StageTimer timer;
+    // host-buffer path (rf_plan_execute_host / _batch): three device image buffers cycled through
+    // upload -> filter (in place) -> download on three streams, created on first use
+    struct HostPipe {
+        static constexpr int NB = 3;
+        DevBuf buf[NB];
+        cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+        cudaEvent_t up[NB] = {}, done[NB] = {}, down[NB] = {};
+        bool ready = false;
+        ~HostPipe()
+        {
+            if (!ready) return;
+            for (int i = 0; i < NB; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(done[i]); cudaEventDestroy(down[i]); }
+            cudaStreamDestroy(s_up); cudaStreamDestroy(s_run); cudaStreamDestroy(s_down);
+        }
+    } pipe;
 };
 
 static int widen_in(rf_plan* plan, const void* in_dev, cudaStream_t st)
@@ -1310,19 +1325,59 @@ int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stre
     return RF_OK;
 }
 
-int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host)
+static int host_pipe_init(rf_plan* plan, int nbuf)
+{
+    rf_plan::HostPipe& hp = plan->pipe;
+    const size_t bytes = (size_t)plan->total * plan->elem_bytes;
+    if (!hp.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_up, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_down, cudaStreamNonBlocking));
+        for (int i = 0; i < rf_plan::HostPipe::NB; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.up[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.down[i], cudaEventDisableTiming));
+        }
+        hp.ready = true;
+    }
+    for (int i = 0; i < nbuf && i < rf_plan::HostPipe::NB; ++i)
+        if (!hp.buf[i].p) CUDA_TRY(hp.buf[i].alloc(bytes));
+    return RF_OK;
+}
+
+int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host, void* const* out_host)
 {
     if (!plan) return fail(RF_EINVAL, "null plan");
-    if (plan->total == 0) return RF_OK;
-    if (!in_host || !out_host) return fail(RF_EINVAL, "null buffer");
-    const size_t bytes = (size_t)plan->total * plan->elem_bytes;
-    DevBuf buf;
-    CUDA_TRY(buf.alloc(bytes));
-    CUDA_TRY(cudaMemcpy(buf.p, in_host, bytes, cudaMemcpyHostToDevice));
-    int rc = rf_plan_execute(plan, buf.p, buf.p, nullptr);
+    if (n < 0 || (n > 0 && (!in_host || !out_host))) return fail(RF_EINVAL, "bad argument");
+    if (plan->total == 0 || n == 0) return RF_OK;
+    for (int i = 0; i < n; ++i)
+        if (!in_host[i] || !out_host[i]) return fail(RF_EINVAL, "null buffer");
+    constexpr int NB = rf_plan::HostPipe::NB;
+    int rc = host_pipe_init(plan, n < NB ? n : NB);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(out_host, buf.p, bytes, cudaMemcpyDeviceToHost));
+    rf_plan::HostPipe& hp = plan->pipe;
+    const size_t bytes = (size_t)plan->total * plan->elem_bytes;
+    // image i: upload on s_up, filter in place on s_run, download on s_down; the upload of image i+1 and the
+    // download of image i-1 run beside the kernels of image i (PCIe is full duplex)
+    for (int i = 0; i < n; ++i) {
+        const int b = i % NB;
+        if (i >= NB) CUDA_TRY(cudaStreamWaitEvent(hp.s_up, hp.down[b], 0));      // buffer b is free again
+        CUDA_TRY(cudaMemcpyAsync(hp.buf[b].p, in_host[i], bytes, cudaMemcpyHostToDevice, hp.s_up));
+        CUDA_TRY(cudaEventRecord(hp.up[b], hp.s_up));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.up[b], 0));
+        if ((rc = rf_plan_execute(plan, hp.buf[b].p, hp.buf[b].p, hp.s_run))) return rc;
+        CUDA_TRY(cudaEventRecord(hp.done[b], hp.s_run));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_down, hp.done[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(out_host[i], hp.buf[b].p, bytes, cudaMemcpyDeviceToHost, hp.s_down));
+        CUDA_TRY(cudaEventRecord(hp.down[b], hp.s_down));
+    }
+    CUDA_TRY(cudaStreamSynchronize(hp.s_down));
     return RF_OK;
+}
+
+int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host)
+{
+    return rf_plan_execute_host_batch(plan, 1, &in_host, &out_host);
 }
 
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter)

@@ -219,3 +219,17 @@ def test_strip_sharded_sat_u32_and_volume(oracle, engine):
     out = run_sharded(v, sc, "zero", 4, 2, engine)
     truth = oracle.apply_filter(v.astype(np.float64), sc, threads=8)
     assert rel_err(out, truth) <= TOL
+
+
+def test_host_batch_pipeline_matches_single_calls(oracle):
+    """rf_plan_execute_host_batch cycles three device buffers over three streams: five images go
+    round the ring more than once and must equal one realize() per image."""
+    plan = Plan((512, 384), "f32", [Scan(*s) for s in C3], "clamp", engine="fused")
+    imgs = [rand_image((384, 512), np.float32, 900 + i) for i in range(5)]
+    single = [plan.realize(a) for a in imgs]
+    batch = plan.realize_batch(imgs)
+    for s, b in zip(single, batch):
+        np.testing.assert_array_equal(s, b)
+    truth = oracle.apply_filter(imgs[4].astype(np.float64), C3, "clamp", threads=8)
+    assert rel_err(batch[4], truth) <= TOL
+    plan.close()
