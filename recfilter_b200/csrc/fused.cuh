@@ -188,6 +188,13 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     const int y0 = (int)(o * p.Nd + (int64_t)bd * TS);                  // row of the [No*Nd][Nx] matrix
 
     pdl_launch_dependents();
+    // does an x scan start at a closed border in the row of this thread?  (signal mode: a row continues the
+    // previous row of the same signal, so only the first / last row of a signal is closed)
+    const int64_t sig_row = p.signal ? ((int64_t)y0 + tid) % p.sig_rows : 0;
+    auto x_closed = [&](bool causal) -> bool {
+        if (p.signal) return causal ? (sig_row == 0) : (sig_row == p.sig_rows - 1);
+        return causal ? (bx == 0 && p.x_lo_closed) : (bx == p.nbx - 1 && p.x_hi_closed);
+    };
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     pdl_wait();                                   // the input (and, for P2, the carries) may come from the previous kernel
@@ -211,7 +218,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             for (int k = 0; k < R; ++k) cp_async4(cbuf + (s * R + k) * TS + tid, p.CY + idx0 + k * (int64_t)p.nbd * p.nly);
         }
         for (int s = 0; s < p.mx; ++s) {
-            const bool closed = p.sx.causal[s] ? (bx == 0 && p.x_lo_closed) : (bx == p.nbx - 1 && p.x_hi_closed);
+            const bool closed = x_closed(p.sx.causal[s] != 0);
             if (closed) continue;
             const int64_t idx0 = ((int64_t)s * R * p.nbx + bx) * p.nlx + o * p.Nd + (int64_t)bd * TS + tid;
 #pragma unroll
@@ -273,8 +280,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         const int64_t lx = o * p.Nd + (int64_t)bd * TS + tid;
         const int64_t kstride = (int64_t)p.nbx * p.nlx;
         auto load_cx = [&](int s) {
-            const bool causal = p.sx.causal[s] != 0;
-            const bool closed = causal ? (bx == 0 && p.x_lo_closed) : (bx == p.nbx - 1 && p.x_hi_closed);
+            const bool closed = x_closed(p.sx.causal[s] != 0);
 #pragma unroll
             for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? cbuf[((p.md + s) * R + k) * TS + tid] : (CT)0;
         };
@@ -294,7 +300,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         }
         for (int s = 0; s < p.mx; ++s) {
             const bool causal = p.sx.causal[s] != 0;
-            const bool closed = causal ? (bx == 0 && p.x_lo_closed) : (bx == p.nbx - 1 && p.x_hi_closed);
+            const bool closed = x_closed(causal);
             CT a[R + 1];
 #pragma unroll
             for (int k = 0; k <= R; ++k) a[k] = p.sx.a[s][k];
@@ -441,22 +447,49 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
     CT* sM      = sP + V_COUNT * S * RR;                        // [V][S][S][R][R]
     CT* sPseg   = sM + V_COUNT * S * S * RR;                    // [S][nseg][R][R]
     CT* segtail = sPseg + S * nseg * RR;                        // [nseg][R][32]
-    CT* sT      = segtail + nseg * R * 32;                      // [L][nthr][R]
-    CT* sC      = sT + (size_t)L * R * nthr;                    // [S][L][nthr][R]
+    // per-tile work arrays: slab m holds the R-vector of every thread's m-th tile.  Thread (g, lane) sits at word
+    // (g*32 + lane) * RS + g*8 of a slab, RS odd, and slabs are `slot` = 1 (mod 32) words apart: a thread's own
+    // accesses, and the panel copies of the strided layout (consecutive tiles = consecutive m, then g), are both
+    // free of bank conflicts
+    constexpr int RS = fchain_rs(R);
+    const int slot = fchain_slot_words(nseg, R);
+    CT* sT      = segtail + nseg * R * 32;                      // [L][slot]
+    CT* sC      = S == 1 ? sT : sT + (size_t)L * slot;          // [S][L][slot]  (one scan: carries overwrite the tails)
 
     const int64_t l = (int64_t)blockIdx.x * 32 + lane;
     const bool valid = l < p.nl;
     const int64_t lc = valid ? l : p.nl - 1;                 // clamp: keep the barriers uniform
     const int j0 = g * L;
     const int cnt = min(p.nb, j0 + L) - j0;                  // tiles of this thread (>= 1)
-    const uint32_t nl32 = (uint32_t)p.nl, plane32 = (uint32_t)p.nb * nl32;
-    const int slot = nthr * R;                               // words per tile slot
-    CT* const myT = sT + tid * R;
-    CT* const myC = sC + tid * R;
-    const CT* const Tl = p.T + lc;
-    CT* const Cl = p.C + lc;
+    const uint32_t plane32 = (uint32_t)p.nb * (uint32_t)p.nl;
+    const uint32_t nl32 = (uint32_t)p.sJ;                    // offset step from one tile of a line to the next
+    CT* const myT = sT + tid * RS + g * 8;
+    CT* const myC = sC + tid * RS + g * 8;
+    const CT* const Tl = p.T + lc * p.sL;
+    CT* const Cl = p.C + lc * p.sL;
 
+    // strided layout of the signal hierarchy (tile index contiguous, S == 1): the tiles of the block's 32 lines
+    // are one contiguous panel per k, moved between global and shared memory by consecutive threads
+    // (coalesced) instead of by the thread that owns them
+    const bool panel = S == 1 && p.sJ == 1 && p.sL == p.nb;
+    const int npanel = 32 * p.nb;
+    const int64_t pan0 = (int64_t)blockIdx.x * npanel, panmax = p.nl * p.nb;
+    auto panel_slot = [&](int e) -> int {                    // word offset of element e's R-vector in sT / sC
+        const int line = e / p.nb, j = e - line * p.nb;
+        const int gg = j / L, m = j - gg * L;
+        return m * slot + (gg * 32 + line) * RS + gg * 8;
+    };
     auto fetch_tails = [&](int s) {                          // tails of scan s -> sT, asynchronously
+        if (panel) {
+            for (int e = tid; e < npanel; e += nthr)
+                if (pan0 + e < panmax) {
+                    CT* dst = sT + panel_slot(e);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) cp_async4(dst + k, p.T + ((int64_t)k * plane32 + pan0 + e));
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+        }
         uint32_t off = (uint32_t)s * R * plane32 + (uint32_t)j0 * nl32;
         CT* dst = myT;
         for (int m = 0; m < cnt; ++m, off += nl32, dst += slot)
@@ -523,7 +556,7 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
             const CT* ap = sA + ((size_t)j * S + s) * R * p.sdk;
             const int da = dm * S * R * p.sdk;
             for (int t = 0; t < cnt; ++t, j += dm, tp += dslot, cp += dslot, ap += da) {
-                const int var = ftile_variant(j, p.nb);
+                const int var = p.uniform ? (int)V_INTERIOR : ftile_variant(j, p.nb);
                 if (var != cur) {                             // warp-uniform, at most three times per sweep
                     cur = var;
                     fload_mat<CT, R>(Pm, sP + (var * S + s) * RR);
@@ -597,20 +630,23 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
             for (int k = 0; k < R; ++k) p.tail_out[((int64_t)s * R + k) * p.nl + l] = fin[k];
         }
         // ---- second sweep: add the propagated segment carry, store the carries ----
-        {
+        if (!(S == 1 && p.no_store)) {
             int j = j0 + m0;
             CT* cp = myC + (s * L + m0) * slot;
             uint32_t off = (uint32_t)s * R * plane32 + (uint32_t)j * nl32;
             const uint32_t doff = (uint32_t)dm * nl32;
             cur = -1;
             for (int t = 0; t < cnt; ++t, j += dm, cp += dslot, off += doff) {
-                const int var = ftile_variant(j, p.nb);
+                const int var = p.uniform ? (int)V_INTERIOR : ftile_variant(j, p.nb);
                 if (var != cur) { cur = var; fload_mat<CT, R>(Pm, sP + (var * S + s) * RR); }
                 CT c[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) { c[k] = cp[k] + u[k]; cp[k] = c[k]; }
                 fdiff_inv<CT, R>(c);
-                if (valid) {
+                if (panel) {                                  // leaves through shared memory, see below
+#pragma unroll
+                    for (int k = 0; k < R; ++k) cp[k] = c[k];
+                } else if (valid && !p.no_store) {
 #pragma unroll
                     for (int k = 0; k < R; ++k) Cl[off + k * plane32] = c[k];
                 }
@@ -623,6 +659,14 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
             }
         }
         __syncthreads();                                      // segtail is reused by the next scan
+        if (panel && !p.no_store) {
+            for (int e = tid; e < npanel; e += nthr)
+                if (pan0 + e < panmax) {
+                    const CT* src = sC + panel_slot(e);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) p.C[(int64_t)k * plane32 + pan0 + e] = src[k];
+                }
+        }
     }
 }
 

@@ -93,11 +93,17 @@ static cudaError_t launch_fchain_T(const FChainParams<CT, R>& p, cudaStream_t st
     const size_t smem = fchain_smem_bytes(p.S, p.nseg, R, p.L, p.nb, p.A ? p.sdk : 0);
     if (smem > 227u * 1024u) return cudaErrorInvalidConfiguration;
     if ((int64_t)p.S * R * p.nb * p.nl > 0x7fffffffLL) return cudaErrorInvalidConfiguration;   // 32-bit offsets
-    switch (p.S) {
-    case 1: return launch_fchain_S<CT, R, 1>(p, grid, block, smem, st);
-    case 2: return launch_fchain_S<CT, R, 2>(p, grid, block, smem, st);
-    case 3: return launch_fchain_S<CT, R, 3>(p, grid, block, smem, st);
-    default: return launch_fchain_S<CT, R, 4>(p, grid, block, smem, st);
+    if (p.sJ <= 0 || p.sL <= 0) return cudaErrorInvalidConfiguration;
+    if constexpr (R > 4) {                                   // high orders: one scan per dimension (register budget)
+        if (p.S != 1) return cudaErrorInvalidConfiguration;
+        return launch_fchain_S<CT, R, 1>(p, grid, block, smem, st);
+    } else {
+        switch (p.S) {
+        case 1: return launch_fchain_S<CT, R, 1>(p, grid, block, smem, st);
+        case 2: return launch_fchain_S<CT, R, 2>(p, grid, block, smem, st);
+        case 3: return launch_fchain_S<CT, R, 3>(p, grid, block, smem, st);
+        default: return launch_fchain_S<CT, R, 4>(p, grid, block, smem, st);
+        }
     }
 }
 

@@ -33,6 +33,10 @@ struct FusedParams {
     CT* TX; const CT* CX;         // x tails (out, P1) / carries (in, P2)   [s][k][bx][lx]
     CT* TY; const CT* CY;         // d tails / carries                     [s][k][bd][ly]
     int64_t nlx, nly;
+    // signal mode (long 1-D signals): the array is viewed as rows of one tile width; a row continues the
+    // row before it, sig_rows rows make one signal (only its first / last row is closed), md = 0, nbx = 1
+    int signal;
+    int64_t sig_rows;
     FusedScanTab<CT, R> sx, sd;
 };
 
@@ -50,6 +54,10 @@ struct FChainParams {
     const CT* Pseg;               // [S][nseg][R][R]   product over a segment, segments in scan order
     const CT* ext;                // [s][k][l] carry entering the first tile (shard cut) or null
     CT* tail_out;                 // [s][k][l] completed tail leaving the last tile or null
+    // addressing of T / C: element (s, k, tile j, line l) at (s*R + k) * nb*nl + j * sJ + l * sL
+    int64_t sJ, sL;               // default layout ("line fastest"): sJ = nl, sL = 1
+    int uniform;                  // 1: every tile is an interior tile (signal hierarchy)
+    int no_store;                 // 1: only tail_out is wanted (up-sweep of the signal hierarchy)
     // x chain only: cross-dimension residual applied while the tails are loaded (null: plain chain)
     const CT* A;                  // [tile][s][kx][sdk]  from fcrossA_kernel
     const CT* G;                  // [V][Sd][ts][R]      d response to a unit carry (times D^-1)
@@ -65,11 +73,18 @@ struct FCrossParams {
 };
 
 // dynamic shared memory of one chain block (layout in fchain_kernel)
+// shared-memory geometry of the chain kernel's per-tile work arrays (see fchain_kernel)
+__host__ __device__ constexpr int fchain_rs(int R) { return (R % 2 == 0) ? R + 1 : R; }
+__host__ __device__ inline int fchain_slot_words(int nseg, int R)
+{
+    return ((32 * nseg * fchain_rs(R) + nseg * 8 + 31) / 32) * 32 + 1;
+}
 inline size_t fchain_smem_bytes(int S, int nseg, int R, int L, int nb, int sdk_if_cross)
 {
-    const size_t nthr = 32u * (size_t)nseg;
+    // with a single scan the carries overwrite the tails in place
+    const size_t work = (size_t)L * fchain_slot_words(nseg, R) * (S == 1 ? 1 : 1 + S);
     return ((size_t)nb * S * R * sdk_if_cross + (size_t)V_COUNT * S * R * R + (size_t)V_COUNT * S * S * R * R +
-            (size_t)S * nseg * R * R + (size_t)nseg * R * 32 + (size_t)L * R * nthr + (size_t)S * L * R * nthr) * 4;
+            (size_t)S * nseg * R * R + (size_t)nseg * R * 32 + work) * 4;
 }
 
 // dynamic shared memory of one tile CTA: the swizzled boxes, alignment slack, the mbarrier

@@ -38,7 +38,7 @@ namespace rfb {
     cudaError_t launch_cross_u##RR(const CrossParams<uint32_t, RR>&, cudaStream_t);
 RFB_FOR_EACH_R(DECLARE_LAUNCHERS)
 
-#define RFB_FOR_EACH_FR(X) X(1) X(2) X(3) X(4)
+#define RFB_FOR_EACH_FR(X) X(1) X(2) X(3) X(4) X(8)
 #define DECLARE_FLAUNCHERS(RR)                                                                      \
     cudaError_t launch_fused_tile_f##RR(const FusedParams<float, RR>&, const void*, void*, int, int, cudaStream_t);    \
     cudaError_t launch_fused_tile_u##RR(const FusedParams<uint32_t, RR>&, const void*, void*, int, int, cudaStream_t); \
@@ -882,6 +882,7 @@ struct FusedPass : PassBase {
         cp.Pseg = (const TT*)(xdim ? dPsegx.p : dPsegd.p);
         cp.ext = xdim ? nullptr : (const CT*)ext_d;
         cp.tail_out = xdim ? nullptr : (CT*)tail_out_d;
+        cp.sJ = cp.nl; cp.sL = 1;
         if (xdim && cross_needed()) {
             cp.A = (const CT*)dA.p; cp.G = (const TT*)dG.p;
             cp.Nd = fp.Nd; cp.nbd = gd.nb; cp.Sd = fp.md; cp.ts = ts; cp.sdk = sdk();
@@ -936,6 +937,179 @@ struct FusedPass : PassBase {
                  "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), launches %d\n",
                  (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
                  launches());
+        return b;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// long 1-D signals (apps/audio: one causal order-8 scan over 64 channels x 2^24 samples).
+// The signal is viewed as rows of 128 samples; the fused tile kernels run with one thread per row
+// (signal mode: a row continues the row before it), so the "tiles" of a signal are its rows and the
+// chain runs along the row index.  A signal has M = N/128 rows -- far more than one chain launch
+// handles -- so the chain is a hierarchy: level l chains groups of nb_l consecutive tiles and emits
+// one aggregate tail per group (up-sweep), the top level sees one line per signal, and the levels
+// are re-run top-down with the carry entering each group (down-sweep).  All levels are the same
+// fchain_kernel with a strided layout (tile index contiguous); the transition matrix of level l+1
+// is P_l ^ nb_l.
+// ---------------------------------------------------------------------------------------------
+template <typename CT, int R>
+struct SignalPass : PassBase {
+    using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
+    FusedParams<CT, R> fp;
+    static constexpr int ts = 128;
+    HostScan scan;
+    int64_t nsig = 1, M = 1;                       // signals, rows per signal
+    struct Level {
+        int nb = 1, L = 8, nseg = 1;
+        int64_t nl = 1;                            // lines = groups of nb tiles
+        DevBuf T, C;                               // [R][nl * nb]   (level 0: the x tails / carries of the tile kernels)
+        DevBuf dP, dM, dPseg;
+    };
+    std::vector<std::unique_ptr<Level>> lv;
+
+    bool needs_carries() const override { return true; }
+    bool d_open() const override { return false; }
+    const void* ext_buffer() const override { return nullptr; }
+    size_t shard_tail_elems() const override { return 0; }
+    int shard_resolve(const void*, int, int, cudaStream_t) override { return RF_OK; }
+    size_t workspace() const override
+    {
+        size_t n = 0;
+        for (auto& l : lv) n += l->T.bytes + l->C.bytes + l->dP.bytes + l->dM.bytes + l->dPseg.bytes;
+        return n;
+    }
+    int launches() const override { return 2 + 2 * (int)lv.size() - 1; }
+
+    // fan-out of one level: the largest divisor of m that one chain launch handles, multiples of 8 preferred
+    static int pick_fanout(int64_t m)
+    {
+        if (m <= 64) return (int)m;
+        for (int d = 64; d >= 8; d -= 8) if (m % d == 0) return d;
+        for (int d = 63; d >= 2; --d) if (m % d == 0) return d;
+        return 0;
+    }
+    static bool eligible(int64_t Nx, int64_t rows)
+    {
+        if (Nx % ts || Nx / ts < 2 || ((Nx / ts) * rows) % ts) return false;
+        if ((Nx / ts) * rows > 0x7fffffffLL / (4 * R)) return false;        // 32-bit carry offsets
+        int64_t m = Nx / ts;
+        int levels = 0;
+        while (m > 1) { const int f = pick_fanout(m); if (f < 2) return false; m /= f; if (++levels > 6) return false; }
+        return true;
+    }
+
+    int init(int64_t Nx, int64_t rows, bool clamp)
+    {
+        M = Nx / ts; nsig = rows;
+        std::memset(&fp, 0, sizeof(fp));
+        fp.Nx = ts; fp.Nd = M * nsig; fp.No = 1;
+        fp.nbx = 1; fp.nbd = (int)(fp.Nd / ts);
+        fp.clamp = clamp ? 1 : 0;
+        fp.x_lo_closed = fp.x_hi_closed = fp.d_lo_closed = fp.d_hi_closed = 1;
+        fp.mx = 1; fp.md = 0;
+        fp.nlx = fp.Nd; fp.nly = ts;
+        fp.signal = 1; fp.sig_rows = M;
+        fp.sx.causal[0] = scan.causal;
+        const std::vector<HT> c = coeff_vec<HT>(scan, R, true);
+        for (int k = 0; k <= R; ++k) fp.sx.a[0][k] = (CT)c[k];
+        fp.gain = std::is_same<CT, float>::value ? (CT)(double)scan.coeff[0] : (CT)cvt_coeff<uint32_t>(scan.coeff[0]);
+
+        // transition of one row (interior tile, unit feed-forward form), difference basis
+        DimGeom g; g.n = Nx; g.t = ts; g.nb = (int)M; g.len_last = ts; g.nscans = 1; g.lo_closed = 1; g.hi_closed = 1;
+        DimTables<HT> tab;
+        build_dim_tables<HT>(tab, std::vector<HostScan>(1, scan), g, R, clamp, 0, 0, false, true, ts);
+        std::vector<HT> P(tab.P.begin() + (size_t)V_INTERIOR * R * R, tab.P.begin() + (size_t)(V_INTERIOR + 1) * R * R);
+        FusedPass<CT, R>::conjugate_blocks(P);
+
+        int64_t m = M;
+        while (true) {
+            std::unique_ptr<Level> l(new Level());
+            l->nb = m > 1 ? pick_fanout(m) : 1;
+            l->nl = nsig * (m / l->nb);
+            l->L = l->nb <= 32 ? 4 : FCHAIN_L;
+            l->nseg = (l->nb + l->L - 1) / l->L;
+            const size_t bytes = (size_t)R * l->nl * l->nb * sizeof(CT);
+            CUDA_TRY(l->T.alloc(bytes)); CUDA_TRY(l->C.alloc(bytes));
+            CUDA_TRY(cudaMemset(l->C.p, 0, bytes));
+            // tables: every tile is an interior tile
+            std::vector<HT> Pv, Mv((size_t)V_COUNT * R * R, (HT)0), Pseg, acc, tmp;
+            for (int v = 0; v < V_COUNT; ++v) Pv.insert(Pv.end(), P.begin(), P.end());
+            for (int gs = 0; gs < l->nseg; ++gs) {
+                const int gmem = scan.causal ? gs : l->nseg - 1 - gs;
+                const int cnt = std::min(l->nb, (gmem + 1) * l->L) - gmem * l->L;
+                acc.assign((size_t)R * R, (HT)0);
+                for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
+                for (int t = 0; t < cnt; ++t) { matmul_rr<HT>(tmp, P.data(), acc.data(), R); acc = tmp; }
+                Pseg.insert(Pseg.end(), acc.begin(), acc.end());
+            }
+            CUDA_TRY((upload<HT, CT>(l->dP, Pv)));
+            CUDA_TRY((upload<HT, CT>(l->dM, Mv)));
+            CUDA_TRY((upload<HT, CT>(l->dPseg, Pseg)));
+            // next level: one tile = one group of this level
+            acc.assign((size_t)R * R, (HT)0);
+            for (int k = 0; k < R; ++k) acc[k * R + k] = (HT)1;
+            for (int t = 0; t < l->nb; ++t) { matmul_rr<HT>(tmp, P.data(), acc.data(), R); acc = tmp; }
+            P = acc;
+            m /= l->nb;
+            lv.push_back(std::move(l));
+            if (m <= 1) break;
+        }
+        fp.TX = (CT*)lv[0]->T.p; fp.CX = (const CT*)lv[0]->C.p;
+        return RF_OK;
+    }
+
+    int run_tails(const void* in, void* out, cudaStream_t st) override
+    {
+        cudaEvent_t ev = timer ? timer->begin(st, ST_TAILS) : nullptr;
+        fp.reverse = 0;
+        CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P1, ts, st)));
+        if (timer) timer->end(st, ev);
+        return RF_OK;
+    }
+    int run_level(int i, const void* ext, void* tail_out, bool store, cudaStream_t st)
+    {
+        Level& l = *lv[i];
+        FChainParams<CT, R> cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.T = (const CT*)l.T.p; cp.C = (CT*)l.C.p;
+        cp.nl = l.nl; cp.nb = l.nb; cp.S = 1; cp.nseg = l.nseg; cp.L = l.L;
+        cp.causal[0] = scan.causal;
+        cp.P = (const CT*)l.dP.p; cp.M = (const CT*)l.dM.p; cp.Pseg = (const CT*)l.dPseg.p;
+        cp.ext = (const CT*)ext; cp.tail_out = (CT*)tail_out;
+        cp.sJ = 1; cp.sL = l.nb; cp.uniform = 1; cp.no_store = store ? 0 : 1;
+        cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
+        CUDA_TRY((FLaunch<CT, R>::chain(cp, st)));
+        if (timer) timer->end(st, ev);
+        return RF_OK;
+    }
+    int run_carries(const void*, void*, cudaStream_t st, int) override
+    {
+        const int top = (int)lv.size() - 1;
+        int rc;
+        for (int i = 0; i < top; ++i)                         // up-sweep: group aggregates
+            if ((rc = run_level(i, nullptr, lv[i + 1]->T.p, false, st))) return rc;
+        if ((rc = run_level(top, nullptr, nullptr, true, st))) return rc;
+        for (int i = top - 1; i >= 0; --i)                    // down-sweep: carries entering each group
+            if ((rc = run_level(i, lv[i + 1]->C.p, nullptr, true, st))) return rc;
+        return RF_OK;
+    }
+    int run_final(const void* in, void* out, cudaStream_t st) override
+    {
+        cudaEvent_t ev = timer ? timer->begin(st, ST_FINAL) : nullptr;
+        fp.reverse = 0;
+        CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P2, ts, st)));
+        if (timer) timer->end(st, ev);
+        return RF_OK;
+    }
+    std::string describe() const override
+    {
+        std::string fan;
+        for (auto& l : lv) fan += (fan.empty() ? "" : "x") + std::to_string(l->nb);
+        char b[512];
+        snprintf(b, sizeof(b),
+                 "  signal pass: %lld signals x %lld rows of %d samples (thread per row, register tiles), 1 %s scan of "
+                 "order<=%d, carry hierarchy %s, launches %d\n",
+                 (long long)nsig, (long long)M, ts, scan.causal ? "causal" : "anticausal", R, fan.c_str(), launches());
         return b;
     }
 };
@@ -1059,6 +1233,54 @@ static int make_fused_pass(rf_plan* plan, const std::vector<HostScan>& sx, const
     if (rc) return rc;
     plan->passes.push_back(std::move(ps));
     return RF_OK;
+}
+
+template <typename CT, int R>
+static int make_signal_pass(rf_plan* plan, const HostScan& sc, int64_t Nx, int64_t rows)
+{
+    auto ps = std::unique_ptr<SignalPass<CT, R>>(new (std::nothrow) SignalPass<CT, R>());
+    if (!ps) return fail(RF_ENOMEM, "out of host memory");
+    ps->scan = sc;
+    int rc = ps->init(Nx, rows, plan->desc.border == RF_BORDER_CLAMP);
+    if (rc) return rc;
+    plan->passes.push_back(std::move(ps));
+    return RF_OK;
+}
+
+// a pass with a single scan along the contiguous dimension of long lines: the signal pass (orders <= 8)
+static bool signal_eligible(const rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                            int64_t Nx, int64_t rows)
+{
+    const rf_options& opt = plan->desc.opt;
+    if (opt.engine == RF_ENGINE_GENERIC || opt.honor_tile) return false;
+    if (!sd.empty() || sx.size() != 1 || plan->R > 8) return false;
+    if (const char* e = getenv("RFB_NO_SIGNAL")) if (atoi(e)) return false;
+    const HostScan& h = sx[0];
+    if (plan->is_float) {
+        const double inv = 1.0 / (double)h.coeff[0];
+        if (h.coeff[0] == 0.f || !std::isfinite((float)inv)) return false;
+    } else if (cvt_coeff<uint32_t>(h.coeff[0]) != 1u) return false;
+    switch (plan->R) {
+    case 1: return SignalPass<float, 1>::eligible(Nx, rows);
+    case 2: return SignalPass<float, 2>::eligible(Nx, rows);
+    case 3: return SignalPass<float, 3>::eligible(Nx, rows);
+    case 4: return SignalPass<float, 4>::eligible(Nx, rows);
+    case 8: return SignalPass<float, 8>::eligible(Nx, rows);
+    }
+    return false;
+}
+
+template <typename CT>
+static int make_signal_pass_R(rf_plan* plan, int R, const HostScan& sc, int64_t Nx, int64_t rows)
+{
+    switch (R) {
+    case 1: return make_signal_pass<CT, 1>(plan, sc, Nx, rows);
+    case 2: return make_signal_pass<CT, 2>(plan, sc, Nx, rows);
+    case 3: return make_signal_pass<CT, 3>(plan, sc, Nx, rows);
+    case 4: return make_signal_pass<CT, 4>(plan, sc, Nx, rows);
+    case 8: return make_signal_pass<CT, 8>(plan, sc, Nx, rows);
+    }
+    return fail(RF_EUNSUPPORTED, "the signal pass supports orders <= 8");
 }
 
 // tile size of the fused fast path for this pass, or 0 when the pass must take the generic engine
@@ -1215,6 +1437,10 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
         auto add = [&](const std::vector<HostScan>& sx, const std::vector<HostScan>& sd, int64_t Nx, int64_t Nd,
                        int64_t No, int tx, int td, bool fused, bool shard) -> int {
             const int fts = fused_tile_size(plan.get(), sx, sd, Nx, Nd, No);
+            if (!fts && !shard && signal_eligible(plan.get(), sx, sd, Nx, Nd * No)) {
+                return plan->is_float ? make_signal_pass_R<float>(plan.get(), R, sx[0], Nx, Nd * No)
+                                      : make_signal_pass_R<uint32_t>(plan.get(), R, sx[0], Nx, Nd * No);
+            }
             if (!fts && opt.engine == RF_ENGINE_FUSED)
                 return fail(RF_EUNSUPPORTED, "engine=fused requested but a pass is not eligible (needs order <= 4, "
                             "extents that are multiples of 64, non-zero float / unit integer feed-forward)");

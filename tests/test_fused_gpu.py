@@ -233,3 +233,37 @@ def test_host_batch_pipeline_matches_single_calls(oracle):
     truth = oracle.apply_filter(imgs[4].astype(np.float64), C3, "clamp", threads=8)
     assert rel_err(batch[4], truth) <= TOL
     plan.close()
+
+
+# ---- long 1-D signals: the signal pass (thread per 128-sample row, hierarchical carry chain) ----
+A8 = [1.0] + [0.01] * 8                                   # the reference's dummy order-8 set (apps/audio/audio_filter_high_order.cpp:41-42)
+B8 = [0.2, 0.9, -0.5, 0.3, -0.2, 0.1, -0.05, 0.02, -0.01]   # a stable order-8 set with a non-unit feed-forward
+B2 = [0.25, 1.2, -0.45]
+
+
+@pytest.mark.parametrize("n,rows", [(24576, 2), (131072, 4), (1 << 20, 1), (256, 64)])
+@pytest.mark.parametrize("coeff", [A8, B8, B2], ids=["ref8", "stable8", "order2"])
+@pytest.mark.parametrize("causal", [True, False])
+def test_signal_pass_matches_oracle(oracle, n, rows, coeff, causal):
+    a = rand_image((rows, n), np.float32, 77) - np.float32(0.5)
+    scans = [(0, causal, coeff)]
+    for border in ("zero", "clamp"):
+        plan = Plan((n, rows), "f32", [Scan(*s) for s in scans], border)
+        if len(coeff) - 1 > 4 or n // 128 > 128:          # otherwise the 2-D fused pass takes it (few tiles per line)
+            assert "signal pass" in plan.describe(), plan.describe()
+        out = plan.realize(a)
+        plan.close()
+        truth = oracle.apply_filter(a.astype(np.float64), scans, border, threads=8)
+        assert np.isfinite(out).all()
+        assert rel_err(out, truth) <= TOL, f"{border}: {rel_err(out, truth):.3e}"
+
+
+def test_signal_pass_u32_prefix_sum_bit_exact(oracle):
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 1 << 32, size=(3, 128 * 128), dtype=np.uint32)          # wraps many times
+    scans = [(0, True, [1, 1])]
+    plan = Plan((128 * 128, 3), "u32", [Scan(*s) for s in scans])
+    # 3 signals x 128 rows = 384 rows: a multiple of the tile height, so the signal pass is eligible
+    assert "signal pass" in plan.describe(), plan.describe()
+    np.testing.assert_array_equal(plan.realize(a), oracle.apply_filter(a, scans))
+    plan.close()
