@@ -222,15 +222,23 @@ def main():
 
     scans = [Scan(*s) for s in scans_c3()]
     B = args.batch
-    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B)
+    # a step = B distinct 8192x8192 images, held as one dense stack [B][rows][W] and filtered as one filter whose
+    # outermost dimension carries no scans (the reference allows that: lib/split.cpp:1888-1898): one launch
+    # sequence -- and, sharded, one tail exchange -- per step
+    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B, stacked=B > 1)
     rows = flt.local_extents[1]
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    srcs = [torch.rand((rows, W), device="cuda", dtype=torch.float32, generator=gen) for _ in range(B)]
-    dsts = [torch.empty_like(s) for s in srcs]
+    src_stack = torch.rand((B, rows, W), device="cuda", dtype=torch.float32, generator=gen)
+    dst_stack = torch.empty_like(src_stack)
+    srcs = [src_stack[i] for i in range(B)]
+    dsts = [dst_stack[i] for i in range(B)]
     launches_per_image = flt.launches_per_image
 
     def step():
-        flt.run(srcs, dsts)
+        if flt.stacked:
+            flt.run_stacked(src_stack, dst_stack)
+        else:
+            flt.run(srcs, dsts)
 
     def barrier():
         if world > 1:
@@ -276,16 +284,20 @@ def main():
     peak, peak_src = measured_peaks()
     fin = stage["tile_final"]
     k_ms = fin["ms"] / max(fin["launches"], 1)
-    alg_bytes = 8.0 * W * rows                       # 4 B read + 4 B written per sample of this rank's strip, per launch
+    imgs_per_launch = B if flt.stacked else 1
+    alg_bytes = 8.0 * W * rows * imgs_per_launch     # 4 B read + 4 B written per sample of this rank's strips, per launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     total_stage_ms = sum(v["ms"] for v in stage.values())
     traffic, traffic_src = ncu_traffic_per_launch() if N == 1 else (None, None)
+    if traffic is not None:
+        traffic *= imgs_per_launch                   # the capture is of a one-image launch; a stack is B of them
     roofline = {"bound": "hbm", "kernel": "fused_tile_kernel<float,3,128,P2> (pass 2: re-scan from carries, store)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_us": k_ms * 1e3, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": fin["ms"] / total_stage_ms if total_stage_ms else None,
                 "stage_us_per_image": {k: v["ms"] * 1e3 / (ksteps * B) for k, v in stage.items() if v["launches"]},
+                "images_per_launch": imgs_per_launch,
                 "kernel_timing": f"CUDA events around every launch on the plan's stream, {ksteps} steps after the timed region",
                 "whole_filter_frac_of_peak": (8.0 * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak}
 
@@ -296,10 +308,15 @@ def main():
     for hi, s in zip(host_in, srcs):
         hi.copy_(s)
 
+    img_plan = None
+    if N == 1:
+        from recfilter_b200 import Plan as _Plan
+        img_plan = _Plan((W, H), "f32", scans, "clamp")          # per-image plan: frames stream through realize()
+
     def e2e_step():
         if N == 1:
             # rf_plan_execute_host_batch: the realize() path for a batch of frames, copies pipelined with the kernels
-            flt.plans[0].realize_batch_ptr([h.data_ptr() for h in host_in], [h.data_ptr() for h in host_out])
+            img_plan.realize_batch_ptr([h.data_ptr() for h in host_in], [h.data_ptr() for h in host_out])
         else:
             for i in range(B):
                 srcs[i].copy_(host_in[i], non_blocking=True)
@@ -307,6 +324,7 @@ def main():
             for i in range(B):
                 host_out[i].copy_(dsts[i], non_blocking=True)
             torch.cuda.synchronize()
+
 
     e2e_step()
     barrier()
@@ -325,6 +343,32 @@ def main():
            "api": "rf_plan_execute_host_batch (RecFilter::realize path, one call per step of %d images; H2D / kernels / D2H "
                   "pipelined over 3 device buffers), pinned host buffers" % B if N == 1 else
                   "pinned H2D + rf_plan_stage1 / all_gather / rf_plan_stage2 + D2H"}
+
+    # ---- N > 1: the batched configuration beside the strip-sharded one (north_star: "strip-sharded and
+    # batched configs"): every rank filters its own B full images, no collective -> weak scaling ----------
+    batch_sharded = None
+    if N > 1:
+        from recfilter_b200 import Plan
+        bplan = Plan((W, H, B), "f32", scans, "clamp")
+        bsrc = torch.rand((B, H, W), device="cuda", dtype=torch.float32, generator=gen)
+        bdst = torch.empty_like(bsrc)
+        for _ in range(args.warmup):
+            bplan.execute(bsrc, bdst)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            bplan.execute(bsrc, bdst)
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        bms = float(tb.item())
+        batch_sharded = {"value": args.steps * B * W * H * N / (bms * 1e-3) / 1e9, "unit": "Gsamples/s",
+                         "scaling": "weak", "ms_per_step": bms / args.steps,
+                         "config": f"every rank filters its own stack of {B} full 8192x8192 images per step (no collective)"}
+        del bsrc, bdst
+        bplan.close()
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
@@ -345,9 +389,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step": B, "sharding": "none" if N == 1 else f"{N} row strips",
-                       "l2": "every image (268 MB) exceeds L2 and a step cycles through %d distinct images" % B,
+                       "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
                        "tile": "128x128 register tiles (fused engine)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "batch_sharded": batch_sharded,
             "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,
             "hbm_roofline_pct": 100.0 * (8.0 * value) / (peak * N),
             "hbm_roofline_pct_of_8TBs": 100.0 * (8.0 * value) / (8000.0 * N),

@@ -864,7 +864,7 @@ struct FusedPass : PassBase {
         return RF_OK;
     }
 
-    int run_chain(bool xdim, const void* ext_d, void* tail_out_d, cudaStream_t st)
+    int run_chain(bool xdim, const void* ext_d, void* tail_out_d, cudaStream_t st, bool tails_only = false)
     {
         FChainParams<CT, R> cp;
         std::memset(&cp, 0, sizeof(cp));
@@ -883,6 +883,7 @@ struct FusedPass : PassBase {
         cp.ext = xdim ? nullptr : (const CT*)ext_d;
         cp.tail_out = xdim ? nullptr : (CT*)tail_out_d;
         cp.sJ = cp.nl; cp.sL = 1;
+        cp.no_store = tails_only ? 1 : 0;            // stage 1 of a sharded run wants the outgoing tails only
         if (xdim && cross_needed()) {
             cp.A = (const CT*)dA.p; cp.G = (const TT*)dG.p;
             cp.Nd = fp.Nd; cp.nbd = gd.nb; cp.Sd = fp.md; cp.ts = ts; cp.sdk = sdk();
@@ -896,7 +897,7 @@ struct FusedPass : PassBase {
     int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st, int stage) override
     {
         if (!needs_carries()) return RF_OK;
-        if (d_needs()) { int rc = run_chain(false, ext_d, tail_out_d, st); if (rc) return rc; }
+        if (d_needs()) { int rc = run_chain(false, ext_d, tail_out_d, st, stage == 1); if (rc) return rc; }
         if (stage == 1) return RF_OK;                // stage 1 of a sharded run: only the outgoing tails are needed
         if (cross_needed()) {
             FCrossParams<CT, R> cr;

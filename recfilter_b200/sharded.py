@@ -54,8 +54,12 @@ class ShardedFilter:
     """
 
     def __init__(self, extents: Sequence[int], dtype, scans: Sequence[Scan], border: str, *, rank: int, world: int,
-                 shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None):
+                 shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None, stacked: bool = False):
+        """stacked=True: the `batch` images are one dense stack [batch][...] and are filtered as ONE filter with
+        an extra outermost dimension that carries no scans (allowed by the reference: lib/split.cpp:1888-1898,
+        it is how apps/audio batches channels): one launch sequence and one tail exchange per stack."""
         self.rank, self.world, self.group, self.batch = rank, world, group, batch
+        self.stacked = stacked and batch > 1
         extents = list(int(e) for e in extents)
         self.shard_dim = len(extents) - 1 if shard_dim is None else shard_dim
         lo, hi = strip_bounds(extents[self.shard_dim], world, rank)
@@ -65,10 +69,28 @@ class ShardedFilter:
         kw = dict(engine=engine)
         if world > 1:
             kw.update(shard_dim=self.shard_dim, open_lo=rank > 0, open_hi=rank < world - 1)
-        # one plan per image in flight: a plan owns the carry workspace of its image
-        self.plans = [Plan(self.local_extents, dtype, scans, border, **kw) for _ in range(batch if world > 1 else 1)]
+        if self.stacked:
+            self.plans = [Plan(self.local_extents + [batch], dtype, scans, border, **kw)]
+        else:
+            # one plan per image in flight: a plan owns the carry workspace of its image
+            self.plans = [Plan(self.local_extents, dtype, scans, border, **kw) for _ in range(batch if world > 1 else 1)]
         self.tail_elems = self.plans[0].shard_tail_bytes // 4 if world > 1 else 0
         self._tails = None
+
+    def run_stacked(self, src: torch.Tensor, dst: torch.Tensor):
+        """Filter a dense stack [batch][local extents...] (stacked=True)."""
+        if not self.stacked:
+            raise ValueError("run_stacked needs stacked=True")
+        plan = self.plans[0]
+        if self.world == 1:
+            plan.execute(src, dst)
+            return
+        if self._tails is None:
+            dt = torch.float32 if src.dtype == torch.float32 else torch.int32
+            self._tails = torch.empty((1, self.tail_elems), device=src.device, dtype=dt)
+        plan.stage1(src, dst, self._tails[0])
+        gathered = exchange_tails(self._tails, self.world, self.group)
+        plan.stage2(src, dst, gathered[0], self.world, self.rank)
 
     def run(self, srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]):
         """Filter `batch` strips (device tensors of the local extents)."""
@@ -87,8 +109,8 @@ class ShardedFilter:
 
     @property
     def launches_per_image(self) -> int:
-        n = self.plans[0].num_launches
-        return n + (2 if self.world > 1 else 0)     # strip resolve + the d chain runs twice
+        n = self.plans[0].num_launches + (2 if self.world > 1 else 0)     # strip resolve + the d chain runs twice
+        return n / self.batch if self.stacked else n
 
     def close(self):
         for p in self.plans:

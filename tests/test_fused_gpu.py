@@ -267,3 +267,19 @@ def test_signal_pass_u32_prefix_sum_bit_exact(oracle):
     assert "signal pass" in plan.describe(), plan.describe()
     np.testing.assert_array_equal(plan.realize(a), oracle.apply_filter(a, scans))
     plan.close()
+
+
+def test_stacked_images_equal_per_image_filtering(oracle):
+    """A stack [B][H][W] filtered as one 3-D filter whose outermost dimension carries no scans (how bench.py
+    batches a step, lib/split.cpp:1888-1898) is the per-image filter applied B times."""
+    B, Hh, Ww = 3, 384, 512
+    stack = rand_image((B, Hh, Ww), np.float32, 4242)
+    plan3 = Plan((Ww, Hh, B), "f32", [Scan(*s) for s in C3], "clamp", engine="fused")
+    out3 = plan3.realize(stack)
+    plan3.close()
+    plan2 = Plan((Ww, Hh), "f32", [Scan(*s) for s in C3], "clamp", engine="fused")
+    for b in range(B):
+        np.testing.assert_array_equal(out3[b], plan2.realize(stack[b]))
+    plan2.close()
+    truth = oracle.apply_filter(stack[1].astype(np.float64), C3, "clamp", threads=8)
+    assert rel_err(out3[1], truth) <= TOL
