@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <type_traits>
 #include "engine.h"
 #include "fused_params.h"
 
@@ -407,9 +408,9 @@ __device__ __forceinline__ void fdiff_inv(CT (&c)[R])
  * instruction-cache misses).  The loop over tiles stays rolled and the per-tile data of a thread
  * lives in shared memory, R consecutive words per (tile, thread) so that every access is a
  * pointer plus an immediate:
- *   sT  this scan's tails, brought in by cp.async (no registers, no scoreboard stall)
- *   sC  the completed carries of every scan (difference basis), re-used by the same-dimension
- *       residual of the later scans and by the second sweep
+ *   sT  every scan's tails, brought in by cp.async (no registers, no scoreboard stall) one scan ahead
+ *   sC  (= sT, in place) the completed carries of every scan (difference basis), re-used by the
+ *       same-dimension residual of the later scans and by the second sweep
  *   sA  (x chain) the A matrices of the block's tile row, see fcrossA_kernel.
  * The matrices of the current tile variant are held in registers and reloaded only when the
  * variant changes (first / last tile of the line).  Offsets are 32-bit (checked by the planner).
@@ -453,8 +454,8 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
     // free of bank conflicts
     constexpr int RS = fchain_rs(R);
     const int slot = fchain_slot_words(nseg, R);
-    CT* sT      = segtail + nseg * R * 32;                      // [L][slot]
-    CT* sC      = S == 1 ? sT : sT + (size_t)L * slot;          // [S][L][slot]  (one scan: carries overwrite the tails)
+    CT* sT      = segtail + nseg * R * 32;                      // [S][L][slot]
+    CT* sC      = sT;                                           // [S][L][slot]: the carries of a scan overwrite its tails in place
 
     const int64_t l = (int64_t)blockIdx.x * 32 + lane;
     const bool valid = l < p.nl;
@@ -491,7 +492,7 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
             return;
         }
         uint32_t off = (uint32_t)s * R * plane32 + (uint32_t)j0 * nl32;
-        CT* dst = myT;
+        CT* dst = myT + s * L * slot;
         for (int m = 0; m < cnt; ++m, off += nl32, dst += slot)
 #pragma unroll
             for (int k = 0; k < R; ++k) cp_async4(dst + k, Tl + (off + k * plane32));
@@ -548,21 +549,27 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
         CT Pm[RR];
         CT Mm[NQ][RR];
         int cur = -1;
+        // every tile of this thread is an interior tile (warp-uniform): no variant bookkeeping in the sweeps
+        const bool allint = p.uniform || (j0 > 0 && j0 + cnt < p.nb);
         // ---- first sweep, scan order: provisional carries (zero carry into the segment) ----
         {
             int j = j0 + m0;
-            const CT* tp = myT + m0 * slot;
+            const CT* tp = myT + (s * L + m0) * slot;      // == cp: a tile's tail is read before its carry is written
             CT* cp = myC + (s * L + m0) * slot;
             const CT* ap = sA + ((size_t)j * S + s) * R * p.sdk;
             const int da = dm * S * R * p.sdk;
-            for (int t = 0; t < cnt; ++t, j += dm, tp += dslot, cp += dslot, ap += da) {
-                const int var = p.uniform ? (int)V_INTERIOR : ftile_variant(j, p.nb);
-                if (var != cur) {                             // warp-uniform, at most three times per sweep
-                    cur = var;
-                    fload_mat<CT, R>(Pm, sP + (var * S + s) * RR);
+            auto load_mats = [&](int var) {
+                fload_mat<CT, R>(Pm, sP + (var * S + s) * RR);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q)
-                        if (q < s) fload_mat<CT, R>(Mm[q], sM + ((var * S + q) * S + s) * RR);
+                for (int q = 0; q < NQ; ++q)
+                    if (q < s) fload_mat<CT, R>(Mm[q], sM + ((var * S + q) * S + s) * RR);
+            };
+            if (allint) load_mats(V_INTERIOR);
+            auto sweep1 = [&](auto interior) {
+            for (int t = 0; t < cnt; ++t, j += dm, tp += dslot, cp += dslot, ap += da) {
+                if constexpr (!decltype(interior)::value) {
+                    const int var = ftile_variant(j, p.nb);
+                    if (var != cur) { cur = var; load_mats(var); }   // warp-uniform, at most three times per sweep
                 }
                 CT x[R];
 #pragma unroll
@@ -602,6 +609,8 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 #pragma unroll
                 for (int k = 0; k < R; ++k) tau[k] = x[k];
             }
+            };
+            if (allint) sweep1(std::true_type()); else sweep1(std::false_type());
         }
         if (s + 1 < S) fetch_tails(s + 1);                   // sT entries of this thread are consumed
 
@@ -636,17 +645,26 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
             uint32_t off = (uint32_t)s * R * plane32 + (uint32_t)j * nl32;
             const uint32_t doff = (uint32_t)dm * nl32;
             cur = -1;
+            if (allint) fload_mat<CT, R>(Pm, sP + (V_INTERIOR * S + s) * RR);
+            const bool store = valid && !p.no_store;
+            auto sweep2 = [&](auto interior) {
             for (int t = 0; t < cnt; ++t, j += dm, cp += dslot, off += doff) {
-                const int var = p.uniform ? (int)V_INTERIOR : ftile_variant(j, p.nb);
-                if (var != cur) { cur = var; fload_mat<CT, R>(Pm, sP + (var * S + s) * RR); }
+                if constexpr (!decltype(interior)::value) {
+                    const int var = ftile_variant(j, p.nb);
+                    if (var != cur) { cur = var; fload_mat<CT, R>(Pm, sP + (var * S + s) * RR); }
+                }
                 CT c[R];
 #pragma unroll
-                for (int k = 0; k < R; ++k) { c[k] = cp[k] + u[k]; cp[k] = c[k]; }
+                for (int k = 0; k < R; ++k) c[k] = cp[k] + u[k];
+                if (s + 1 < S) {                              // later scans need the completed carries (difference basis)
+#pragma unroll
+                    for (int k = 0; k < R; ++k) cp[k] = c[k];
+                }
                 fdiff_inv<CT, R>(c);
                 if (panel) {                                  // leaves through shared memory, see below
 #pragma unroll
                     for (int k = 0; k < R; ++k) cp[k] = c[k];
-                } else if (valid && !p.no_store) {
+                } else if (store) {
 #pragma unroll
                     for (int k = 0; k < R; ++k) Cl[off + k * plane32] = c[k];
                 }
@@ -657,6 +675,8 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 #pragma unroll
                 for (int k = 0; k < R; ++k) u[k] = nu[k];
             }
+            };
+            if (allint) sweep2(std::true_type()); else sweep2(std::false_type());
         }
         __syncthreads();                                      // segtail is reused by the next scan
         if (panel && !p.no_store) {

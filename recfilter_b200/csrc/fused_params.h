@@ -81,8 +81,8 @@ __host__ __device__ inline int fchain_slot_words(int nseg, int R)
 }
 inline size_t fchain_smem_bytes(int S, int nseg, int R, int L, int nb, int sdk_if_cross)
 {
-    // with a single scan the carries overwrite the tails in place
-    const size_t work = (size_t)L * fchain_slot_words(nseg, R) * (S == 1 ? 1 : 1 + S);
+    // the carries of a scan overwrite its tails in place
+    const size_t work = (size_t)L * fchain_slot_words(nseg, R) * S;
     return ((size_t)nb * S * R * sdk_if_cross + (size_t)V_COUNT * S * R * R + (size_t)V_COUNT * S * S * R * R +
             (size_t)S * nseg * R * R + (size_t)nseg * R * 32 + work) * 4;
 }
