@@ -11,7 +11,10 @@ synthetic images (so consecutive launches never re-read a cached input; every im
   N > 1   every image is cut into N horizontal strips, one per rank; x scans are strip
           local, the y scans exchange only their order-3 boundary tails (2*3*8192 floats
           per image and rank) with ONE NCCL all-gather per step (rf_plan_stage1 /
-          all_gather / rf_plan_stage2).  Total work is fixed: "scaling": "strong".
+          all_gather / rf_plan_stage2).  A step is --batch x N images, so the samples per GPU per
+          step are fixed: "scaling": "weak".  --strong keeps --batch images per step; that figure
+          and the collective-free batch sharding are also reported (`strip_sharded_strong`,
+          `batch_sharded`).
 
 Metric: Gsamples/s = filtered output samples per second over all ranks (device time,
 CUDA events, max over ranks).  `roofline` is the dominant kernel (the final tile kernel,
@@ -161,7 +164,7 @@ def run_reference(args, rank: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_step": 1},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
                          "sample": "one full 8192x8192 image per step, oracle/oracle.c serial recurrence loops, "
@@ -193,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: keep --batch images per step (strong scaling) instead of --batch x N (weak scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,7 +226,11 @@ def main():
     assert N == args.gpus or world == 1, "--gpus must match the torchrun world size"
 
     scans = [Scan(*s) for s in scans_c3()]
-    B = args.batch
+    # N > 1: every image is cut into N row strips (one per rank, carries exchanged).  Weak scaling (default): a step
+    # is --batch x N images, so every rank holds --batch images' worth of samples whatever N is; --strong keeps
+    # --batch images per step.
+    weak = N > 1 and not args.strong
+    B = args.batch * (N if weak else 1)
     # a step = B distinct 8192x8192 images, held as one dense stack [B][rows][W] and filtered as one filter whose
     # outermost dimension carries no scans (the reference allows that: lib/split.cpp:1888-1898): one launch
     # sequence -- and, sharded, one tail exchange -- per step
@@ -344,13 +353,44 @@ def main():
                   "pipelined over 3 device buffers), pinned host buffers" % B if N == 1 else
                   "pinned H2D + rf_plan_stage1 / all_gather / rf_plan_stage2 + D2H"}
 
+    # ---- N > 1, weak run: the strong-scaling figure (fixed --batch images per step) beside it -----------------
+    strong = None
+    if weak:
+        sflt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=args.batch,
+                             stacked=args.batch > 1)
+        ssrc, sdst = src_stack[:args.batch].contiguous(), dst_stack[:args.batch].contiguous()
+
+        def sstep():
+            if sflt.stacked:
+                sflt.run_stacked(ssrc, sdst)
+            else:
+                sflt.run([ssrc[i] for i in range(args.batch)], [sdst[i] for i in range(args.batch)])
+        for _ in range(args.warmup):
+            sstep()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            sstep()
+        s1.record()
+        barrier()
+        ts_ = torch.tensor([s0.elapsed_time(s1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        sms = float(ts_.item())
+        strong = {"value": args.steps * args.batch * W * H / (sms * 1e-3) / 1e9, "unit": "Gsamples/s", "scaling": "strong",
+                  "ms_per_step": sms / args.steps,
+                  "config": f"{args.batch} images per step whatever N is, each cut into {N} row strips"}
+        sflt.close()
+        del ssrc, sdst
+
     # ---- N > 1: the batched configuration beside the strip-sharded one (north_star: "strip-sharded and
     # batched configs"): every rank filters its own B full images, no collective -> weak scaling ----------
     batch_sharded = None
     if N > 1:
         from recfilter_b200 import Plan
-        bplan = Plan((W, H, B), "f32", scans, "clamp")
-        bsrc = torch.rand((B, H, W), device="cuda", dtype=torch.float32, generator=gen)
+        Bb = args.batch
+        bplan = Plan((W, H, Bb), "f32", scans, "clamp")
+        bsrc = torch.rand((Bb, H, W), device="cuda", dtype=torch.float32, generator=gen)
         bdst = torch.empty_like(bsrc)
         for _ in range(args.warmup):
             bplan.execute(bsrc, bdst)
@@ -364,9 +404,9 @@ def main():
         tb = torch.tensor([b0.elapsed_time(b1)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         bms = float(tb.item())
-        batch_sharded = {"value": args.steps * B * W * H * N / (bms * 1e-3) / 1e9, "unit": "Gsamples/s",
+        batch_sharded = {"value": args.steps * Bb * W * H * N / (bms * 1e-3) / 1e9, "unit": "Gsamples/s",
                          "scaling": "weak", "ms_per_step": bms / args.steps,
-                         "config": f"every rank filters its own stack of {B} full 8192x8192 images per step (no collective)"}
+                         "config": f"every rank filters its own stack of {Bb} full 8192x8192 images per step (no collective)"}
         del bsrc, bdst
         bplan.close()
 
@@ -387,11 +427,15 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": N, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_step": B, "sharding": "none" if N == 1 else f"{N} row strips",
+            "scaling": "strong" if (N > 1 and not weak) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": B,
+                       "sharding": "none" if N == 1 else
+                                   f"every image cut into {N} row strips, one per GPU; one all-gather of the order-3 strip "
+                                   f"tails per step; {args.batch} images' worth of samples per GPU per step",
                        "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
                        "tile": "128x128 register tiles (fused engine)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "batch_sharded": batch_sharded,
+            "strip_sharded_strong": strong,
             "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,
             "hbm_roofline_pct": 100.0 * (8.0 * value) / (peak * N),
             "hbm_roofline_pct_of_8TBs": 100.0 * (8.0 * value) / (8000.0 * N),
