@@ -138,6 +138,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
+// L2 prefetch of a box (no shared memory, no barrier): lets a CTA pull in the tile of the CTA that will follow it
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int x, int y)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tmap), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, int x, int y, const void* smem_src)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
@@ -203,6 +208,16 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         mbar_expect_tx(bar, NBOX * BOX_BYTES);
 #pragma unroll
         for (int bb = 0; bb < NBOX; ++bb) tma_load_2d(tile + bb * BOX_BYTES, &tm_in, x0 + bb * 32, y0, bar);
+        // the tile of the CTA that takes over this CTA's slot (`prefetch` blocks further on) starts its way into L2
+        const int64_t nxt = (int64_t)blockIdx.x + p.prefetch;
+        if (p.prefetch > 0 && nxt < (int64_t)gridDim.x) {
+            int64_t b2 = p.reverse ? (int64_t)gridDim.x - 1 - nxt : nxt;
+            const int bx2 = (int)(b2 % p.nbx); b2 /= p.nbx;
+            const int bd2 = (int)(b2 % p.nbd);
+            const int y2 = (int)((b2 / p.nbd) * p.Nd + (int64_t)bd2 * TS);
+#pragma unroll
+            for (int bb = 0; bb < NBOX; ++bb) tma_prefetch_2d(&tm_in, bx2 * TS + bb * 32, y2);
+        }
     }
 
     CT v[TS];

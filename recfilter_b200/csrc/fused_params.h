@@ -29,6 +29,7 @@ struct FusedParams {
     int x_lo_closed, x_hi_closed, d_lo_closed, d_hi_closed;
     int mx, md;
     int reverse;                  // walk the tiles backwards (pass 2: most recently read first)
+    int prefetch;                 // > 0: a CTA prefetches (L2) the tile of block blockIdx + prefetch
     CT  gain;                     // product of the feed-forward coefficients
     CT* TX; const CT* CX;         // x tails (out, P1) / carries (in, P2)   [s][k][bx][lx]
     CT* TY; const CT* CY;         // d tails / carries                     [s][k][bd][ly]
