@@ -196,6 +196,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", type=int, default=1,
+                    help="sub-stacks of a step that run on their own CUDA streams (carry stage of one beside the tile "
+                         "kernels of another); 1 = one stream")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: keep --batch images per step (strong scaling) instead of --batch x N (weak scaling)")
     args = ap.parse_args()
@@ -234,7 +237,8 @@ def main():
     # a step = B distinct 8192x8192 images, held as one dense stack [B][rows][W] and filtered as one filter whose
     # outermost dimension carries no scans (the reference allows that: lib/split.cpp:1888-1898): one launch
     # sequence -- and, sharded, one tail exchange -- per step
-    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B, stacked=B > 1)
+    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B, stacked=B > 1,
+                        overlap=args.overlap)
     rows = flt.local_extents[1]
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     src_stack = torch.rand((B, rows, W), device="cuda", dtype=torch.float32, generator=gen)
@@ -293,7 +297,7 @@ def main():
     peak, peak_src = measured_peaks()
     fin = stage["tile_final"]
     k_ms = fin["ms"] / max(fin["launches"], 1)
-    imgs_per_launch = B if flt.stacked else 1
+    imgs_per_launch = flt.sub if flt.stacked else 1
     alg_bytes = 8.0 * W * rows * imgs_per_launch     # 4 B read + 4 B written per sample of this rank's strips, per launch
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     total_stage_ms = sum(v["ms"] for v in stage.values())
@@ -433,7 +437,8 @@ def main():
                                    f"every image cut into {N} row strips, one per GPU; one all-gather of the order-3 strip "
                                    f"tails per step; {args.batch} images' worth of samples per GPU per step",
                        "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
-                       "tile": "128x128 register tiles (fused engine)"},
+                       "tile": "128x128 register tiles (fused engine)",
+                       "streams": f"{flt.groups} sub-stacks of {flt.sub} images on their own CUDA streams" if flt.stacked else "1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "batch_sharded": batch_sharded,
             "strip_sharded_strong": strong,
             "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,

@@ -54,12 +54,17 @@ class ShardedFilter:
     """
 
     def __init__(self, extents: Sequence[int], dtype, scans: Sequence[Scan], border: str, *, rank: int, world: int,
-                 shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None, stacked: bool = False):
+                 shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None, stacked: bool = False,
+                 overlap: int = 1):
         """stacked=True: the `batch` images are one dense stack [batch][...] and are filtered as ONE filter with
         an extra outermost dimension that carries no scans (allowed by the reference: lib/split.cpp:1888-1898,
-        it is how apps/audio batches channels): one launch sequence and one tail exchange per stack."""
+        it is how apps/audio batches channels): one launch sequence and one tail exchange per stack.
+        overlap=g > 1 (stacked only): the stack is split into g sub-stacks, each with its own plan (carry
+        workspace) and CUDA stream, so the latency-bound carry stage of one sub-stack runs beside the
+        bandwidth-bound tile kernels of another."""
         self.rank, self.world, self.group, self.batch = rank, world, group, batch
         self.stacked = stacked and batch > 1
+        self.groups = overlap if (self.stacked and overlap > 1 and batch % overlap == 0) else 1
         extents = list(int(e) for e in extents)
         self.shard_dim = len(extents) - 1 if shard_dim is None else shard_dim
         lo, hi = strip_bounds(extents[self.shard_dim], world, rank)
@@ -70,7 +75,9 @@ class ShardedFilter:
         if world > 1:
             kw.update(shard_dim=self.shard_dim, open_lo=rank > 0, open_hi=rank < world - 1)
         if self.stacked:
-            self.plans = [Plan(self.local_extents + [batch], dtype, scans, border, **kw)]
+            self.sub = batch // self.groups
+            self.plans = [Plan(self.local_extents + [self.sub], dtype, scans, border, **kw) for _ in range(self.groups)]
+            self.streams = [torch.cuda.Stream() for _ in range(self.groups)] if self.groups > 1 else []
         else:
             # one plan per image in flight: a plan owns the carry workspace of its image
             self.plans = [Plan(self.local_extents, dtype, scans, border, **kw) for _ in range(batch if world > 1 else 1)]
@@ -81,16 +88,41 @@ class ShardedFilter:
         """Filter a dense stack [batch][local extents...] (stacked=True)."""
         if not self.stacked:
             raise ValueError("run_stacked needs stacked=True")
-        plan = self.plans[0]
-        if self.world == 1:
-            plan.execute(src, dst)
-            return
-        if self._tails is None:
+        G, sub = self.groups, self.sub
+        if self.world > 1 and self._tails is None:
             dt = torch.float32 if src.dtype == torch.float32 else torch.int32
-            self._tails = torch.empty((1, self.tail_elems), device=src.device, dtype=dt)
-        plan.stage1(src, dst, self._tails[0])
-        gathered = exchange_tails(self._tails, self.world, self.group)
-        plan.stage2(src, dst, gathered[0], self.world, self.rank)
+            self._tails = torch.empty((G, self.tail_elems), device=src.device, dtype=dt)
+        if G == 1:
+            plan = self.plans[0]
+            if self.world == 1:
+                plan.execute(src, dst)
+                return
+            plan.stage1(src, dst, self._tails[0])
+            gathered = exchange_tails(self._tails, self.world, self.group)
+            plan.stage2(src, dst, gathered[0], self.world, self.rank)
+            return
+        # sub-stacks on their own streams; the caller's stream is joined at both ends
+        cur = torch.cuda.current_stream()
+        parts = [(src[g * sub:(g + 1) * sub], dst[g * sub:(g + 1) * sub]) for g in range(G)]
+        for st in self.streams:
+            st.wait_stream(cur)
+        if self.world == 1:
+            for g, (a, b) in enumerate(parts):
+                with torch.cuda.stream(self.streams[g]):
+                    self.plans[g].execute(a, b)
+        else:
+            for g, (a, b) in enumerate(parts):
+                with torch.cuda.stream(self.streams[g]):
+                    self.plans[g].stage1(a, b, self._tails[g])
+            gathered = []
+            for g in range(G):                       # collectives are issued in the same order on every rank
+                with torch.cuda.stream(self.streams[g]):
+                    gathered.append(exchange_tails(self._tails[g:g + 1], self.world, self.group))
+            for g, (a, b) in enumerate(parts):
+                with torch.cuda.stream(self.streams[g]):
+                    self.plans[g].stage2(a, b, gathered[g][0], self.world, self.rank)
+        for st in self.streams:
+            cur.wait_stream(st)
 
     def run(self, srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]):
         """Filter `batch` strips (device tensors of the local extents)."""
@@ -110,7 +142,7 @@ class ShardedFilter:
     @property
     def launches_per_image(self) -> int:
         n = self.plans[0].num_launches + (2 if self.world > 1 else 0)     # strip resolve + the d chain runs twice
-        return n / self.batch if self.stacked else n
+        return n * self.groups / self.batch if self.stacked else n
 
     def close(self):
         for p in self.plans:
