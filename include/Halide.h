@@ -119,6 +119,7 @@ private:
 // expressions
 // ---------------------------------------------------------------------------------------------
 struct ExprNode;
+struct FuncDef;
 class Expr {
 public:
     Expr() {}
@@ -140,7 +141,15 @@ struct ExprNode {
     std::vector<Expr> args;                      // operands / indices
     std::shared_ptr<BufferData> buffer;          // Load: the image
     std::shared_ptr<RecFilterContents> filter;   // Call: another RecFilter's result
+    std::shared_ptr<FuncDef> func;               // Call: a pure Func defined by an expression (inlined by the engine)
     int tuple_index = 0;
+};
+
+// pure definition of a Func:  f(u, v) = body
+struct FuncDef {
+    std::string name;
+    std::vector<std::string> args;
+    Expr body;
 };
 
 inline Type Expr::type() const { return node ? node->type : Type(); }
@@ -184,9 +193,10 @@ template <typename T> inline Expr cast(Expr a) { return cast(type_of<T>(), a); }
 
 class Var {
 public:
-    Var() : n("_v") {}
+    Var() : n(unique_name()) {}                       // Halide gives anonymous Vars distinct names
     Var(const std::string& name) : n(name) {}
     const std::string& name() const { return n; }
+    static std::string unique_name() { static int counter = 0; return "_v" + std::to_string(counter++); }
     operator Expr() const
     {
         auto e = std::make_shared<ExprNode>();
@@ -302,24 +312,41 @@ private:
 class FuncRefExpr {
 public:
     FuncRefExpr(std::shared_ptr<RecFilterContents> f, const std::vector<Expr>& a) : filter(f), args(a) {}
+    FuncRefExpr(std::shared_ptr<RecFilterContents> f, std::shared_ptr<FuncDef> d, const std::vector<Expr>& a)
+        : filter(f), def(d), args(a) {}
     operator Expr() const;
     Expr operator[](int i) const;
+    // pure definition  f(u, v) = expr  (the arguments must be plain Vars)
+    void operator=(Expr body)
+    {
+        if (filter || !def) { std::cerr << "Func: only a Func that is not a RecFilter result can be defined" << std::endl; assert(false); }
+        def->args.clear();
+        for (const Expr& a : args) {
+            if (!a.defined() || a.node->kind != ExprNode::Variable) {
+                std::cerr << "Func: the arguments of a pure definition must be Vars" << std::endl; assert(false);
+            }
+            def->args.push_back(a.node->name);
+        }
+        def->body = body;
+    }
+    void operator=(const FuncRefExpr& other) { *this = Expr(other); }
     std::shared_ptr<RecFilterContents> filter;
+    std::shared_ptr<FuncDef> def;
     std::vector<Expr> args;
 };
 typedef FuncRefExpr FuncRefVar;
 
 class Func {
 public:
-    Func() {}
-    explicit Func(const std::string& n) : nm(n) {}
+    Func() : def(std::make_shared<FuncDef>()) {}
+    explicit Func(const std::string& n) : def(std::make_shared<FuncDef>()), nm(n) { def->name = n; }
     explicit Func(std::shared_ptr<RecFilterContents> f, const std::string& n = "") : filter(f), nm(n) {}
     const std::string& name() const { return nm; }
-    bool defined() const { return (bool)filter; }
-    FuncRefExpr operator()(Expr x) const { return FuncRefExpr(filter, { x }); }
-    FuncRefExpr operator()(Expr x, Expr y) const { return FuncRefExpr(filter, { x, y }); }
-    FuncRefExpr operator()(Expr x, Expr y, Expr z) const { return FuncRefExpr(filter, { x, y, z }); }
-    FuncRefExpr operator()(const std::vector<Expr>& a) const { return FuncRefExpr(filter, a); }
+    bool defined() const { return (bool)filter || (def && def->body.defined()); }
+    FuncRefExpr operator()(Expr x) const { return FuncRefExpr(filter, def, { x }); }
+    FuncRefExpr operator()(Expr x, Expr y) const { return FuncRefExpr(filter, def, { x, y }); }
+    FuncRefExpr operator()(Expr x, Expr y, Expr z) const { return FuncRefExpr(filter, def, { x, y, z }); }
+    FuncRefExpr operator()(const std::vector<Expr>& a) const { return FuncRefExpr(filter, def, a); }
     // accepted and ignored schedule directives
     Func& compute_root() { return *this; }
     Func& compute_at(Func, Var) { return *this; }
@@ -335,6 +362,7 @@ public:
     Func& gpu_tile(Var, Var, int, int) { return *this; }
     Func& bound(Var, Expr, Expr) { return *this; }
     std::shared_ptr<RecFilterContents> filter;
+    std::shared_ptr<FuncDef> def;                // pure definition (when the Func is not a RecFilter result)
 private:
     std::string nm;
 };
@@ -343,6 +371,7 @@ inline FuncRefExpr::operator Expr() const
 {
     auto n = std::make_shared<ExprNode>();
     n->kind = ExprNode::Call; n->filter = filter; n->args = args;
+    if (!filter) n->func = def;
     n->type = Float(32);          // refined by RecFilter::define from the callee's type
     return Expr(n);
 }

@@ -139,6 +139,25 @@ int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host);
  */
 int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host, void* const* out_host);
 
+/*
+ * Pointwise epilogue: out(x) = post_scale * sum_i weight_i * in(clamp(x + offset_i, lo_i, hi_i)) per dimension
+ * (the common factor is applied after the sum, as "(a - b - c + d) / area" does: the taps of a summed-area table
+ * are large numbers whose differences must be taken before scaling) -- the finite
+ * differencing that turns a summed-area table into a box filter (apps/box/box_filter.h:36-39, 128-139 in the
+ * reference, where it is a separate Halide Func scheduled with compute_root) and similar small linear stencils
+ * of one filter result.  Indices are additionally clamped to the array.  dtype: RF_F32, RF_I32 or RF_U32
+ * (integer weights are the rounded float weights, arithmetic wraps).  in_dev and out_dev must not alias.
+ */
+#define RF_MAX_TAPS 32
+typedef struct rf_tap {
+    float   weight;
+    int32_t offset[RF_MAX_DIMS];
+    int32_t lo[RF_MAX_DIMS];            /* INT32_MIN: no lower clamp */
+    int32_t hi[RF_MAX_DIMS];            /* INT32_MAX: no upper clamp */
+} rf_tap;
+int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, const rf_tap* taps, float post_scale,
+                       const void* in_dev, void* out_dev, void* stream);
+
 /* Time `iters` executions on device-resident data with CUDA events (ms per iteration). */
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter);
 

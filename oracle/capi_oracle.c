@@ -83,6 +83,44 @@ int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stre
     return RF_OK;
 }
 int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host) { return rf_plan_execute(plan, in_host, out_host, 0); }
+/* pointwise linear stencil (plain loops; the reference's box_filter.h differencing Func) */
+int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, const rf_tap* taps, float post_scale,
+                       const void* in_dev, void* out_dev, void* stream)
+{
+    (void)stream;
+    if (ndim < 1 || ndim > RF_MAX_DIMS || ntaps < 1 || ntaps > RF_MAX_TAPS || !in_dev || !out_dev || in_dev == out_dev) return RF_EINVAL;
+    if (dtype != RF_F32 && dtype != RF_I32 && dtype != RF_U32) return RF_EUNSUPPORTED;
+    int64_t ext[RF_MAX_DIMS] = { 1, 1, 1, 1 }, total = 1;
+    for (int d = 0; d < ndim; ++d) { ext[d] = extent[d]; total *= extent[d]; }
+    for (int64_t i = 0; i < total; ++i) {
+        int64_t c[RF_MAX_DIMS], r = i;
+        for (int d = 0; d < RF_MAX_DIMS; ++d) { c[d] = r % ext[d]; r /= ext[d]; }
+        float accf = 0.0f; uint32_t accu = 0u;
+        for (int t = 0; t < ntaps; ++t) {
+            int64_t idx = 0, stride = 1;
+            for (int d = 0; d < ndim; ++d) {
+                int64_t v = c[d] + taps[t].offset[d];
+                if (v > taps[t].hi[d]) v = taps[t].hi[d];
+                if (v < taps[t].lo[d]) v = taps[t].lo[d];
+                if (v > ext[d] - 1) v = ext[d] - 1;
+                if (v < 0) v = 0;
+                idx += v * stride; stride *= ext[d];
+            }
+            if (dtype == RF_F32) accf = accf + taps[t].weight * ((const float*)in_dev)[idx];
+            else accu = accu + (uint32_t)(int32_t)(taps[t].weight < 0 ? taps[t].weight - 0.5f : taps[t].weight + 0.5f) * ((const uint32_t*)in_dev)[idx];
+        }
+        if (dtype == RF_F32) ((float*)out_dev)[i] = accf * post_scale;
+        else ((uint32_t*)out_dev)[i] = accu * (uint32_t)(int32_t)(post_scale < 0 ? post_scale - 0.5f : post_scale + 0.5f);
+    }
+    return RF_OK;
+}
+
+int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host, void* const* out_host)
+{
+    for (int i = 0; i < n; ++i) { int rc = rf_plan_execute(plan, in_host[i], out_host[i], 0); if (rc) return rc; }
+    return RF_OK;
+}
+
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms)
 {
     struct timespec a, b;

@@ -1130,6 +1130,72 @@ __global__ void narrow_kernel(const uint32_t* __restrict__ in, ST* __restrict__ 
         out[i] = (ST)in[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// pointwise linear stencil of one array (rf_stencil_execute): box-filter finite differencing etc.
+// ---------------------------------------------------------------------------------------------
+struct StencilParams {
+    int ndim, ntaps;
+    float post_scale;
+    int64_t extent[RF_MAX_DIMS];
+    int64_t total;
+    rf_tap tap[RF_MAX_TAPS];
+};
+
+template <typename CT>
+__global__ void __launch_bounds__(256) stencil_kernel(const __grid_constant__ StencilParams p, const CT* __restrict__ in,
+                                                      CT* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c[RF_MAX_DIMS], r = i;
+#pragma unroll
+        for (int d = 0; d < RF_MAX_DIMS; ++d) {
+            if (d < p.ndim) { c[d] = r % p.extent[d]; r /= p.extent[d]; } else c[d] = 0;
+        }
+        CT acc = (CT)0;
+        for (int t = 0; t < p.ntaps; ++t) {
+            int64_t idx = 0, stride = 1;
+#pragma unroll
+            for (int d = 0; d < RF_MAX_DIMS; ++d) {
+                if (d < p.ndim) {
+                    int64_t v = c[d] + p.tap[t].offset[d];
+                    v = min(v, (int64_t)p.tap[t].hi[d]);              // clamp(a, lo, hi) = max(min(a, hi), lo)
+                    v = max(v, (int64_t)p.tap[t].lo[d]);
+                    v = max((int64_t)0, min(v, p.extent[d] - 1));
+                    idx += v * stride; stride *= p.extent[d];
+                }
+            }
+            const CT w = std::is_same<CT, float>::value ? (CT)p.tap[t].weight : (CT)(int32_t)lrintf(p.tap[t].weight);
+            acc = acc + w * __ldg(in + idx);
+        }
+        out[i] = std::is_same<CT, float>::value ? acc * (CT)p.post_scale : acc * (CT)(int32_t)lrintf(p.post_scale);
+    }
+}
+
+// 1-D / 2-D arrays: 32-bit coordinates, one output per thread, rows on blockIdx.y -- neighbouring threads read
+// neighbouring words of every tap, so the taps are coalesced and mostly served by L1/L2
+template <typename CT>
+__global__ void __launch_bounds__(256) stencil2d_kernel(const __grid_constant__ StencilParams p, const CT* __restrict__ in,
+                                                        CT* __restrict__ out)
+{
+    const int W = (int)p.extent[0], Hh = p.ndim > 1 ? (int)p.extent[1] : 1;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const CT scale = std::is_same<CT, float>::value ? (CT)p.post_scale : (CT)(int32_t)lrintf(p.post_scale);
+    for (int y = blockIdx.y; y < Hh; y += gridDim.y) {
+        CT acc = (CT)0;
+        for (int t = 0; t < p.ntaps; ++t) {
+            int xx = max(min(x + p.tap[t].offset[0], p.tap[t].hi[0]), p.tap[t].lo[0]);
+            xx = max(0, min(xx, W - 1));
+            int yy = max(min(y + p.tap[t].offset[1], p.tap[t].hi[1]), p.tap[t].lo[1]);
+            yy = max(0, min(yy, Hh - 1));
+            const CT w = std::is_same<CT, float>::value ? (CT)p.tap[t].weight : (CT)(int32_t)lrintf(p.tap[t].weight);
+            acc = acc + w * __ldg(in + (size_t)yy * W + xx);
+        }
+        out[(size_t)y * W + x] = acc * scale;
+    }
+}
+
 } // namespace rfb
 
 // ---------------------------------------------------------------------------------------------
@@ -1605,6 +1671,32 @@ int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host,
 int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host)
 {
     return rf_plan_execute_host_batch(plan, 1, &in_host, &out_host);
+}
+
+int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, const rf_tap* taps, float post_scale,
+                       const void* in_dev, void* out_dev, void* stream)
+{
+    if (ndim < 1 || ndim > RF_MAX_DIMS || !extent || !taps) return fail(RF_EINVAL, "bad stencil descriptor");
+    if (ntaps < 1 || ntaps > RF_MAX_TAPS) return fail(RF_EINVAL, "a stencil has 1..%d taps", RF_MAX_TAPS);
+    if (dtype != RF_F32 && dtype != RF_I32 && dtype != RF_U32) return fail(RF_EUNSUPPORTED, "stencils need a 32-bit element type");
+    if (!in_dev || !out_dev) return fail(RF_EINVAL, "null buffer");
+    if (in_dev == out_dev) return fail(RF_EINVAL, "a stencil cannot run in place");
+    StencilParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.ndim = ndim; p.ntaps = ntaps; p.total = 1; p.post_scale = post_scale;
+    for (int d = 0; d < ndim; ++d) { if (extent[d] < 0) return fail(RF_EINVAL, "negative extent"); p.extent[d] = extent[d]; p.total *= extent[d]; }
+    for (int t = 0; t < ntaps; ++t) p.tap[t] = taps[t];
+    if (p.total == 0) return RF_OK;
+    const unsigned blocks = (unsigned)std::min<int64_t>((p.total + 255) / 256, 148 * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndim <= 2 && p.extent[0] < 0x7fffff00LL && (ndim < 2 || p.extent[1] < 0x7fffff00LL)) {
+        const dim3 grid((unsigned)((p.extent[0] + 255) / 256), (unsigned)std::min<int64_t>(ndim > 1 ? p.extent[1] : 1, 65535));
+        if (dtype == RF_F32) stencil2d_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)in_dev, (float*)out_dev);
+        else                 stencil2d_kernel<uint32_t><<<grid, 256, 0, st>>>(p, (const uint32_t*)in_dev, (uint32_t*)out_dev);
+    } else if (dtype == RF_F32) stencil_kernel<float><<<blocks, 256, 0, st>>>(p, (const float*)in_dev, (float*)out_dev);
+    else                        stencil_kernel<uint32_t><<<blocks, 256, 0, st>>>(p, (const uint32_t*)in_dev, (uint32_t*)out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return RF_OK;
 }
 
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter)

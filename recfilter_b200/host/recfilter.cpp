@@ -18,6 +18,9 @@
 #include <recfilter_b200.h>
 
 #include <cassert>
+#include <climits>
+#include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -49,14 +52,20 @@ struct RecFilterContents {
     // resolved input: an image (dense host buffer) or the result of another filter
     std::shared_ptr<BufferData> src_image;
     std::shared_ptr<RecFilterContents> src_filter;
+    // pointwise linear stencil of the input applied before the scans (empty: the input itself):
+    // box-filter finite differencing and similar epilogues (apps/box/box_filter.h:36-39)
+    vector<rf_tap> stencil;
+    float stencil_scale = 1.0f;     // common factor of the taps, applied after the sum
     vector<ScanDef> scans;
     std::map<string, int> tiles;    // split() hints
     rf_plan* plan = nullptr;
     void* dev_out = nullptr;        // device result buffer, reused across realize()/profile()
+    void* dev_tmp = nullptr;        // stencil output when scans follow
     ~RecFilterContents()
     {
         if (plan) rf_plan_destroy(plan);
         if (dev_out) rf_free(dev_out);
+        if (dev_tmp) rf_free(dev_tmp);
     }
     size_t count() const { size_t n = 1; for (const auto& d : dims) n *= (size_t)d.num_pixels(); return n; }
     int dim_index(const string& var) const
@@ -107,6 +116,129 @@ bool is_identity_index(const Expr& e, const string& name, int extent)
         return is_identity_index(v, name, extent);
     }
     return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// definitions that are a small linear stencil of ONE image / filter result:
+//   D(x,y) = (f(clamp(x+B,..), clamp(y+B,..)) - f(..) + ..) / area      (apps/box/box_filter.h:36-39)
+// possibly through pure helper Funcs (fA(u,v) = ..., box_filter.h:122-131), which are inlined.
+// ---------------------------------------------------------------------------------------------
+struct IndexMap {                  // clamp(var_dim + off, lo, hi)
+    int dim = -1;
+    long long off = 0, lo = INT32_MIN, hi = INT32_MAX;
+};
+struct LinTap {
+    double w = 0.0;
+    std::shared_ptr<BufferData> image;
+    std::shared_ptr<RecFilterContents> filter;
+    vector<IndexMap> idx;
+};
+typedef std::map<string, IndexMap> IndexEnv;
+
+bool const_value(const Expr& e, double& v)
+{
+    if (!e.defined()) return false;
+    const ExprNode& n = *e.node;
+    double a, b;
+    switch (n.kind) {
+    case ExprNode::Const: v = n.value; return true;
+    case ExprNode::Cast:  return const_value(n.args[0], v);
+    case ExprNode::Add: if (const_value(n.args[0], a) && const_value(n.args[1], b)) { v = a + b; return true; } return false;
+    case ExprNode::Sub: if (const_value(n.args[0], a) && const_value(n.args[1], b)) { v = a - b; return true; } return false;
+    case ExprNode::Mul: if (const_value(n.args[0], a) && const_value(n.args[1], b)) { v = a * b; return true; } return false;
+    case ExprNode::Div: if (const_value(n.args[0], a) && const_value(n.args[1], b) && b != 0.0) { v = a / b; return true; } return false;
+    default: return false;
+    }
+}
+
+IndexMap eval_index(const RecFilterContents& c, const Expr& e, const IndexEnv& env)
+{
+    if (!e.defined()) die("RecFilter " + c.name + ": undefined index expression");
+    const ExprNode& n = *e.node;
+    double k;
+    auto shift = [](IndexMap m, long long d) {
+        m.off += d;
+        if (m.lo != INT32_MIN) m.lo += d;
+        if (m.hi != INT32_MAX) m.hi += d;
+        return m;
+    };
+    switch (n.kind) {
+    case ExprNode::Variable: {
+        auto it = env.find(n.name);
+        if (it != env.end()) return it->second;
+        IndexMap m; m.dim = c.dim_index(n.name);
+        if (m.dim < 0) die("RecFilter " + c.name + ": variable " + n.name + " in an index is not a dimension of the filter");
+        return m;
+    }
+    case ExprNode::Cast: return eval_index(c, n.args[0], env);
+    case ExprNode::Add:
+        if (const_value(n.args[1], k)) return shift(eval_index(c, n.args[0], env), (long long)k);
+        if (const_value(n.args[0], k)) return shift(eval_index(c, n.args[1], env), (long long)k);
+        break;
+    case ExprNode::Sub:
+        if (const_value(n.args[1], k)) return shift(eval_index(c, n.args[0], env), -(long long)k);
+        break;
+    case ExprNode::Min:
+    case ExprNode::Max: {
+        const bool c1 = const_value(n.args[1], k);
+        if (!c1 && !const_value(n.args[0], k)) break;
+        IndexMap m = eval_index(c, n.args[c1 ? 0 : 1], env);
+        const long long kk = (long long)k;
+        if (n.kind == ExprNode::Min) { m.lo = m.lo == INT32_MIN ? m.lo : std::min(m.lo, kk); m.hi = std::min(m.hi, kk); }
+        else                         { m.lo = std::max(m.lo, kk); m.hi = m.hi == INT32_MAX ? m.hi : std::max(m.hi, kk); }
+        return m;
+    }
+    default: break;
+    }
+    die("RecFilter " + c.name + ": index expressions must be a dimension plus a constant, optionally clamped "
+        "(min / max / clamp with constants)");
+}
+
+// e -> list of taps (+ a constant term that must vanish)
+void linearize(const RecFilterContents& c, const Expr& e, const IndexEnv& env, double scale, vector<LinTap>& taps,
+               double& constant, int depth = 0)
+{
+    if (!e.defined()) die("RecFilter " + c.name + ": undefined expression in the definition");
+    if (depth > 32) die("RecFilter " + c.name + ": Func definitions nest too deeply (recursive definition?)");
+    const ExprNode& n = *e.node;
+    double k;
+    if (const_value(e, k)) { constant += scale * k; return; }
+    switch (n.kind) {
+    case ExprNode::Cast: linearize(c, n.args[0], env, scale, taps, constant, depth); return;
+    case ExprNode::Add:
+        linearize(c, n.args[0], env, scale, taps, constant, depth);
+        linearize(c, n.args[1], env, scale, taps, constant, depth);
+        return;
+    case ExprNode::Sub:
+        linearize(c, n.args[0], env, scale, taps, constant, depth);
+        linearize(c, n.args[1], env, -scale, taps, constant, depth);
+        return;
+    case ExprNode::Mul:
+        if (const_value(n.args[0], k)) { linearize(c, n.args[1], env, scale * k, taps, constant, depth); return; }
+        if (const_value(n.args[1], k)) { linearize(c, n.args[0], env, scale * k, taps, constant, depth); return; }
+        break;
+    case ExprNode::Div:
+        if (const_value(n.args[1], k) && k != 0.0) { linearize(c, n.args[0], env, scale / k, taps, constant, depth); return; }
+        break;
+    case ExprNode::Load:
+    case ExprNode::Call: {
+        if (n.kind == ExprNode::Call && !n.filter) {              // pure Func: inline its definition
+            if (!n.func || !n.func->body.defined()) die("RecFilter " + c.name + ": call of an undefined Func");
+            if (n.func->args.size() != n.args.size()) die("RecFilter " + c.name + ": Func called with the wrong number of arguments");
+            IndexEnv inner;
+            for (size_t i = 0; i < n.args.size(); ++i) inner[n.func->args[i]] = eval_index(c, n.args[i], env);
+            linearize(c, n.func->body, inner, scale, taps, constant, depth + 1);
+            return;
+        }
+        LinTap t; t.w = scale; t.image = n.kind == ExprNode::Load ? n.buffer : nullptr; t.filter = n.filter;
+        for (const Expr& a : n.args) t.idx.push_back(eval_index(c, a, env));
+        taps.push_back(t);
+        return;
+    }
+    default: break;
+    }
+    die("RecFilter " + c.name + ": the definition must be linear in the image / filter it reads (sums, differences and "
+        "constant factors of taps); general expressions are not supported by the B200 engine");
 }
 
 void build_plan(RecFilterContents& c)
@@ -174,17 +306,37 @@ void* input_device(RecFilterContents& c, bool& owned)
     return dev;
 }
 
+// run filter c on the device buffer `in`: the stencil of the definition (if any), then the scans
+void* run_filter(RecFilterContents& c, const void* in)
+{
+    const size_t bytes = c.count() * (size_t)c.type.bytes();
+    if (!c.dev_out) engine_check(rf_malloc(&c.dev_out, bytes), "rf_malloc");
+    if (!c.stencil.empty()) {
+        int64_t ext[RF_MAX_DIMS] = { 1, 1, 1, 1 };
+        for (size_t i = 0; i < c.dims.size(); ++i) ext[i] = c.dims[i].num_pixels();
+        void* dst = c.dev_out;
+        if (!c.scans.empty()) {
+            if (!c.dev_tmp) engine_check(rf_malloc(&c.dev_tmp, bytes), "rf_malloc");
+            dst = c.dev_tmp;
+        }
+        engine_check(rf_stencil_execute((int)c.dims.size(), ext, engine_dtype(c.type), (int)c.stencil.size(), c.stencil.data(),
+                                        c.stencil_scale, in, dst, nullptr), "rf_stencil_execute");
+        if (c.scans.empty()) return c.dev_out;
+        in = dst;
+    }
+    build_plan(c);
+    engine_check(rf_plan_execute(c.plan, in, c.dev_out, nullptr), "rf_plan_execute");
+    return c.dev_out;
+}
+
 void* evaluate_device(RecFilterContents& c)
 {
     if (!c.defined) die("RecFilter " + c.name + " is used before it is defined");
-    build_plan(c);
-    const size_t bytes = c.count() * (size_t)c.type.bytes();
-    if (!c.dev_out) engine_check(rf_malloc(&c.dev_out, bytes), "rf_malloc");
     bool owned = false;
     void* in = input_device(c, owned);
-    engine_check(rf_plan_execute(c.plan, in, c.dev_out, nullptr), "rf_plan_execute");
+    void* out = run_filter(c, in);
     if (owned) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(in), "rf_free"); }
-    return c.dev_out;
+    return out;
 }
 
 // every plan of the chain ending in c, upstream first
@@ -277,25 +429,66 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     c.src_image.reset(); c.src_filter.reset();
     if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
 
-    const ExprNode& n = *e.node;
-    bool identity = n.args.size() == c.dims.size();
-    for (size_t i = 0; identity && i < c.dims.size(); ++i)
-        identity = is_identity_index(n.args[i], c.dims[i].var().name(), c.dims[i].num_pixels());
-    if (n.kind == ExprNode::Load && identity) {
-        if (!n.buffer) die("RecFilter " + c.name + ": the image in the definition has no data");
+    vector<LinTap> taps;
+    double constant = 0.0;
+    linearize(c, e, IndexEnv(), 1.0, taps, constant);
+    if (taps.empty()) die("RecFilter " + c.name + ": the definition does not read an image or a filter");
+    if (constant != 0.0) die("RecFilter " + c.name + ": constant terms in the definition are not supported");
+    // merge equal taps, check that everything reads the same source with the filter's own dimension order
+    vector<LinTap> merged;
+    for (const LinTap& t : taps) {
+        if (t.image != taps[0].image || t.filter != taps[0].filter)
+            die("RecFilter " + c.name + ": the definition may read one image or one filter only");
+        if (t.idx.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch in the definition");
+        for (size_t i = 0; i < t.idx.size(); ++i)
+            if (t.idx[i].dim != (int)i) die("RecFilter " + c.name + ": indices must use the filter's dimensions in order");
+        bool found = false;
+        for (LinTap& m : merged) {
+            bool same = true;
+            for (size_t i = 0; same && i < t.idx.size(); ++i)
+                same = m.idx[i].off == t.idx[i].off && m.idx[i].lo == t.idx[i].lo && m.idx[i].hi == t.idx[i].hi;
+            if (same) { m.w += t.w; found = true; break; }
+        }
+        if (!found) merged.push_back(t);
+    }
+    if (taps[0].image) {
+        if (!taps[0].image) die("RecFilter " + c.name + ": the image in the definition has no data");
         for (size_t i = 0; i < c.dims.size(); ++i)
-            if (n.buffer->extent[i] < c.dims[i].num_pixels())
+            if (taps[0].image->extent[i] < c.dims[i].num_pixels())
                 die("RecFilter " + c.name + ": the image is smaller than the filter domain");
-        c.src_image = n.buffer;
-        c.type = n.buffer->type;                                    // type of the filter = type of the RHS (lib/recfilter.cpp:197)
-    } else if (n.kind == ExprNode::Call && identity && n.filter) {
-        if (!n.filter->defined) die("RecFilter " + c.name + ": the filter called in the definition is not defined");
-        if (n.filter->dims.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch with the called filter");
-        c.src_filter = n.filter;
-        c.type = n.filter->type;
+        c.src_image = taps[0].image;
+        c.type = taps[0].image->type;                               // type of the filter = type of the RHS (lib/recfilter.cpp:197)
     } else {
-        die("RecFilter " + c.name + ": the B200 engine filters an image or another filter's result indexed by the "
-            "filter's own dimensions (optionally clamped to the image); general expressions are not supported");
+        if (!taps[0].filter->defined) die("RecFilter " + c.name + ": the filter called in the definition is not defined");
+        if (taps[0].filter->dims.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch with the called filter");
+        c.src_filter = taps[0].filter;
+        c.type = taps[0].filter->type;
+    }
+    // a single unit tap whose indices are the identity inside the domain is the input itself
+    c.stencil.clear();
+    bool identity = merged.size() == 1 && merged[0].w == 1.0;
+    for (size_t i = 0; identity && i < c.dims.size(); ++i) {
+        const IndexMap& m = merged[0].idx[i];
+        identity = m.off == 0 && m.lo <= 0 && m.hi >= (long long)c.dims[i].num_pixels() - 1;
+    }
+    if (!identity) {
+        if (merged.size() > RF_MAX_TAPS) die("RecFilter " + c.name + ": too many taps in the definition");
+        if (c.type.bytes() != 4) die("RecFilter " + c.name + ": stencil definitions need a 32-bit element type");
+        // factor the first weight out: "(a - b - c + d) / area" becomes unit taps and one scale after the sum
+        const double w0 = merged[0].w != 0.0 ? merged[0].w : 1.0;
+        c.stencil_scale = (float)w0;
+        for (const LinTap& t : merged) {
+            rf_tap rt;
+            std::memset(&rt, 0, sizeof(rt));
+            rt.weight = (float)(t.w / w0);
+            for (int d = 0; d < RF_MAX_DIMS; ++d) { rt.lo[d] = INT32_MIN; rt.hi[d] = INT32_MAX; }
+            for (size_t i = 0; i < t.idx.size(); ++i) {
+                rt.offset[i] = (int32_t)t.idx[i].off;
+                rt.lo[i] = (int32_t)std::max<long long>(t.idx[i].lo, INT32_MIN);
+                rt.hi[i] = (int32_t)std::min<long long>(t.idx[i].hi, INT32_MAX);
+            }
+            c.stencil.push_back(rt);
+        }
     }
     c.defined = true;
 }
@@ -392,7 +585,7 @@ vector<RecFilter> RecFilter::cascade(vector<vector<int> > groups)
         RecFilter f(c.name + "_" + std::to_string(g));
         RecFilterContents& fc = *f.contents;
         fc.dims = c.dims; fc.type = c.type; fc.clamped = c.clamped; fc.defined = true;
-        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; }
+        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; fc.stencil = c.stencil; fc.stencil_scale = c.stencil_scale; }
         else        { fc.src_filter = out[g - 1].contents; }
         vector<int> ids = groups[g];
         std::sort(ids.begin(), ids.end());                           // add_filter order inside a group
@@ -435,7 +628,7 @@ RecFilter RecFilter::overlap_to_higher_order_filter(RecFilter fB, string overlap
     RecFilter ab(overlap_name);
     RecFilterContents& c = *ab.contents;
     c.dims = a.dims; c.type = a.type; c.clamped = a.clamped; c.defined = true;
-    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter;
+    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter; c.stencil = a.stencil; c.stencil_scale = a.stencil_scale;
     for (size_t d = 0; d < a.dims.size(); ++d) {
         vector<const ScanDef*> sa, sb;
         for (const ScanDef& s : a.scans) if (s.dim == (int)d) sa.push_back(&s);
@@ -504,18 +697,11 @@ float RecFilter::profile(int iterations)
     if (iterations < 1) iterations = 1;
     vector<RecFilterContents*> chain;
     collect_chain(c, chain);
-    for (RecFilterContents* f : chain) {
-        build_plan(*f);
-        if (!f->dev_out) engine_check(rf_malloc(&f->dev_out, f->count() * (size_t)f->type.bytes()), "rf_malloc");
-    }
     bool owned = false;
     void* root_in = input_device(*chain[0], owned);                   // the image stays resident: kernels only are timed
     auto run_chain = [&]() {
         const void* in = root_in;
-        for (RecFilterContents* f : chain) {
-            engine_check(rf_plan_execute(f->plan, in, f->dev_out, nullptr), "rf_plan_execute");
-            in = f->dev_out;
-        }
+        for (RecFilterContents* f : chain) in = run_filter(*f, in);
     };
     run_chain();                                                      // warm-up (lib/recfilter.cpp:995-997)
     void* clock = nullptr;

@@ -283,3 +283,29 @@ def test_stacked_images_equal_per_image_filtering(oracle):
     plan2.close()
     truth = oracle.apply_filter(stack[1].astype(np.float64), C3, "clamp", threads=8)
     assert rel_err(out3[1], truth) <= TOL
+
+
+def test_box_filter_from_summed_table_bit_exact_on_integers(oracle):
+    """apps/box/box_filter.h:36-39 through the C ABI: summed-area table (u32-exact values in fp32) followed by the
+    4-tap finite-differencing stencil equals a direct (2B+1)^2 box sum."""
+    import torch
+    from recfilter_b200.capi import stencil
+    B, n = 5, 512
+    rng = np.random.default_rng(11)
+    img = np.zeros((n, n), np.float32)
+    img[8:-8, 8:-8] = rng.integers(0, 16, size=(n - 16, n - 16)).astype(np.float32)
+    sat_scans = [(0, True, [1.0, 1.0]), (1, True, [1.0, 1.0])]
+    plan = Plan((n, n), "f32", [Scan(*s) for s in sat_scans])
+    sat = torch.from_numpy(plan.realize(img)).cuda()
+    plan.close()
+    hi = [n - 1, n - 1]
+    taps = [(1.0, [B, B], [0, 0], hi), (-1.0, [B, -B - 1], [0, 0], hi), (1.0, [-B - 1, -B - 1], [0, 0], hi),
+            (-1.0, [-B - 1, B], [0, 0], hi)]
+    out = stencil(sat, taps, 1.0).cpu().numpy()
+    ref = np.zeros_like(img, dtype=np.float64)
+    pad = np.pad(img.astype(np.float64), B)
+    for dy in range(2 * B + 1):
+        for dx in range(2 * B + 1):
+            ref += pad[dy:dy + n, dx:dx + n]
+    inner = (slice(B + 1, n - B - 1),) * 2
+    np.testing.assert_array_equal(out[inner], ref[inner].astype(np.float32))

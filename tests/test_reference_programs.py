@@ -25,7 +25,11 @@ APPS = [("summed_table", ["-w", "512", "-t", "32"], True),
         ("gaussian_filter_3x_3y", ["-w", "512", "-t", "32", "-iter", "2"], False),
         ("gaussian_filter_1xy_2xy", ["-w", "256", "-t", "32", "-iter", "1"], False),
         ("gaussian_filter_1xy_2x_2y", ["-w", "256", "-t", "32", "-iter", "1"], False),
-        ("gaussian_filter_1xy_1xy_1xy", ["-w", "256", "-t", "32", "-iter", "1"], False)]
+        ("gaussian_filter_1xy_1xy_1xy", ["-w", "256", "-t", "32", "-iter", "1"], False),
+        # apps/box: summed-area tables + finite differencing Funcs (pointwise stencil epilogue)
+        ("box_filter_1", ["-w", "512", "-t", "32", "-iter", "2"], False),
+        ("box_filter_3", ["-w", "512", "-t", "32", "-iter", "2"], False),
+        ("box_filter_6", ["-w", "512", "-t", "32", "-iter", "2"], False)]
 MAX_PERCENT = 1e-3          # the programs print percent: 1e-3 % == 1e-5 relative (BASELINE.json tolerance)
 
 
@@ -90,6 +94,24 @@ def test_reference_apps_on_b200(prog, args, checks, tmp_path):
         assert max_error(out) is not None and max_error(out) <= MAX_PERCENT
     else:
         assert "ms per iteration" in out
+
+
+def _box_check(kind, tmp_path):
+    # tests/cpp/box_check.cpp: the reference's box_filter.h (unchanged) against direct box averaging
+    rc, out = run(kind, "box_check", ["128"], cwd=tmp_path)
+    errs = [float(v) for v in re.findall(r"Max\s+relative error = (\S+) %", out)]
+    assert rc == 0 and len(errs) == 2, out[-2000:]
+    assert errs[0] <= 1e-3            # one box: exact summed table, one rounding
+    assert errs[1] <= 5e-2            # box twice through a 2nd-order integral image (fp32-unstable by construction)
+
+
+def test_reference_box_filters_match_direct_box_on_oracle_backend(tmp_path):
+    _box_check("pin", tmp_path)
+
+
+@pytest.mark.gpu
+def test_reference_box_filters_match_direct_box_on_b200(tmp_path):
+    _box_check("gpu", tmp_path)
 
 
 @pytest.mark.gpu
