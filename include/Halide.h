@@ -197,6 +197,8 @@ public:
     Var(const std::string& name) : n(name) {}
     const std::string& name() const { return n; }
     static std::string unique_name() { static int counter = 0; return "_v" + std::to_string(counter++); }
+    static Var gpu_blocks() { return Var("__block_id_x"); }       // schedule granularities: accepted, ignored
+    static Var gpu_threads() { return Var("__thread_id_x"); }
     operator Expr() const
     {
         auto e = std::make_shared<ExprNode>();

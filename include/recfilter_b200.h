@@ -145,18 +145,21 @@ int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host,
  * are large numbers whose differences must be taken before scaling) -- the finite
  * differencing that turns a summed-area table into a box filter (apps/box/box_filter.h:36-39, 128-139 in the
  * reference, where it is a separate Halide Func scheduled with compute_root) and similar small linear stencils
- * of one filter result.  Indices are additionally clamped to the array.  dtype: RF_F32, RF_I32 or RF_U32
+ * of one filter result, or of two arrays of the same shape (unsharp mask: (1+w)*image - w*blur,
+ * apps/usm/unsharp_mask_naive.cpp:61; in2_dev may be NULL when no tap reads source 1).  Indices are
+ * additionally clamped to the array.  dtype: RF_F32, RF_I32 or RF_U32
  * (integer weights are the rounded float weights, arithmetic wraps).  in_dev and out_dev must not alias.
  */
 #define RF_MAX_TAPS 32
 typedef struct rf_tap {
     float   weight;
+    int32_t source;                     /* 0: in_dev, 1: in2_dev (e.g. the original image beside its blur) */
     int32_t offset[RF_MAX_DIMS];
     int32_t lo[RF_MAX_DIMS];            /* INT32_MIN: no lower clamp */
     int32_t hi[RF_MAX_DIMS];            /* INT32_MAX: no upper clamp */
 } rf_tap;
 int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, const rf_tap* taps, float post_scale,
-                       const void* in_dev, void* out_dev, void* stream);
+                       const void* in_dev, const void* in2_dev, void* out_dev, void* stream);
 
 /* Time `iters` executions on device-resident data with CUDA events (ms per iteration). */
 int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters, float* ms_per_iter);

@@ -85,7 +85,7 @@ int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stre
 int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host) { return rf_plan_execute(plan, in_host, out_host, 0); }
 /* pointwise linear stencil (plain loops; the reference's box_filter.h differencing Func) */
 int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, const rf_tap* taps, float post_scale,
-                       const void* in_dev, void* out_dev, void* stream)
+                       const void* in_dev, const void* in2_dev, void* out_dev, void* stream)
 {
     (void)stream;
     if (ndim < 1 || ndim > RF_MAX_DIMS || ntaps < 1 || ntaps > RF_MAX_TAPS || !in_dev || !out_dev || in_dev == out_dev) return RF_EINVAL;
@@ -106,8 +106,10 @@ int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, co
                 if (v < 0) v = 0;
                 idx += v * stride; stride *= ext[d];
             }
-            if (dtype == RF_F32) accf = accf + taps[t].weight * ((const float*)in_dev)[idx];
-            else accu = accu + (uint32_t)(int32_t)(taps[t].weight < 0 ? taps[t].weight - 0.5f : taps[t].weight + 0.5f) * ((const uint32_t*)in_dev)[idx];
+            const void* src = taps[t].source ? in2_dev : in_dev;
+            if (!src) return RF_EINVAL;
+            if (dtype == RF_F32) accf = accf + taps[t].weight * ((const float*)src)[idx];
+            else accu = accu + (uint32_t)(int32_t)(taps[t].weight < 0 ? taps[t].weight - 0.5f : taps[t].weight + 0.5f) * ((const uint32_t*)src)[idx];
         }
         if (dtype == RF_F32) ((float*)out_dev)[i] = accf * post_scale;
         else ((uint32_t*)out_dev)[i] = accu * (uint32_t)(int32_t)(post_scale < 0 ? post_scale - 0.5f : post_scale + 0.5f);

@@ -93,7 +93,7 @@ def lib():
     L.rf_plan_execute_host.argtypes = [vp, vp, vp]
     L.rf_plan_execute_host_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.rf_plan_profile.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_float)]
-    L.rf_stencil_execute.argtypes = [i32, C.POINTER(C.c_int64), i32, i32, vp, C.c_float, vp, vp, vp]
+    L.rf_stencil_execute.argtypes = [i32, C.POINTER(C.c_int64), i32, i32, vp, C.c_float, vp, vp, vp, vp]
     L.rf_plan_shard_tail_bytes.argtypes = [vp]
     L.rf_plan_shard_tail_bytes.restype = sz
     L.rf_plan_stage1.argtypes = [vp, vp, vp, vp, vp]
@@ -314,10 +314,11 @@ class Plan:
 
 
 class _Tap(C.Structure):
-    _fields_ = [("weight", C.c_float), ("offset", C.c_int32 * 4), ("lo", C.c_int32 * 4), ("hi", C.c_int32 * 4)]
+    _fields_ = [("weight", C.c_float), ("source", C.c_int32), ("offset", C.c_int32 * 4), ("lo", C.c_int32 * 4),
+                ("hi", C.c_int32 * 4)]
 
 
-def stencil(src, taps, post_scale: float = 1.0, dst=None):
+def stencil(src, taps, post_scale: float = 1.0, dst=None, src2=None):
     """Pointwise linear stencil of a torch CUDA tensor (rf_stencil_execute): taps are
     (weight, offsets[, lo, hi]) with offsets / clamps per dimension, dimension 0 = contiguous.
     out(x) = post_scale * sum_i w_i * src(clamp(x + off_i, lo_i, hi_i))."""
@@ -332,12 +333,14 @@ def stencil(src, taps, post_scale: float = 1.0, dst=None):
         lo = t[2] if len(t) > 2 else [None] * nd
         hi = t[3] if len(t) > 3 else [None] * nd
         arr[i].weight = float(w)
+        arr[i].source = int(t[4]) if len(t) > 4 else 0
         for d in range(4):
             arr[i].offset[d] = int(off[d]) if d < nd else 0
             arr[i].lo[d] = int(lo[d]) if d < nd and lo[d] is not None else -2**31
             arr[i].hi[d] = int(hi[d]) if d < nd and hi[d] is not None else 2**31 - 1
     dt = {torch.float32: 0, torch.int32: 2}[src.dtype]
     _check(lib().rf_stencil_execute(nd, ext, dt, len(taps), C.cast(arr, C.c_void_p), float(post_scale),
-                                    C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                    C.c_void_p(src.data_ptr()), C.c_void_p(src2.data_ptr() if src2 is not None else None),
+                                    C.c_void_p(dst.data_ptr()),
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "rf_stencil_execute")
     return dst

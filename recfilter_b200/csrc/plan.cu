@@ -1144,7 +1144,7 @@ struct StencilParams {
 
 template <typename CT>
 __global__ void __launch_bounds__(256) stencil_kernel(const __grid_constant__ StencilParams p, const CT* __restrict__ in,
-                                                      CT* __restrict__ out)
+                                                      const CT* __restrict__ in2, CT* __restrict__ out)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t c[RF_MAX_DIMS], r = i;
@@ -1166,7 +1166,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const __grid_constant__ St
                 }
             }
             const CT w = std::is_same<CT, float>::value ? (CT)p.tap[t].weight : (CT)(int32_t)lrintf(p.tap[t].weight);
-            acc = acc + w * __ldg(in + idx);
+            acc = acc + w * __ldg((p.tap[t].source ? in2 : in) + idx);
         }
         out[i] = std::is_same<CT, float>::value ? acc * (CT)p.post_scale : acc * (CT)(int32_t)lrintf(p.post_scale);
     }
@@ -1176,7 +1176,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const __grid_constant__ St
 // neighbouring words of every tap, so the taps are coalesced and mostly served by L1/L2
 template <typename CT>
 __global__ void __launch_bounds__(256) stencil2d_kernel(const __grid_constant__ StencilParams p, const CT* __restrict__ in,
-                                                        CT* __restrict__ out)
+                                                        const CT* __restrict__ in2, CT* __restrict__ out)
 {
     const int W = (int)p.extent[0], Hh = p.ndim > 1 ? (int)p.extent[1] : 1;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(256) stencil2d_kernel(const __grid_constant__ 
             int yy = max(min(y + p.tap[t].offset[1], p.tap[t].hi[1]), p.tap[t].lo[1]);
             yy = max(0, min(yy, Hh - 1));
             const CT w = std::is_same<CT, float>::value ? (CT)p.tap[t].weight : (CT)(int32_t)lrintf(p.tap[t].weight);
-            acc = acc + w * __ldg(in + (size_t)yy * W + xx);
+            acc = acc + w * __ldg((p.tap[t].source ? in2 : in) + (size_t)yy * W + xx);
         }
         out[(size_t)y * W + x] = acc * scale;
     }
@@ -1674,13 +1674,16 @@ int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host)
 }
 
 int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, const rf_tap* taps, float post_scale,
-                       const void* in_dev, void* out_dev, void* stream)
+                       const void* in_dev, const void* in2_dev, void* out_dev, void* stream)
 {
     if (ndim < 1 || ndim > RF_MAX_DIMS || !extent || !taps) return fail(RF_EINVAL, "bad stencil descriptor");
     if (ntaps < 1 || ntaps > RF_MAX_TAPS) return fail(RF_EINVAL, "a stencil has 1..%d taps", RF_MAX_TAPS);
     if (dtype != RF_F32 && dtype != RF_I32 && dtype != RF_U32) return fail(RF_EUNSUPPORTED, "stencils need a 32-bit element type");
     if (!in_dev || !out_dev) return fail(RF_EINVAL, "null buffer");
-    if (in_dev == out_dev) return fail(RF_EINVAL, "a stencil cannot run in place");
+    if (in_dev == out_dev || in2_dev == out_dev) return fail(RF_EINVAL, "a stencil cannot run in place");
+    for (int t = 0; t < ntaps; ++t)
+        if (taps[t].source < 0 || taps[t].source > 1 || (taps[t].source == 1 && !in2_dev))
+            return fail(RF_EINVAL, "tap %d reads a source that was not given", t);
     StencilParams p;
     std::memset(&p, 0, sizeof(p));
     p.ndim = ndim; p.ntaps = ntaps; p.total = 1; p.post_scale = post_scale;
@@ -1691,10 +1694,10 @@ int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, co
     cudaStream_t st = (cudaStream_t)stream;
     if (ndim <= 2 && p.extent[0] < 0x7fffff00LL && (ndim < 2 || p.extent[1] < 0x7fffff00LL)) {
         const dim3 grid((unsigned)((p.extent[0] + 255) / 256), (unsigned)std::min<int64_t>(ndim > 1 ? p.extent[1] : 1, 65535));
-        if (dtype == RF_F32) stencil2d_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)in_dev, (float*)out_dev);
-        else                 stencil2d_kernel<uint32_t><<<grid, 256, 0, st>>>(p, (const uint32_t*)in_dev, (uint32_t*)out_dev);
-    } else if (dtype == RF_F32) stencil_kernel<float><<<blocks, 256, 0, st>>>(p, (const float*)in_dev, (float*)out_dev);
-    else                        stencil_kernel<uint32_t><<<blocks, 256, 0, st>>>(p, (const uint32_t*)in_dev, (uint32_t*)out_dev);
+        if (dtype == RF_F32) stencil2d_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)in_dev, (const float*)in2_dev, (float*)out_dev);
+        else                 stencil2d_kernel<uint32_t><<<grid, 256, 0, st>>>(p, (const uint32_t*)in_dev, (const uint32_t*)in2_dev, (uint32_t*)out_dev);
+    } else if (dtype == RF_F32) stencil_kernel<float><<<blocks, 256, 0, st>>>(p, (const float*)in_dev, (const float*)in2_dev, (float*)out_dev);
+    else                        stencil_kernel<uint32_t><<<blocks, 256, 0, st>>>(p, (const uint32_t*)in_dev, (const uint32_t*)in2_dev, (uint32_t*)out_dev);
     CUDA_TRY(cudaGetLastError());
     return RF_OK;
 }

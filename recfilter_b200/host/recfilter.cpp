@@ -56,6 +56,10 @@ struct RecFilterContents {
     // box-filter finite differencing and similar epilogues (apps/box/box_filter.h:36-39)
     vector<rf_tap> stencil;
     float stencil_scale = 1.0f;     // common factor of the taps, applied after the sum
+    // second source of a stencil: an image read beside the result of src_filter
+    // (unsharp mask: (1+w)*image - w*blur, apps/usm/unsharp_mask_naive.cpp:61); taps with source == 1 read it
+    std::shared_ptr<BufferData> side_image;
+    void* dev_side = nullptr;
     vector<ScanDef> scans;
     std::map<string, int> tiles;    // split() hints
     rf_plan* plan = nullptr;
@@ -66,6 +70,7 @@ struct RecFilterContents {
         if (plan) rf_plan_destroy(plan);
         if (dev_out) rf_free(dev_out);
         if (dev_tmp) rf_free(dev_tmp);
+        if (dev_side) rf_free(dev_side);
     }
     size_t count() const { size_t n = 1; for (const auto& d : dims) n *= (size_t)d.num_pixels(); return n; }
     int dim_index(const string& var) const
@@ -274,15 +279,12 @@ void build_plan(RecFilterContents& c)
 // `owned` tells the caller whether it must free the buffer.
 void* evaluate_device(RecFilterContents& c);
 
-void* input_device(RecFilterContents& c, bool& owned)
+// dense device copy of the [0, extent) box of a host image (which may be larger than the filter domain)
+void* upload_image(RecFilterContents& c, const BufferData& b)
 {
     const size_t bytes = c.count() * (size_t)c.type.bytes();
-    if (c.src_filter) { owned = false; return evaluate_device(*c.src_filter); }
-    if (!c.src_image) die("RecFilter " + c.name + ": the input image is not set (ImageParam::set was not called?)");
     void* dev = nullptr;
     engine_check(rf_malloc(&dev, bytes), "rf_malloc");
-    owned = true;
-    const BufferData& b = *c.src_image;
     bool same = b.dims == (int)c.dims.size();
     for (int i = 0; same && i < b.dims; ++i) same = b.extent[i] == c.dims[i].num_pixels();
     if (same) {
@@ -306,6 +308,14 @@ void* input_device(RecFilterContents& c, bool& owned)
     return dev;
 }
 
+void* input_device(RecFilterContents& c, bool& owned)
+{
+    if (c.src_filter) { owned = false; return evaluate_device(*c.src_filter); }
+    if (!c.src_image) die("RecFilter " + c.name + ": the input image is not set (ImageParam::set was not called?)");
+    owned = true;
+    return upload_image(c, *c.src_image);
+}
+
 // run filter c on the device buffer `in`: the stencil of the definition (if any), then the scans
 void* run_filter(RecFilterContents& c, const void* in)
 {
@@ -319,8 +329,9 @@ void* run_filter(RecFilterContents& c, const void* in)
             if (!c.dev_tmp) engine_check(rf_malloc(&c.dev_tmp, bytes), "rf_malloc");
             dst = c.dev_tmp;
         }
+        if (c.side_image && !c.dev_side) c.dev_side = upload_image(c, *c.side_image);   // stays resident
         engine_check(rf_stencil_execute((int)c.dims.size(), ext, engine_dtype(c.type), (int)c.stencil.size(), c.stencil.data(),
-                                        c.stencil_scale, in, dst, nullptr), "rf_stencil_execute");
+                                        c.stencil_scale, in, c.dev_side, dst, nullptr), "rf_stencil_execute");
         if (c.scans.empty()) return c.dev_out;
         in = dst;
     }
@@ -434,39 +445,52 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     linearize(c, e, IndexEnv(), 1.0, taps, constant);
     if (taps.empty()) die("RecFilter " + c.name + ": the definition does not read an image or a filter");
     if (constant != 0.0) die("RecFilter " + c.name + ": constant terms in the definition are not supported");
-    // merge equal taps, check that everything reads the same source with the filter's own dimension order
+    // merge equal taps; everything must read ONE filter result and / or ONE image, with the filter's own
+    // dimension order.  With both, the filter result is source 0 and the image source 1.
+    std::shared_ptr<BufferData> image;
+    std::shared_ptr<RecFilterContents> filter;
+    for (const LinTap& t : taps) {
+        if (t.filter) { if (filter && filter != t.filter) die("RecFilter " + c.name + ": the definition may read one filter only"); filter = t.filter; }
+        else          { if (image && image != t.image) die("RecFilter " + c.name + ": the definition may read one image only"); image = t.image; }
+    }
     vector<LinTap> merged;
     for (const LinTap& t : taps) {
-        if (t.image != taps[0].image || t.filter != taps[0].filter)
-            die("RecFilter " + c.name + ": the definition may read one image or one filter only");
         if (t.idx.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch in the definition");
         for (size_t i = 0; i < t.idx.size(); ++i)
             if (t.idx[i].dim != (int)i) die("RecFilter " + c.name + ": indices must use the filter's dimensions in order");
         bool found = false;
         for (LinTap& m : merged) {
-            bool same = true;
+            bool same = m.image == t.image && m.filter == t.filter;
             for (size_t i = 0; same && i < t.idx.size(); ++i)
                 same = m.idx[i].off == t.idx[i].off && m.idx[i].lo == t.idx[i].lo && m.idx[i].hi == t.idx[i].hi;
             if (same) { m.w += t.w; found = true; break; }
         }
         if (!found) merged.push_back(t);
     }
-    if (taps[0].image) {
-        if (!taps[0].image) die("RecFilter " + c.name + ": the image in the definition has no data");
+    c.side_image.reset();
+    if (c.dev_side) { rf_free(c.dev_side); c.dev_side = nullptr; }
+    if (image) {
+        if (image->bytes.empty()) die("RecFilter " + c.name + ": the image in the definition has no data");
         for (size_t i = 0; i < c.dims.size(); ++i)
-            if (taps[0].image->extent[i] < c.dims[i].num_pixels())
+            if (image->extent[i] < c.dims[i].num_pixels())
                 die("RecFilter " + c.name + ": the image is smaller than the filter domain");
-        c.src_image = taps[0].image;
-        c.type = taps[0].image->type;                               // type of the filter = type of the RHS (lib/recfilter.cpp:197)
+    }
+    if (filter) {
+        if (!filter->defined) die("RecFilter " + c.name + ": the filter called in the definition is not defined");
+        if (filter->dims.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch with the called filter");
+        c.src_filter = filter;
+        c.type = filter->type;
+        if (image) {
+            if (image->type != filter->type) die("RecFilter " + c.name + ": the image and the filter in the definition differ in type");
+            c.side_image = image;
+        }
     } else {
-        if (!taps[0].filter->defined) die("RecFilter " + c.name + ": the filter called in the definition is not defined");
-        if (taps[0].filter->dims.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch with the called filter");
-        c.src_filter = taps[0].filter;
-        c.type = taps[0].filter->type;
+        c.src_image = image;
+        c.type = image->type;                                       // type of the filter = type of the RHS (lib/recfilter.cpp:197)
     }
     // a single unit tap whose indices are the identity inside the domain is the input itself
     c.stencil.clear();
-    bool identity = merged.size() == 1 && merged[0].w == 1.0;
+    bool identity = merged.size() == 1 && merged[0].w == 1.0 && !c.side_image;
     for (size_t i = 0; identity && i < c.dims.size(); ++i) {
         const IndexMap& m = merged[0].idx[i];
         identity = m.off == 0 && m.lo <= 0 && m.hi >= (long long)c.dims[i].num_pixels() - 1;
@@ -481,6 +505,7 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
             rf_tap rt;
             std::memset(&rt, 0, sizeof(rt));
             rt.weight = (float)(t.w / w0);
+            rt.source = (c.side_image && !t.filter) ? 1 : 0;
             for (int d = 0; d < RF_MAX_DIMS; ++d) { rt.lo[d] = INT32_MIN; rt.hi[d] = INT32_MAX; }
             for (size_t i = 0; i < t.idx.size(); ++i) {
                 rt.offset[i] = (int32_t)t.idx[i].off;
@@ -585,7 +610,7 @@ vector<RecFilter> RecFilter::cascade(vector<vector<int> > groups)
         RecFilter f(c.name + "_" + std::to_string(g));
         RecFilterContents& fc = *f.contents;
         fc.dims = c.dims; fc.type = c.type; fc.clamped = c.clamped; fc.defined = true;
-        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; fc.stencil = c.stencil; fc.stencil_scale = c.stencil_scale; }
+        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; fc.stencil = c.stencil; fc.stencil_scale = c.stencil_scale; fc.side_image = c.side_image; }
         else        { fc.src_filter = out[g - 1].contents; }
         vector<int> ids = groups[g];
         std::sort(ids.begin(), ids.end());                           // add_filter order inside a group
@@ -628,7 +653,7 @@ RecFilter RecFilter::overlap_to_higher_order_filter(RecFilter fB, string overlap
     RecFilter ab(overlap_name);
     RecFilterContents& c = *ab.contents;
     c.dims = a.dims; c.type = a.type; c.clamped = a.clamped; c.defined = true;
-    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter; c.stencil = a.stencil; c.stencil_scale = a.stencil_scale;
+    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter; c.stencil = a.stencil; c.stencil_scale = a.stencil_scale; c.side_image = a.side_image;
     for (size_t d = 0; d < a.dims.size(); ++d) {
         vector<const ScanDef*> sa, sb;
         for (const ScanDef& s : a.scans) if (s.dim == (int)d) sa.push_back(&s);

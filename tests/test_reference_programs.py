@@ -29,7 +29,10 @@ APPS = [("summed_table", ["-w", "512", "-t", "32"], True),
         # apps/box: summed-area tables + finite differencing Funcs (pointwise stencil epilogue)
         ("box_filter_1", ["-w", "512", "-t", "32", "-iter", "2"], False),
         ("box_filter_3", ["-w", "512", "-t", "32", "-iter", "2"], False),
-        ("box_filter_6", ["-w", "512", "-t", "32", "-iter", "2"], False)]
+        ("box_filter_6", ["-w", "512", "-t", "32", "-iter", "2"], False),
+        # apps/usm: (1+w)*image - w*blur, a pointwise combination of an image and a filter result
+        ("unsharp_mask_naive", ["-w", "512", "-t", "32", "-iter", "2"], False),
+        ("unsharp_mask_optimized", ["-w", "512", "-t", "32", "-iter", "2"], False)]
 MAX_PERCENT = 1e-3          # the programs print percent: 1e-3 % == 1e-5 relative (BASELINE.json tolerance)
 
 
@@ -103,6 +106,20 @@ def _box_check(kind, tmp_path):
     assert rc == 0 and len(errs) == 2, out[-2000:]
     assert errs[0] <= 1e-3            # one box: exact summed table, one rounding
     assert errs[1] <= 5e-2            # box twice through a 2nd-order integral image (fp32-unstable by construction)
+
+
+def _usm_check(kind, tmp_path):
+    rc, out = run(kind, "usm_check", ["256"], cwd=tmp_path)
+    assert rc == 0 and max_error(out) is not None and max_error(out) <= 1e-4, out[-2000:]
+
+
+def test_unsharp_mask_matches_host_combination_on_oracle_backend(tmp_path):
+    _usm_check("pin", tmp_path)
+
+
+@pytest.mark.gpu
+def test_unsharp_mask_matches_host_combination_on_b200(tmp_path):
+    _usm_check("gpu", tmp_path)
 
 
 def test_reference_box_filters_match_direct_box_on_oracle_backend(tmp_path):
