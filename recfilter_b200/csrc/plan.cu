@@ -1172,27 +1172,53 @@ __global__ void __launch_bounds__(256) stencil_kernel(const __grid_constant__ St
     }
 }
 
-// 1-D / 2-D arrays: 32-bit coordinates, one output per thread, rows on blockIdx.y -- neighbouring threads read
-// neighbouring words of every tap, so the taps are coalesced and mostly served by L1/L2
+// 1-D / 2-D arrays: 32-bit coordinates, four consecutive outputs per thread (one 128-bit store when the row
+// length allows), rows on blockIdx.y -- neighbouring threads read neighbouring words of every tap, so the taps
+// are coalesced and mostly served by L1/L2
 template <typename CT>
 __global__ void __launch_bounds__(256) stencil2d_kernel(const __grid_constant__ StencilParams p, const CT* __restrict__ in,
                                                         const CT* __restrict__ in2, CT* __restrict__ out)
 {
     const int W = (int)p.extent[0], Hh = p.ndim > 1 ? (int)p.extent[1] : 1;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x0 >= W) return;
     const CT scale = std::is_same<CT, float>::value ? (CT)p.post_scale : (CT)(int32_t)lrintf(p.post_scale);
+    const bool vec = (W & 3) == 0;
     for (int y = blockIdx.y; y < Hh; y += gridDim.y) {
-        CT acc = (CT)0;
+        CT acc[4] = { (CT)0, (CT)0, (CT)0, (CT)0 };
         for (int t = 0; t < p.ntaps; ++t) {
-            int xx = max(min(x + p.tap[t].offset[0], p.tap[t].hi[0]), p.tap[t].lo[0]);
-            xx = max(0, min(xx, W - 1));
-            int yy = max(min(y + p.tap[t].offset[1], p.tap[t].hi[1]), p.tap[t].lo[1]);
+            const rf_tap& tp = p.tap[t];
+            int yy = max(min(y + tp.offset[1], tp.hi[1]), tp.lo[1]);
             yy = max(0, min(yy, Hh - 1));
-            const CT w = std::is_same<CT, float>::value ? (CT)p.tap[t].weight : (CT)(int32_t)lrintf(p.tap[t].weight);
-            acc = acc + w * __ldg((p.tap[t].source ? in2 : in) + (size_t)yy * W + xx);
+            const CT* row = (tp.source ? in2 : in) + (size_t)yy * W;
+            const CT w = std::is_same<CT, float>::value ? (CT)tp.weight : (CT)(int32_t)lrintf(tp.weight);
+            const int xs = x0 + tp.offset[0];
+            const int lo = max(tp.lo[0], 0), hi = min(tp.hi[0], W - 1);
+            if (vec && xs >= lo && xs + 3 <= hi && (xs & 3) == 0) {            // interior, aligned: one 128-bit load
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + xs));
+                acc[0] = acc[0] + w * *reinterpret_cast<const CT*>(&q.x);
+                acc[1] = acc[1] + w * *reinterpret_cast<const CT*>(&q.y);
+                acc[2] = acc[2] + w * *reinterpret_cast<const CT*>(&q.z);
+                acc[3] = acc[3] + w * *reinterpret_cast<const CT*>(&q.w);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int xx = max(min(xs + e, tp.hi[0]), tp.lo[0]);
+                    xx = max(0, min(xx, W - 1));
+                    acc[e] = acc[e] + w * __ldg(row + xx);
+                }
+            }
         }
-        out[(size_t)y * W + x] = acc * scale;
+        CT* o = out + (size_t)y * W + x0;
+        if (vec) {
+            uint4 q;
+            *reinterpret_cast<CT*>(&q.x) = acc[0] * scale; *reinterpret_cast<CT*>(&q.y) = acc[1] * scale;
+            *reinterpret_cast<CT*>(&q.z) = acc[2] * scale; *reinterpret_cast<CT*>(&q.w) = acc[3] * scale;
+            *reinterpret_cast<uint4*>(o) = q;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (x0 + e < W) o[e] = acc[e] * scale;
+        }
     }
 }
 
@@ -1693,7 +1719,7 @@ int rf_stencil_execute(int ndim, const int64_t* extent, int dtype, int ntaps, co
     const unsigned blocks = (unsigned)std::min<int64_t>((p.total + 255) / 256, 148 * 32);
     cudaStream_t st = (cudaStream_t)stream;
     if (ndim <= 2 && p.extent[0] < 0x7fffff00LL && (ndim < 2 || p.extent[1] < 0x7fffff00LL)) {
-        const dim3 grid((unsigned)((p.extent[0] + 255) / 256), (unsigned)std::min<int64_t>(ndim > 1 ? p.extent[1] : 1, 65535));
+        const dim3 grid((unsigned)((p.extent[0] + 1023) / 1024), (unsigned)std::min<int64_t>(ndim > 1 ? p.extent[1] : 1, 65535));
         if (dtype == RF_F32) stencil2d_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)in_dev, (const float*)in2_dev, (float*)out_dev);
         else                 stencil2d_kernel<uint32_t><<<grid, 256, 0, st>>>(p, (const uint32_t*)in_dev, (const uint32_t*)in2_dev, (uint32_t*)out_dev);
     } else if (dtype == RF_F32) stencil_kernel<float><<<blocks, 256, 0, st>>>(p, (const float*)in_dev, (const float*)in2_dev, (float*)out_dev);

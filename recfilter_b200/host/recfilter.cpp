@@ -63,6 +63,7 @@ struct RecFilterContents {
     vector<ScanDef> scans;
     std::map<string, int> tiles;    // split() hints
     rf_plan* plan = nullptr;
+    string plan_sig;                // the scans the plan was built for (its own, or a fused cascade's)
     void* dev_out = nullptr;        // device result buffer, reused across realize()/profile()
     void* dev_tmp = nullptr;        // stencil output when scans follow
     ~RecFilterContents()
@@ -246,20 +247,68 @@ void linearize(const RecFilterContents& c, const Expr& e, const IndexEnv& env, d
         "constant factors of taps); general expressions are not supported by the B200 engine");
 }
 
-void build_plan(RecFilterContents& c)
+// ---------------------------------------------------------------------------------------------
+// cascade fusion.  A filter whose input is another filter's result, unchanged, continues that filter's
+// scan list: running "x scans -> store -> load -> y scans" (cascade_by_dimension, apps/gaussian/
+// gaussian_filter_3x_3y.cpp:45-52) is the same computation as one filter with all the scans, and the
+// planner can then fuse them into one pass instead of one HBM round-trip per link (the reference pays a
+// full round-trip per link, lib/reorder.cpp:28-176).  unit_first(c) is the first filter of the maximal
+// fusable run that ends in c.  RECFILTER_NO_CHAIN_FUSION=1 turns the fusion off.
+// ---------------------------------------------------------------------------------------------
+bool fusable_with_parent(const RecFilterContents& f)
 {
-    if (c.plan) return;
+    static const bool off = getenv("RECFILTER_NO_CHAIN_FUSION") && atoi(getenv("RECFILTER_NO_CHAIN_FUSION")) != 0;
+    if (off || !f.src_filter || !f.stencil.empty()) return false;
+    const RecFilterContents& p = *f.src_filter;
+    if (!p.defined || p.clamped != f.clamped || !(p.type == f.type) || p.dims.size() != f.dims.size()) return false;
+    for (size_t i = 0; i < f.dims.size(); ++i)
+        if (p.dims[i].num_pixels() != f.dims[i].num_pixels()) return false;
+    return true;
+}
+RecFilterContents& unit_first(RecFilterContents& c)
+{
+    // the fused tile kernels take up to 4 scans per dimension: a longer run would fall back to the generic engine,
+    // which is slower than one more fused pass
+    const int cap = 4;
+    int per_dim[RF_MAX_DIMS] = { 0, 0, 0, 0 };
+    auto add = [&](const RecFilterContents& g) {
+        int tmp[RF_MAX_DIMS];
+        for (int d = 0; d < RF_MAX_DIMS; ++d) tmp[d] = per_dim[d];
+        for (const ScanDef& sc : g.scans) if (sc.dim >= 0 && sc.dim < RF_MAX_DIMS && ++tmp[sc.dim] > cap) return false;
+        for (int d = 0; d < RF_MAX_DIMS; ++d) per_dim[d] = tmp[d];
+        return true;
+    };
+    RecFilterContents* f = &c;
+    add(c);
+    while (fusable_with_parent(*f) && add(*f->src_filter)) f = f->src_filter.get();
+    return *f;
+}
+vector<ScanDef> unit_scans(RecFilterContents& first, RecFilterContents& last)
+{
+    vector<RecFilterContents*> run;
+    for (RecFilterContents* f = &last; ; f = f->src_filter.get()) { run.push_back(f); if (f == &first) break; }
+    vector<ScanDef> scans;
+    for (auto it = run.rbegin(); it != run.rend(); ++it) scans.insert(scans.end(), (*it)->scans.begin(), (*it)->scans.end());
+    return scans;
+}
+
+void build_plan(RecFilterContents& c, const vector<ScanDef>& scans)
+{
+    std::ostringstream sig;
+    for (const ScanDef& sc : scans) { sig << sc.dim << (sc.causal ? '+' : '-'); for (float v : sc.coeff) sig << v << ','; sig << ';'; }
+    if (c.plan && c.plan_sig == sig.str()) return;
+    if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
     rf_desc d;
     std::memset(&d, 0, sizeof(d));
     if (c.dims.size() > RF_MAX_DIMS) die("RecFilter: at most 4 dimensions are supported");
-    if (c.scans.size() > RF_MAX_SCANS) die("RecFilter: too many scans");
+    if (scans.size() > RF_MAX_SCANS) die("RecFilter: too many scans");
     d.ndim = (int)c.dims.size();
     for (int i = 0; i < d.ndim; ++i) d.extent[i] = c.dims[i].num_pixels();
     d.dtype = engine_dtype(c.type);
     d.border = c.clamped ? RF_BORDER_CLAMP : RF_BORDER_ZERO;
-    d.nscans = (int)c.scans.size();
+    d.nscans = (int)scans.size();
     for (int s = 0; s < d.nscans; ++s) {
-        const ScanDef& sc = c.scans[s];
+        const ScanDef& sc = scans[s];
         if ((int)sc.coeff.size() - 1 > RF_MAX_ORDER) die("RecFilter: filter order above 32 is not supported");
         d.scans[s].dim = sc.dim;
         d.scans[s].causal = sc.causal ? 1 : 0;
@@ -273,7 +322,9 @@ void build_plan(RecFilterContents& c)
     d.opt.fuse_dims = -1;
     d.opt.shard_dim = -1;
     engine_check(rf_plan_create(&d, &c.plan), "rf_plan_create");
+    c.plan_sig = sig.str();
 }
+void build_plan(RecFilterContents& c) { build_plan(c, unit_scans(unit_first(c), c)); }
 
 // Device buffer holding the input of `c` (uploads an image, or evaluates the upstream filter).
 // `owned` tells the caller whether it must free the buffer.
@@ -316,45 +367,57 @@ void* input_device(RecFilterContents& c, bool& owned)
     return upload_image(c, *c.src_image);
 }
 
-// run filter c on the device buffer `in`: the stencil of the definition (if any), then the scans
-void* run_filter(RecFilterContents& c, const void* in)
+// run the unit first..c on the device buffer `in` (the input of `first`): the stencil of first's definition
+// (if any), then every scan of the run in one plan
+void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in)
 {
     const size_t bytes = c.count() * (size_t)c.type.bytes();
+    const vector<ScanDef> scans = unit_scans(first, c);
     if (!c.dev_out) engine_check(rf_malloc(&c.dev_out, bytes), "rf_malloc");
-    if (!c.stencil.empty()) {
+    if (!first.stencil.empty()) {
+        RecFilterContents& f = first;
         int64_t ext[RF_MAX_DIMS] = { 1, 1, 1, 1 };
         for (size_t i = 0; i < c.dims.size(); ++i) ext[i] = c.dims[i].num_pixels();
         void* dst = c.dev_out;
-        if (!c.scans.empty()) {
+        if (!scans.empty()) {
             if (!c.dev_tmp) engine_check(rf_malloc(&c.dev_tmp, bytes), "rf_malloc");
             dst = c.dev_tmp;
         }
-        if (c.side_image && !c.dev_side) c.dev_side = upload_image(c, *c.side_image);   // stays resident
-        engine_check(rf_stencil_execute((int)c.dims.size(), ext, engine_dtype(c.type), (int)c.stencil.size(), c.stencil.data(),
-                                        c.stencil_scale, in, c.dev_side, dst, nullptr), "rf_stencil_execute");
-        if (c.scans.empty()) return c.dev_out;
+        if (f.side_image && !f.dev_side) f.dev_side = upload_image(f, *f.side_image);   // stays resident
+        engine_check(rf_stencil_execute((int)c.dims.size(), ext, engine_dtype(c.type), (int)f.stencil.size(), f.stencil.data(),
+                                        f.stencil_scale, in, f.dev_side, dst, nullptr), "rf_stencil_execute");
+        if (scans.empty()) return c.dev_out;
         in = dst;
     }
-    build_plan(c);
+    build_plan(c, scans);
     engine_check(rf_plan_execute(c.plan, in, c.dev_out, nullptr), "rf_plan_execute");
     return c.dev_out;
 }
 
+
 void* evaluate_device(RecFilterContents& c)
 {
     if (!c.defined) die("RecFilter " + c.name + " is used before it is defined");
+    RecFilterContents& first = unit_first(c);
     bool owned = false;
-    void* in = input_device(c, owned);
-    void* out = run_filter(c, in);
+    void* in = input_device(first, owned);
+    void* out = run_unit(first, c, in);
     if (owned) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(in), "rf_free"); }
     return out;
 }
 
-// every plan of the chain ending in c, upstream first
+// every filter of the chain ending in c as declared, upstream first
 void collect_chain(RecFilterContents& c, vector<RecFilterContents*>& chain)
 {
     if (c.src_filter) collect_chain(*c.src_filter, chain);
     chain.push_back(&c);
+}
+// the execution units (fused runs) of the chain ending in c, upstream first: (first, last) pairs
+void collect_units(RecFilterContents& c, vector<std::pair<RecFilterContents*, RecFilterContents*>>& units)
+{
+    RecFilterContents& first = unit_first(c);
+    if (first.src_filter) collect_units(*first.src_filter, units);
+    units.push_back({ &first, &c });
 }
 
 } // namespace
@@ -720,13 +783,13 @@ float RecFilter::profile(int iterations)
     RecFilterContents& c = *contents;
     if (!c.defined) die("Filter " + c.name + " cannot be profiled before it is defined");
     if (iterations < 1) iterations = 1;
-    vector<RecFilterContents*> chain;
-    collect_chain(c, chain);
+    vector<std::pair<RecFilterContents*, RecFilterContents*>> units;
+    collect_units(c, units);
     bool owned = false;
-    void* root_in = input_device(*chain[0], owned);                   // the image stays resident: kernels only are timed
+    void* root_in = input_device(*units[0].first, owned);             // the image stays resident: kernels only are timed
     auto run_chain = [&]() {
         const void* in = root_in;
-        for (RecFilterContents* f : chain) in = run_filter(*f, in);
+        for (auto& u : units) in = run_unit(*u.first, *u.second, in);
     };
     run_chain();                                                      // warm-up (lib/recfilter.cpp:995-997)
     void* clock = nullptr;
