@@ -1,7 +1,8 @@
 /*
- * usm_check.cpp -- the unsharp mask of the reference's apps/usm/unsharp_mask_naive.cpp:41-61, restated with a
- * check (the reference app only times it): USM = (1+w)*image - w*blur, a pointwise combination of an image and
- * a filter result.  The blur is also realized on its own and combined on the host; the two must agree.
+ * usm_check.cpp -- checks the two-source pointwise stencil of the C++ surface: an unsharp mask
+ * sharp = (1 + amount) * picture - amount * smooth, where `smooth` is a cascaded 3rd-order recursive
+ * Gaussian of `picture` (the construction the reference times in apps/usm/unsharp_mask_naive.cpp:41-61
+ * without checking it).  `smooth` is also realized on its own and combined on the host; both must agree.
  */
 #include <Halide.h>
 #include <recfilter.h>
@@ -11,44 +12,42 @@
 #include <cstdlib>
 
 using namespace Halide;
-using std::vector;
 
 int main(int argc, char** argv)
 {
-    const int width = argc > 1 ? atoi(argv[1]) : 256, height = width, tile_width = 32;
-    Image<float> image(width, height);
+    const int n = argc > 1 ? atoi(argv[1]) : 256;
+    const float amount = 1.0f;
+    Halide::Image<float> picture(n, n);
     srand(4321);
-    for (int y = 0; y < height; y++)
-        for (int x = 0; x < width; x++) image(x, y) = float(rand() % 1024) / 1024.0f;
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) picture(c, r) = float(rand() % 1024) / 1024.0f;
 
-    const float sigma = 5.0f, weight = 1.0f;
-    vector<float> W3 = gaussian_weights(sigma, 3);
+    RecFilterDim col("col", n), row("row", n);
+    RecFilter smooth("smooth"), sharp("sharp");
+    const std::vector<float> g3 = gaussian_weights(5.0f, 3);
+    smooth.set_clamped_image_border();
+    smooth(col, row) = picture(col, row);
+    for (int pass = 0; pass < 2; pass++) {                 // causal + anticausal along each dimension
+        smooth.add_filter(+(pass ? row : col), g3);
+        smooth.add_filter(-(pass ? row : col), g3);
+    }
+    std::vector<RecFilter> stages = smooth.cascade_by_dimension();
+    for (RecFilter& s : stages) s.split_all_dimensions(32);
+    RecFilter& last = stages.back();
 
-    RecFilter USM("USM"), B("Blur");
-    RecFilterDim x("x", width), y("y", height);
-    B.set_clamped_image_border();
-    B(x, y) = image(x, y);
-    B.add_filter(+x, W3);
-    B.add_filter(-x, W3);
-    B.add_filter(+y, W3);
-    B.add_filter(-y, W3);
-    vector<RecFilter> fc = B.cascade_by_dimension();
-    fc[0].split_all_dimensions(tile_width);
-    fc[1].split_all_dimensions(tile_width);
-    USM(x, y) = (1.0f + weight) * image(x, y) - (weight) * fc[1](x, y);
+    sharp(col, row) = (1.0f + amount) * picture(col, row) - amount * last(col, row);
     RecFilter::set_max_threads_per_cuda_warp(128);
-    fc[0].gpu_auto_schedule();
-    fc[1].gpu_auto_schedule();
-    USM.gpu_auto_schedule(tile_width);
+    for (RecFilter& s : stages) s.gpu_auto_schedule();
+    sharp.gpu_auto_schedule(32);
 
-    Image<float> out(USM.realize());
-    Image<float> blur(fc[1].realize());
+    Halide::Image<float> got(sharp.realize());
+    Halide::Image<float> blur(last.realize());
     double worst = 0.0, scale = 0.0;
-    for (int j = 0; j < height; j++)
-        for (int i = 0; i < width; i++) {
-            const float ref = (1.0f + weight) * image(i, j) - weight * blur(i, j);
-            worst = std::max(worst, (double)std::fabs(ref - out(i, j)));
-            scale = std::max(scale, (double)std::fabs(ref));
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) {
+            const float want = (1.0f + amount) * picture(c, r) - amount * blur(c, r);
+            worst = std::max(worst, (double)std::fabs(want - got(c, r)));
+            scale = std::max(scale, (double)std::fabs(want));
         }
     const double pct = 100.0 * worst / (scale + 1e-9);
     printf("unsharp mask vs host combination of image and blur: Max  relative error = %g %%\n", pct);
