@@ -448,8 +448,10 @@ __device__ __forceinline__ void fmatvec_acc_reg(CT (&y)[R], const CT (&m)[R * R]
     }
 }
 
-template <typename CT, int R, int S>
-__global__ void __launch_bounds__(32 * 16, 1)
+// MAXT: block size the instantiation is compiled for (256: up to 8 segments, three blocks per SM by registers;
+// 512: up to 16 segments)
+template <typename CT, int R, int S, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? (R <= 4 ? 3 : 2) : 1)
 fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 {
     extern __shared__ __align__(16) unsigned char fchain_smem[];

@@ -76,16 +76,23 @@ static cudaError_t launch_fused_tile_T(const FusedParams<CT, R>& p, const void* 
     return cudaErrorInvalidValue;
 }
 
-template <typename CT, int R, int S>
-static cudaError_t launch_fchain_S(const FChainParams<CT, R>& p, unsigned grid, dim3 block, size_t smem, cudaStream_t st)
+template <typename CT, int R, int S, int MAXT>
+static cudaError_t launch_fchain_M(const FChainParams<CT, R>& p, unsigned grid, dim3 block, size_t smem, cudaStream_t st)
 {
     static size_t attr_bytes = 0;
     if (smem > 48u * 1024u && smem > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(fchain_kernel<CT, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fchain_kernel<CT, R, S, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_bytes = smem;
     }
-    return launch_pdl(fchain_kernel<CT, R, S>, dim3(grid), block, smem, st, p);
+    return launch_pdl(fchain_kernel<CT, R, S, MAXT>, dim3(grid), block, smem, st, p);
+}
+template <typename CT, int R, int S>
+static cudaError_t launch_fchain_S(const FChainParams<CT, R>& p, unsigned grid, dim3 block, size_t smem, cudaStream_t st)
+{
+    static const bool small_off = getenv("RFB_CHAIN_NO256") && atoi(getenv("RFB_CHAIN_NO256")) != 0;
+    if (block.x * block.y <= 256 && !small_off) return launch_fchain_M<CT, R, S, 256>(p, grid, block, smem, st);
+    return launch_fchain_M<CT, R, S, 512>(p, grid, block, smem, st);
 }
 
 template <typename CT, int R>
