@@ -71,6 +71,12 @@ struct BufferData {
     int dims = 0;
     int extent[4] = { 0, 0, 0, 0 };
     std::vector<unsigned char> bytes;
+    // a view of the trailing-index plane of a larger image (image(x, y, 2)): no bytes of its own, the
+    // parent's data is read when the filter runs
+    std::shared_ptr<BufferData> parent;
+    size_t parent_offset = 0;          // bytes
+    const unsigned char* host_data() const { return parent ? parent->host_data() + parent_offset : bytes.data(); }
+    bool has_data() const { return parent ? parent->has_data() : !bytes.empty(); }
     size_t count() const
     {
         size_t n = dims ? 1 : 0;

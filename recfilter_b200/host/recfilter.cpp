@@ -64,6 +64,9 @@ struct RecFilterContents {
     std::map<string, int> tiles;    // split() hints
     rf_plan* plan = nullptr;
     string plan_sig;                // the scans the plan was built for (its own, or a fused cascade's)
+    // Tuple (multi-output) filters, lib/recfilter.cpp:68-74,197-203: every Tuple element is filtered
+    // independently with the same scans -- one channel filter per element, kept in step by sync_channels()
+    vector<std::shared_ptr<RecFilterContents>> channels;
     void* dev_out = nullptr;        // device result buffer, reused across realize()/profile()
     void* dev_tmp = nullptr;        // stencil output when scans follow
     ~RecFilterContents()
@@ -129,6 +132,8 @@ bool is_identity_index(const Expr& e, const string& name, int extent)
 //   D(x,y) = (f(clamp(x+B,..), clamp(y+B,..)) - f(..) + ..) / area      (apps/box/box_filter.h:36-39)
 // possibly through pure helper Funcs (fA(u,v) = ..., box_filter.h:122-131), which are inlined.
 // ---------------------------------------------------------------------------------------------
+void sync_channels(RecFilterContents& c);
+
 struct IndexMap {                  // clamp(var_dim + off, lo, hi)
     int dim = -1;
     long long off = 0, lo = INT32_MIN, hi = INT32_MAX;
@@ -237,7 +242,39 @@ void linearize(const RecFilterContents& c, const Expr& e, const IndexEnv& env, d
             return;
         }
         LinTap t; t.w = scale; t.image = n.kind == ExprNode::Load ? n.buffer : nullptr; t.filter = n.filter;
-        for (const Expr& a : n.args) t.idx.push_back(eval_index(c, a, env));
+        if (t.filter && !t.filter->channels.empty()) {              // F(x,y)[i] of a Tuple filter
+            if (n.tuple_index < 0 || n.tuple_index >= (int)t.filter->channels.size())
+                die("RecFilter " + c.name + ": Tuple index out of range in the definition");
+            sync_channels(*t.filter);
+            t.filter = t.filter->channels[n.tuple_index];
+        }
+        size_t nidx = n.args.size();
+        if (t.image && nidx > c.dims.size() && (int)nidx == t.image->dims) {
+            // image(x, y, 2): trailing constant indices select one plane of a larger image
+            size_t off = 0, stride = 1;
+            for (size_t i = 0; i < nidx; ++i) {
+                if (i >= c.dims.size()) {
+                    double k;
+                    if (!const_value(n.args[i], k) || k < 0 || k >= t.image->extent[i])
+                        die("RecFilter " + c.name + ": indices beyond the filter's dimensions must be constants inside the image");
+                    off += (size_t)k * stride;
+                }
+                stride *= (size_t)t.image->extent[i];
+            }
+            static std::map<std::pair<BufferData*, size_t>, std::shared_ptr<BufferData>> views;   // one view per plane
+            auto key = std::make_pair(t.image.get(), off);
+            auto it = views.find(key);
+            if (it == views.end()) {
+                auto v = std::make_shared<BufferData>();
+                v->type = t.image->type; v->dims = (int)c.dims.size();
+                for (size_t i = 0; i < c.dims.size(); ++i) v->extent[i] = t.image->extent[i];
+                v->parent = t.image; v->parent_offset = off * (size_t)t.image->type.bytes();
+                it = views.emplace(key, v).first;
+            }
+            t.image = it->second;
+            nidx = c.dims.size();
+        }
+        for (size_t i = 0; i < nidx; ++i) t.idx.push_back(eval_index(c, n.args[i], env));
         taps.push_back(t);
         return;
     }
@@ -339,7 +376,7 @@ void* upload_image(RecFilterContents& c, const BufferData& b)
     bool same = b.dims == (int)c.dims.size();
     for (int i = 0; same && i < b.dims; ++i) same = b.extent[i] == c.dims[i].num_pixels();
     if (same) {
-        engine_check(rf_memcpy_h2d(dev, b.bytes.data(), bytes), "rf_memcpy_h2d");
+        engine_check(rf_memcpy_h2d(dev, b.host_data(), bytes), "rf_memcpy_h2d");
     } else {
         // the image is larger than the filter domain: pack the [0, extent) box
         const int eb = c.type.bytes();
@@ -351,7 +388,7 @@ void* upload_image(RecFilterContents& c, const BufferData& b)
             for (int z = 0; z < ext[2]; ++z)
                 for (int y = 0; y < ext[1]; ++y) {
                     const size_t src = (((size_t)w * bext[2] + z) * bext[1] + y) * (size_t)bext[0];
-                    std::memcpy(&packed[o * eb], &b.bytes[src * eb], (size_t)ext[0] * eb);
+                    std::memcpy(&packed[o * eb], b.host_data() + src * eb, (size_t)ext[0] * eb);
                     o += (size_t)ext[0];
                 }
         engine_check(rf_memcpy_h2d(dev, packed.data(), bytes), "rf_memcpy_h2d");
@@ -404,6 +441,16 @@ void* evaluate_device(RecFilterContents& c)
     void* out = run_unit(first, c, in);
     if (owned) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(in), "rf_free"); }
     return out;
+}
+
+// a Tuple filter's channels follow its scans, tiling hints and border mode
+void sync_channels(RecFilterContents& c)
+{
+    for (auto& ch : c.channels) {
+        ch->scans = c.scans;
+        ch->tiles = c.tiles;
+        ch->clamped = c.clamped;
+    }
 }
 
 // every filter of the chain ending in c as declared, upstream first
@@ -492,9 +539,26 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
 {
     RecFilterContents& c = *contents;
     if (pure_args.empty() || pure_def.empty()) die("RecFilter " + c.name + ": empty definition");
-    if (pure_def.size() != 1)
-        die("RecFilter " + c.name + ": Tuple (multi-output) filters are not supported by the B200 engine yet; "
-            "filter each channel as its own RecFilter");
+    c.channels.clear();
+    if (pure_def.size() > 1) {
+        // Tuple: one channel filter per element (same dimensions, border mode and, later, scans)
+        c.dims = pure_args;
+        c.rhs = pure_def;
+        c.scans.clear();
+        c.src_image.reset(); c.src_filter.reset(); c.stencil.clear(); c.side_image.reset();
+        if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
+        for (size_t i = 0; i < pure_def.size(); ++i) {
+            RecFilter ch(c.name + "_" + std::to_string(i));
+            if (c.clamped) ch.set_clamped_image_border();
+            ch.define(pure_args, vector<Expr>(1, pure_def[i]));
+            c.channels.push_back(ch.handle());
+        }
+        c.type = c.channels[0]->type;
+        for (auto& ch : c.channels)
+            if (!(ch->type == c.type)) die("RecFilter " + c.name + ": the elements of a Tuple must have the same type");
+        c.defined = true;
+        return;
+    }
     const Expr& e = pure_def[0];
     if (!e.defined()) die("RecFilter " + c.name + ": undefined expression in the definition");
     c.dims = pure_args;
@@ -533,7 +597,7 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     c.side_image.reset();
     if (c.dev_side) { rf_free(c.dev_side); c.dev_side = nullptr; }
     if (image) {
-        if (image->bytes.empty()) die("RecFilter " + c.name + ": the image in the definition has no data");
+        if (!image->has_data()) die("RecFilter " + c.name + ": the image in the definition has no data");
         for (size_t i = 0; i < c.dims.size(); ++i)
             if (image->extent[i] < c.dims[i].num_pixels())
                 die("RecFilter " + c.name + ": the image is smaller than the filter domain");
@@ -652,6 +716,7 @@ vector<RecFilter> RecFilter::cascade(vector<vector<int> > groups)
 {
     RecFilterContents& c = *contents;
     if (c.tiled) die("Cascading must be done before the filter " + c.name + " is tiled");
+    if (!c.channels.empty()) die("RecFilter " + c.name + ": cascading a Tuple filter is not supported; cascade its channels");
     const int n = (int)c.scans.size();
     vector<int> group_of(n, -1);
     for (size_t g = 0; g < groups.size(); ++g)
@@ -709,6 +774,7 @@ RecFilter RecFilter::overlap_to_higher_order_filter(RecFilter fB, string overlap
     RecFilterContents& a = *contents;
     RecFilterContents& b = *fB.contents;
     if (a.tiled || b.tiled) die("Overlapping directive overlap() cannot be used after the filter is already tiled");
+    if (!a.channels.empty() || !b.channels.empty()) die("Overlapping Tuple filters is not supported; overlap their channels");
     if (b.src_filter.get() != &a)
         die("Filters cannot be overlapped because the input to second does not match the output of the first");
     if (a.clamped != b.clamped) die("Filters cannot be overlapped because one clamps image border while the other does not");
@@ -748,6 +814,19 @@ Realization RecFilter::realize()
 {
     RecFilterContents& c = *contents;
     if (!c.defined) die("Filter " + c.name + " cannot be realized before it is defined");
+    if (!c.channels.empty()) {                                       // Tuple: one Buffer per element
+        sync_channels(c);
+        vector<Buffer> bufs;
+        for (auto& ch : c.channels) {
+            void* d = evaluate_device(*ch);
+            vector<int> e;
+            for (const RecFilterDim& dim : c.dims) e.push_back(dim.num_pixels());
+            Buffer b(ch->type, e);
+            engine_check(rf_memcpy_d2h(b.host_ptr(), d, b.size_in_bytes()), "rf_memcpy_d2h");
+            bufs.push_back(b);
+        }
+        return Realization(bufs);
+    }
     void* dev = evaluate_device(c);
     vector<int> ext;
     for (const RecFilterDim& d : c.dims) ext.push_back(d.num_pixels());
@@ -783,6 +862,13 @@ float RecFilter::profile(int iterations)
     RecFilterContents& c = *contents;
     if (!c.defined) die("Filter " + c.name + " cannot be profiled before it is defined");
     if (iterations < 1) iterations = 1;
+    if (!c.channels.empty()) {                                       // Tuple: the channels run one after the other
+        sync_channels(c);
+        float total = 0.0f;
+        for (auto& ch : c.channels) { RecFilter f; f.contents = ch; total += f.profile(iterations); }
+        cerr << c.name << ": " << total << " ms per iteration for " << c.channels.size() << " Tuple elements" << endl;
+        return total;
+    }
     vector<std::pair<RecFilterContents*, RecFilterContents*>> units;
     collect_units(c, units);
     bool owned = false;

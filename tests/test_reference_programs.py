@@ -108,6 +108,22 @@ def _box_check(kind, tmp_path):
     assert errs[1] <= 5e-2            # box twice through a 2nd-order integral image (fp32-unstable by construction)
 
 
+def _tuple_check(kind, tmp_path):
+    # tests/cpp/tuple_check.cpp: a Tuple filter equals its planes filtered one by one; F(x,y)[i] feeds another filter
+    rc, out = run(kind, "tuple_check", ["128"], cwd=tmp_path)
+    errs = [float(v) for v in re.findall(r"Max\s+relative error = (\S+) %", out)]
+    assert rc == 0 and len(errs) == 2 and errs[0] == 0.0 and errs[1] <= 1e-3, out[-2000:]
+
+
+def test_tuple_filter_on_oracle_backend(tmp_path):
+    _tuple_check("pin", tmp_path)
+
+
+@pytest.mark.gpu
+def test_tuple_filter_on_b200(tmp_path):
+    _tuple_check("gpu", tmp_path)
+
+
 def _usm_check(kind, tmp_path):
     rc, out = run(kind, "usm_check", ["256"], cwd=tmp_path)
     assert rc == 0 and max_error(out) is not None and max_error(out) <= 1e-4, out[-2000:]
