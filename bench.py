@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--overlap", type=int, default=1,
                     help="sub-stacks of a step that run on their own CUDA streams (carry stage of one beside the tile "
                          "kernels of another); 1 = one stream")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "alltoall"],
+                    help="N > 1: how the strip tails travel (auto: column-chunked all-to-all from 4 ranks on)")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: keep --batch images per step (strong scaling) instead of --batch x N (weak scaling)")
     args = ap.parse_args()
@@ -238,7 +240,7 @@ def main():
     # outermost dimension carries no scans (the reference allows that: lib/split.cpp:1888-1898): one launch
     # sequence -- and, sharded, one tail exchange -- per step
     flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B, stacked=B > 1,
-                        overlap=args.overlap)
+                        overlap=args.overlap, exchange=args.exchange)
     rows = flt.local_extents[1]
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     src_stack = torch.rand((B, rows, W), device="cuda", dtype=torch.float32, generator=gen)
@@ -361,7 +363,7 @@ def main():
     strong = None
     if weak:
         sflt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=args.batch,
-                             stacked=args.batch > 1)
+                             stacked=args.batch > 1, exchange=args.exchange)
         ssrc, sdst = src_stack[:args.batch].contiguous(), dst_stack[:args.batch].contiguous()
 
         def sstep():
@@ -434,8 +436,9 @@ def main():
             "scaling": "strong" if (N > 1 and not weak) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step": B,
                        "sharding": "none" if N == 1 else
-                                   f"every image cut into {N} row strips, one per GPU; one all-gather of the order-3 strip "
-                                   f"tails per step; {args.batch} images' worth of samples per GPU per step",
+                                   f"every image cut into {N} row strips, one per GPU; the order-3 strip tails travel once per step "
+                                   f"({'two column-chunked all-to-alls' if flt.chunked else 'one all-gather'}); "
+                                   f"{args.batch} images' worth of samples per GPU per step",
                        "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
                        "tile": "128x128 register tiles (fused engine)",
                        "streams": f"{flt.groups} sub-stacks of {flt.sub} images on their own CUDA streams" if flt.stacked else "1"},

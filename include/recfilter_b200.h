@@ -187,6 +187,18 @@ int rf_plan_stage_times(rf_plan* plan, double* ms, long* counts, int n);
  *           carries and finishes the filter.
  */
 size_t rf_plan_shard_tail_bytes(const rf_plan* plan);
+/*
+ * Column-chunked exchange (less traffic than the all-gather when there are many shards): the tails are
+ * [vectors][lines] with vectors = scans x order (rf_plan_shard_vectors) and lines = tail elements / vectors.
+ * Every rank receives the tails of ALL shards for ITS chunk of the lines (all-to-all), resolves the carries
+ * entering every shard for those lines (rf_plan_shard_resolve_lines: gathered is [nshards][vectors][nlines],
+ * ext_all the same shape), returns each shard its chunk (all-to-all) and finishes with rf_plan_stage2_ext,
+ * whose ext_dev is the [vectors][lines] array of carries entering this shard.
+ */
+int rf_plan_shard_vectors(const rf_plan* plan);
+int rf_plan_shard_resolve_lines(rf_plan* plan, const void* gathered_tails_dev, int nshards, int64_t nlines,
+                                void* ext_all_dev, void* stream);
+int rf_plan_stage2_ext(rf_plan* plan, const void* in_dev, void* out_dev, const void* ext_dev, void* stream);
 int rf_plan_stage1(rf_plan* plan, const void* in_dev, void* out_dev, void* tails_dev, void* stream);
 int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev,
                    const void* gathered_tails_dev, int nshards, int shard_rank, void* stream);

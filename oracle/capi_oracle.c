@@ -144,6 +144,11 @@ int rf_plan_stage1(rf_plan* p, const void* i, void* o, void* t, void* s) { (void
 int rf_plan_stage2(rf_plan* p, const void* i, void* o, const void* g, int n, int r, void* s)
 { (void)p; (void)i; (void)o; (void)g; (void)n; (void)r; (void)s; return RF_EUNSUPPORTED; }
 
+int rf_plan_shard_vectors(const rf_plan* p) { (void)p; return 0; }
+int rf_plan_shard_resolve_lines(rf_plan* p, const void* g, int n, int64_t l, void* e, void* s)
+{ (void)p; (void)g; (void)n; (void)l; (void)e; (void)s; return RF_EUNSUPPORTED; }
+int rf_plan_stage2_ext(rf_plan* p, const void* i, void* o, const void* e, void* s)
+{ (void)p; (void)i; (void)o; (void)e; (void)s; return RF_EUNSUPPORTED; }
 int rf_clock_begin(void* stream, void** clock)
 {
     (void)stream;

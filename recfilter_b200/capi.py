@@ -98,6 +98,9 @@ def lib():
     L.rf_plan_shard_tail_bytes.restype = sz
     L.rf_plan_stage1.argtypes = [vp, vp, vp, vp, vp]
     L.rf_plan_stage2.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.rf_plan_shard_vectors.argtypes = [vp]
+    L.rf_plan_shard_resolve_lines.argtypes = [vp, vp, i32, C.c_int64, vp, vp]
+    L.rf_plan_stage2_ext.argtypes = [vp, vp, vp, vp, vp]
     L.rf_plan_stage_timing.argtypes = [vp, i32]
     L.rf_plan_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), i32]
     L.rf_clock_begin.argtypes = [vp, C.POINTER(vp)]
@@ -304,6 +307,22 @@ class Plan:
         st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
         _check(lib().rf_plan_stage1(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
                                     C.c_void_p(tails.data_ptr()), C.c_void_p(st)), "rf_plan_stage1")
+
+    @property
+    def shard_vectors(self) -> int:
+        return int(lib().rf_plan_shard_vectors(self._h))
+
+    def shard_resolve_lines(self, gathered, nshards: int, nlines: int, ext_all, stream=None):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        _check(lib().rf_plan_shard_resolve_lines(self._h, C.c_void_p(gathered.data_ptr()), int(nshards), int(nlines),
+                                                 C.c_void_p(ext_all.data_ptr()), C.c_void_p(st)), "rf_plan_shard_resolve_lines")
+
+    def stage2_ext(self, src, dst, ext, stream=None):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        _check(lib().rf_plan_stage2_ext(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                        C.c_void_p(ext.data_ptr()), C.c_void_p(st)), "rf_plan_stage2_ext")
 
     def stage2(self, src, dst, gathered, nshards: int, rank: int, stream=None):
         import torch

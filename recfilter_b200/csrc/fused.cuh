@@ -1,7 +1,8 @@
 #pragma once
 /*
  * fused.cuh -- the fast path: fused two-dimension tile kernels with register-resident
- * lines and a parallel fp64 carry algebra.
+ * lines and a segmented carry algebra in a difference basis (fp32 / the u32 ring; the matrices
+ * are built in fp64 on the host).  Also the tile kernels' "signal mode" for long 1-D signals.
  *
  * What it replaces in the reference (/root/reference): the Halide-generated stages of
  * lib/split.cpp -- intra-tile term :503-665, tail extraction :256-499, inter-tile carry
@@ -29,7 +30,7 @@
  *
  *   fused_tile_kernel<P1>   zero-history scans, emits per-scan tails (TY, TX)
  *   fchain_kernel           tails -> carries along one dimension, all scans, segmented
- *   fcross_kernel           A = L_x * CY  per tile (cross-dimension residual, part 1)
+ *   fcrossA_kernel          A = L_x * CY  per tile (cross-dimension residual, part 1)
  *   fchain_kernel (x)       adds G_y * A to the x tails on the fly (part 2), then chains
  *   fused_tile_kernel<P2>   re-scan from the completed carries, scale, store
  */

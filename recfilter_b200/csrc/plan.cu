@@ -397,7 +397,12 @@ __global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restric
                     t[k] = t[k] + Pdim[((int64_t)s * R + k) * R + kk] * tau[kk];
             for (int k = 0; k < R; ++k) tau[k] = t[k];
         }
-        for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = (CT)c[s][rank][k];
+        if (rank >= 0) {
+            for (int k = 0; k < R; ++k) ext[((int64_t)s * R + k) * nl + l] = (CT)c[s][rank][k];
+        } else {                                   // rank < 0: the carries entering EVERY shard, ext[g][s][k][l]
+            for (int gg = 0; gg < nshards; ++gg)
+                for (int k = 0; k < R; ++k) ext[gg * shard_stride + ((int64_t)s * R + k) * nl + l] = (CT)c[s][gg][k];
+        }
     }
 }
 
@@ -430,6 +435,7 @@ struct ShardResolver {
         ready = true;
         return RF_OK;
     }
+    // rank < 0: resolve the carries entering every shard for the given lines (ext_out is [nshards][S][R][nl])
     int run(int64_t nl, const void* gathered, int nshards, int rank, void* ext_out, cudaStream_t st)
     {
         if (!ready) return fail(RF_EINVAL, "plan was not created for sharded execution");
@@ -456,6 +462,9 @@ struct PassBase {
     virtual bool d_open() const = 0;
     virtual size_t shard_tail_elems() const = 0;     // elements of the compute type exported per shard
     virtual int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) = 0;
+    // carries entering every shard for `nlines` lines of the cut (column-chunked exchange); vectors = scans x order
+    virtual int shard_resolve_lines(const void* gathered, int nshards, int64_t nlines, void* ext_all, cudaStream_t st) = 0;
+    virtual int shard_vectors() const = 0;
     virtual const void* ext_buffer() const = 0;
 };
 
@@ -644,6 +653,12 @@ struct Pass : PassBase {
         if (!d_open()) return RF_OK;
         return resolver->run(pp.nly, gathered, nshards, rank, dExt.p, st);
     }
+    int shard_resolve_lines(const void* gathered, int nshards, int64_t nlines, void* ext_all, cudaStream_t st) override
+    {
+        if (!d_open()) return RF_OK;
+        return resolver->run(nlines, gathered, nshards, -1, ext_all, st);
+    }
+    int shard_vectors() const override { return pp.md * R; }
 
     std::string describe() const override
     {
@@ -929,6 +944,12 @@ struct FusedPass : PassBase {
         if (!d_open()) return RF_OK;
         return resolver->run(fp.nly, gathered, nshards, rank, dExt.p, st);
     }
+    int shard_resolve_lines(const void* gathered, int nshards, int64_t nlines, void* ext_all, cudaStream_t st) override
+    {
+        if (!d_open()) return RF_OK;
+        return resolver->run(nlines, gathered, nshards, -1, ext_all, st);
+    }
+    int shard_vectors() const override { return fp.md * R; }
 
     std::string describe() const override
     {
@@ -973,6 +994,8 @@ struct SignalPass : PassBase {
     const void* ext_buffer() const override { return nullptr; }
     size_t shard_tail_elems() const override { return 0; }
     int shard_resolve(const void*, int, int, cudaStream_t) override { return RF_OK; }
+    int shard_resolve_lines(const void*, int, int64_t, void*, cudaStream_t) override { return RF_OK; }
+    int shard_vectors() const override { return 0; }
     size_t workspace() const override
     {
         size_t n = 0;
@@ -1786,6 +1809,43 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev, const void*
             if ((rc = p->shard_resolve(gathered_tails_dev, nshards, shard_rank, st))) return rc;
             // tails of K1 are still valid: redo the carry completion with the incoming shard carries
             if ((rc = p->run_carries(p->ext_buffer(), nullptr, st, 2))) return rc;
+        } else {
+            if ((rc = p->run_tails(src, out_dev, st))) return rc;
+            if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;
+        }
+        if ((rc = p->run_final(src, out_dev, st))) return rc;
+        src = out_dev;
+    }
+    return RF_OK;
+}
+
+int rf_plan_shard_vectors(const rf_plan* plan)
+{
+    if (!plan || plan->shard_pass < 0) return 0;
+    return plan->passes[plan->shard_pass]->shard_vectors();
+}
+
+int rf_plan_shard_resolve_lines(rf_plan* plan, const void* gathered_tails_dev, int nshards, int64_t nlines,
+                                void* ext_all_dev, void* stream)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
+    if (nshards < 1 || nlines < 0 || !gathered_tails_dev || !ext_all_dev) return fail(RF_EINVAL, "bad argument");
+    return plan->passes[plan->shard_pass]->shard_resolve_lines(gathered_tails_dev, nshards, nlines, ext_all_dev, (cudaStream_t)stream);
+}
+
+int rf_plan_stage2_ext(rf_plan* plan, const void* in_dev, void* out_dev, const void* ext_dev, void* stream)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
+    if (!ext_dev) return fail(RF_EINVAL, "null carries");
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* src = plan->shard_pass == 0 ? in_dev : out_dev;
+    for (int i = plan->shard_pass; i < (int)plan->passes.size(); ++i) {
+        auto& p = plan->passes[i];
+        int rc;
+        if (i == plan->shard_pass) {
+            if ((rc = p->run_carries(ext_dev, nullptr, st, 2))) return rc;
         } else {
             if ((rc = p->run_tails(src, out_dev, st))) return rc;
             if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;

@@ -38,6 +38,27 @@ def exchange_tails(my_tails: torch.Tensor, world: int, group=None) -> torch.Tens
     return gathered.view(world, b, e).transpose(0, 1).contiguous()
 
 
+def scatter_tail_chunks(my_tails: torch.Tensor, vectors: int, world: int, group=None) -> torch.Tensor:
+    """Column-chunked exchange, step 1.  my_tails is this shard's [vectors * lines] tail array; every rank
+    receives the tails of ALL shards for ITS chunk of the lines: returns [world, vectors, lines // world]
+    (shard-major: the layout rf_plan_shard_resolve_lines expects)."""
+    lines = my_tails.numel() // vectors
+    c = lines // world
+    send = my_tails.view(vectors, world, c).permute(1, 0, 2).contiguous()        # [dest rank][vectors][c]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv
+
+
+def gather_carry_chunks(ext_all: torch.Tensor, group=None) -> torch.Tensor:
+    """Column-chunked exchange, step 2.  ext_all is [world (target shard), vectors, c]: the carries entering
+    every shard for this rank's line chunk.  Returns this shard's full [vectors * lines] carry array."""
+    world, vectors, c = ext_all.shape
+    back = torch.empty_like(ext_all)
+    dist.all_to_all_single(back, ext_all.contiguous(), group=group)              # back[q] = my carries, chunk q
+    return back.permute(1, 0, 2).contiguous().view(vectors * world * c)
+
+
 def strip_bounds(extent: int, world: int, rank: int, multiple: int = 1) -> tuple[int, int]:
     """[lo, hi) of rank's strip along the cut dimension: equal strips, `multiple` keeps tile alignment."""
     if extent % (world * multiple) != 0:
@@ -55,13 +76,16 @@ class ShardedFilter:
 
     def __init__(self, extents: Sequence[int], dtype, scans: Sequence[Scan], border: str, *, rank: int, world: int,
                  shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None, stacked: bool = False,
-                 overlap: int = 1):
+                 overlap: int = 1, exchange: str = "auto"):
         """stacked=True: the `batch` images are one dense stack [batch][...] and are filtered as ONE filter with
         an extra outermost dimension that carries no scans (allowed by the reference: lib/split.cpp:1888-1898,
         it is how apps/audio batches channels): one launch sequence and one tail exchange per stack.
         overlap=g > 1 (stacked only): the stack is split into g sub-stacks, each with its own plan (carry
         workspace) and CUDA stream, so the latency-bound carry stage of one sub-stack runs beside the
-        bandwidth-bound tile kernels of another."""
+        bandwidth-bound tile kernels of another.
+        exchange: "allgather" (every rank receives the tails of all shards and resolves its own carries),
+        "alltoall" (column-chunked: every rank resolves 1/world of the lines for all shards; 2 small all-to-alls
+        instead of one all-gather whose volume grows with world) or "auto" (alltoall from 4 ranks on)."""
         self.rank, self.world, self.group, self.batch = rank, world, group, batch
         self.stacked = stacked and batch > 1
         self.groups = overlap if (self.stacked and overlap > 1 and batch % overlap == 0) else 1
@@ -83,6 +107,23 @@ class ShardedFilter:
             self.plans = [Plan(self.local_extents, dtype, scans, border, **kw) for _ in range(batch if world > 1 else 1)]
         self.tail_elems = self.plans[0].shard_tail_bytes // 4 if world > 1 else 0
         self._tails = None
+        self.vectors = self.plans[0].shard_vectors if world > 1 else 0
+        lines = self.tail_elems // self.vectors if self.vectors else 0
+        chunked_ok = world > 1 and self.vectors > 0 and lines % world == 0
+        if exchange == "alltoall" and not chunked_ok:
+            raise ValueError("exchange='alltoall' needs the cut lines to divide evenly among the ranks")
+        self.chunked = chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4))
+
+    def _finish(self, plan, src, dst, tails):
+        """Exchange the strip tails and finish the filter (stage 2) for one plan."""
+        if self.chunked:
+            recv = scatter_tail_chunks(tails, self.vectors, self.world, self.group)
+            ext_all = torch.empty_like(recv)
+            plan.shard_resolve_lines(recv, self.world, recv.shape[2], ext_all)
+            plan.stage2_ext(src, dst, gather_carry_chunks(ext_all, self.group))
+        else:
+            gathered = exchange_tails(tails.view(1, -1), self.world, self.group)
+            plan.stage2(src, dst, gathered[0], self.world, self.rank)
 
     def run_stacked(self, src: torch.Tensor, dst: torch.Tensor):
         """Filter a dense stack [batch][local extents...] (stacked=True)."""
@@ -98,8 +139,7 @@ class ShardedFilter:
                 plan.execute(src, dst)
                 return
             plan.stage1(src, dst, self._tails[0])
-            gathered = exchange_tails(self._tails, self.world, self.group)
-            plan.stage2(src, dst, gathered[0], self.world, self.rank)
+            self._finish(plan, src, dst, self._tails[0])
             return
         # sub-stacks on their own streams; the caller's stream is joined at both ends
         cur = torch.cuda.current_stream()
@@ -114,13 +154,9 @@ class ShardedFilter:
             for g, (a, b) in enumerate(parts):
                 with torch.cuda.stream(self.streams[g]):
                     self.plans[g].stage1(a, b, self._tails[g])
-            gathered = []
-            for g in range(G):                       # collectives are issued in the same order on every rank
+            for g, (a, b) in enumerate(parts):       # collectives are issued in the same order on every rank
                 with torch.cuda.stream(self.streams[g]):
-                    gathered.append(exchange_tails(self._tails[g:g + 1], self.world, self.group))
-            for g, (a, b) in enumerate(parts):
-                with torch.cuda.stream(self.streams[g]):
-                    self.plans[g].stage2(a, b, gathered[g][0], self.world, self.rank)
+                    self._finish(self.plans[g], a, b, self._tails[g])
         for st in self.streams:
             cur.wait_stream(st)
 

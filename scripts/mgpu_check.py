@@ -17,7 +17,8 @@ for (W, H) in [(2048, 2048), (8192, 8192)]:
     scans = [Scan(0, True, G3), Scan(0, False, G3), Scan(1, True, G3), Scan(1, False, G3)]
     gen = torch.Generator(device="cuda").manual_seed(99)
     full = torch.rand((H, W), device="cuda", generator=gen)            # same image on every rank
-    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=world, shard_dim=1, batch=1)
+    flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=world, shard_dim=1, batch=1,
+                        exchange=os.environ.get("RF_EXCHANGE", "auto"))
     lo, hi = flt.rows
     src = full[lo:hi].contiguous(); dst = torch.empty_like(src)
     flt.run([src], [dst]); torch.cuda.synchronize()
@@ -33,7 +34,9 @@ B, W, H = 3, 2048, 2048
 scans = [Scan(0, True, G3), Scan(0, False, G3), Scan(1, True, G3), Scan(1, False, G3)]
 gen = torch.Generator(device="cuda").manual_seed(7)
 full = torch.rand((B, H, W), device="cuda", generator=gen)
-flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=world, shard_dim=1, batch=B, stacked=True)
+flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=world, shard_dim=1, batch=B, stacked=True,
+                    exchange=os.environ.get("RF_EXCHANGE", "auto"))
+if rank == 0: print("exchange:", "alltoall (column-chunked)" if flt.chunked else "allgather", flush=True)
 lo, hi = flt.rows
 src = full[:, lo:hi].contiguous(); dst = torch.empty_like(src)
 flt.run_stacked(src, dst); torch.cuda.synchronize()

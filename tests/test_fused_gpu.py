@@ -169,7 +169,9 @@ def test_device_resident_in_place(oracle):
 
 
 # ---- strip-sharded execution with virtual strips on one device -------------------------------------------
-def run_sharded(a, scans, border, nshards, shard_dim, engine):
+def run_sharded(a, scans, border, nshards, shard_dim, engine, chunked=False):
+    """chunked=True: the column-chunked exchange (two all-to-alls, rf_plan_shard_resolve_lines +
+    rf_plan_stage2_ext) emulated on one device: virtual rank q resolves line chunk q for every strip."""
     import torch
     nd = a.ndim
     ax = nd - 1 - shard_dim
@@ -188,8 +190,23 @@ def run_sharded(a, scans, border, nshards, shard_dim, engine):
     for p, s, d, t in zip(plans, srcs, dsts, tails):
         p.stage1(s, d, t)
     gathered = torch.stack(tails).contiguous()              # what an all-gather delivers, rank major
-    for r, (p, s, d) in enumerate(zip(plans, srcs, dsts)):
-        p.stage2(s, d, gathered, nshards, r)
+    if chunked:
+        V = plans[0].shard_vectors
+        lines = gathered.shape[1] // V
+        assert V > 0 and lines % nshards == 0
+        c = lines // nshards
+        g3 = gathered.view(nshards, V, nshards, c)          # [strip][vector][chunk][line in chunk]
+        ext = torch.empty((nshards, V, nshards, c), device="cuda", dtype=gathered.dtype)
+        for q in range(nshards):                            # what virtual rank q receives, resolves and sends back
+            recv = g3[:, :, q, :].contiguous()
+            ext_all = torch.empty_like(recv)
+            plans[q].shard_resolve_lines(recv, nshards, c, ext_all)
+            ext[:, :, q, :] = ext_all
+        for r, (p, s, d) in enumerate(zip(plans, srcs, dsts)):
+            p.stage2_ext(s, d, ext[r].contiguous().view(-1))
+    else:
+        for r, (p, s, d) in enumerate(zip(plans, srcs, dsts)):
+            p.stage2(s, d, gathered, nshards, r)
     torch.cuda.synchronize()
     out = np.concatenate([d.cpu().numpy() for d in dsts], axis=ax).view(np_dtype)
     for p in plans:
@@ -207,6 +224,18 @@ def test_strip_sharded_gaussian(oracle, engine, nshards):
         assert rel_err(out, truth) <= TOL
         whole = run(a, C3, border, engine=engine)
         assert rel_err(out, whole) < TOL        # different tile cuts: two independent fp32 evaluations
+
+
+@pytest.mark.parametrize("engine", ["fused", "generic"])
+@pytest.mark.parametrize("nshards", [2, 8])
+def test_strip_sharded_column_chunked_exchange_equals_allgather(oracle, engine, nshards):
+    a = rand_image((1024, 512), np.float32, 700 + nshards)
+    for border in ("clamp", "zero"):
+        np.testing.assert_array_equal(run_sharded(a, C3, border, nshards, 1, engine, chunked=True),
+                                      run_sharded(a, C3, border, nshards, 1, engine))
+    sat = [(0, True, [1, 1]), (1, True, [1, 1]), (1, False, [1, 1])]
+    u = rand_image((512, 256), np.uint32, 701)
+    np.testing.assert_array_equal(run_sharded(u, sat, "zero", 4, 1, engine, chunked=True), oracle.apply_filter(u, sat, threads=8))
 
 
 @pytest.mark.parametrize("engine", ["fused", "generic"])

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from recfilter_b200.sharded import exchange_tails, strip_bounds
+from recfilter_b200.sharded import exchange_tails, gather_carry_chunks, scatter_tail_chunks, strip_bounds
 
 
 def _free_port():
@@ -71,3 +71,43 @@ def test_strip_bounds():
         strip_bounds(1000, 3, 0)
     with pytest.raises(ValueError):
         strip_bounds(8192, 8, 0, multiple=2048)
+
+
+def _chunk_worker(rank, world, port, vectors, lines, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # tails of shard r: value encodes (shard, vector, line)
+        def tails_of(r):
+            v = torch.arange(vectors, dtype=torch.float32).unsqueeze(1) * 10000.0
+            return (v + torch.arange(lines, dtype=torch.float32).unsqueeze(0) + 1e6 * r).reshape(-1)
+        c = lines // world
+        recv = scatter_tail_chunks(tails_of(rank), vectors, world)          # [shard][vector][my chunk of the lines]
+        ok = list(recv.shape) == [world, vectors, c]
+        for g in range(world):
+            ok = ok and bool(torch.equal(recv[g], tails_of(g).view(vectors, lines)[:, rank * c:(rank + 1) * c]))
+        # a stand-in resolver: the carry entering shard g is the sum of the tails of the shards before it
+        ext_all = torch.stack([recv[:g].sum(0) if g else torch.zeros_like(recv[0]) for g in range(world)])
+        ext = gather_carry_chunks(ext_all)
+        want = sum((tails_of(g) for g in range(rank)), torch.zeros(vectors * lines))
+        ok = ok and bool(torch.equal(ext, want))
+        q.put((rank, ok))
+    except Exception as exc:
+        q.put((rank, f"{type(exc).__name__}: {exc}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_chunked_exchange_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chunk_worker, args=(r, world, port, 6, 32, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in results) == [0, 1]
+    assert all(ok is True for _, ok in results), results
