@@ -85,7 +85,8 @@ class ShardedFilter:
         bandwidth-bound tile kernels of another.
         exchange: "allgather" (every rank receives the tails of all shards and resolves its own carries),
         "alltoall" (column-chunked: every rank resolves 1/world of the lines for all shards; 2 small all-to-alls
-        instead of one all-gather whose volume grows with world) or "auto" (alltoall from 4 ranks on)."""
+        instead of one all-gather whose volume grows with world) or "auto" (alltoall from 4 ranks on when the
+        all-gather would deliver 8 MB or more per rank)."""
         self.rank, self.world, self.group, self.batch = rank, world, group, batch
         self.stacked = stacked and batch > 1
         self.groups = overlap if (self.stacked and overlap > 1 and batch % overlap == 0) else 1
@@ -112,7 +113,10 @@ class ShardedFilter:
         chunked_ok = world > 1 and self.vectors > 0 and lines % world == 0
         if exchange == "alltoall" and not chunked_ok:
             raise ValueError("exchange='alltoall' needs the cut lines to divide evenly among the ranks")
-        self.chunked = chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4))
+        # measured on 4 and 8 B200s (profiles/): the two all-to-alls win once the all-gather would deliver >= ~8 MB
+        # per rank; below that its single collective is faster
+        big = self.tail_elems * 4 * world >= (8 << 20)
+        self.chunked = chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4 and big))
 
     def _finish(self, plan, src, dst, tails):
         """Exchange the strip tails and finish the filter (stage 2) for one plan."""
