@@ -1424,7 +1424,9 @@ static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx,
         if (nbx * nbd * No > 0x7fffffffLL) continue;
         if (!fchain_fits(plan->R, (int)sx.size(), (int)sd.size(), (int)nbx, (int)nbd)) continue;
         if ((int64_t)std::max(sx.size(), sd.size()) * plan->R * std::max(nbx * Nd, nbd * Nx) * No > 0x7fffffffLL) continue;   // 32-bit carry offsets
-        if (!force && ts == 128 && nbx * nbd * No < 2 * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
+        // few tiles per SM: 64x64 tiles balance the machine better; with first-order scans (summed-area tables) their
+        // extra tails are cheap, so the switch comes later (measured: C2 4096^2 SAT 45.2 -> 41.8 us)
+        if (!force && ts == 128 && nbx * nbd * No < (plan->R == 1 ? 8 : 2) * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
             (sx.empty() || Nx / 64 <= 16 * FCHAIN_L) && (sd.empty() || Nd / 64 <= 16 * FCHAIN_L))
             continue;                       // small problem: smaller tiles fill the machine better
         return ts;
