@@ -108,6 +108,27 @@ def _box_check(kind, tmp_path):
     assert errs[1] <= 5e-2            # box twice through a 2nd-order integral image (fp32-unstable by construction)
 
 
+def _cascade_check(kind, tmp_path):
+    # tests/cpp/cascade_check.cpp: cascaded filters equal the uncut filter, links fused by the planner or not
+    for fusion_off in ("0", "1"):
+        exe = os.path.join(ROOT, "oracle", "_ref", kind, "cascade_check")
+        if not os.path.exists(exe):
+            pytest.skip(f"{exe} not built")
+        env = dict(os.environ, RECFILTER_NO_CHAIN_FUSION=fusion_off)
+        p = subprocess.run([exe, "256"], capture_output=True, text=True, timeout=600, cwd=tmp_path, env=env)
+        errs = [float(v) for v in re.findall(r"Max\s+relative error = (\S+) %", p.stdout)]
+        assert p.returncode == 0 and len(errs) == 2 and max(errs) <= MAX_PERCENT, (fusion_off, p.stdout + p.stderr)
+
+
+def test_cascades_equal_uncut_filter_on_oracle_backend(tmp_path):
+    _cascade_check("pin", tmp_path)
+
+
+@pytest.mark.gpu
+def test_cascades_equal_uncut_filter_on_b200(tmp_path):
+    _cascade_check("gpu", tmp_path)
+
+
 def _tuple_check(kind, tmp_path):
     # tests/cpp/tuple_check.cpp: a Tuple filter equals its planes filtered one by one; F(x,y)[i] feeds another filter
     rc, out = run(kind, "tuple_check", ["128"], cwd=tmp_path)
