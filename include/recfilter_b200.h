@@ -56,8 +56,9 @@ enum rf_dtype {
 /* image border (RecFilter::set_clamped_image_border, lib/recfilter.cpp:252-258) */
 enum rf_border { RF_BORDER_ZERO = 0, RF_BORDER_CLAMP = 1 };
 
-/* tile engines: the fused fast path (128x128 / 64x64 register tiles, orders <= 4, extents that are
- * multiples of the tile) and the generic engine (any order <= 32, ragged extents, honoured split() tiles) */
+/* tile engines: the fused fast path (128x128 / 64x64 register tiles, orders <= 4 -- 8 for single-scan long
+ * signals --, partial last tiles when the row pitch is a multiple of 16 bytes) and the generic engine (any
+ * order <= 32, any extents, honoured split() tiles) */
 enum rf_engine { RF_ENGINE_AUTO = 0, RF_ENGINE_GENERIC = 1, RF_ENGINE_FUSED = 2 };
 
 /* error codes */

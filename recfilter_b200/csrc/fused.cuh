@@ -98,6 +98,55 @@ __device__ __forceinline__ void scan_line(CT (&v)[N], CT (&h)[R], const CT (&a)[
     }
 }
 
+/*
+ * The same scan for a line of a partial tile (the last tile of a ragged extent): only the first `len`
+ * samples are real, the rest is padding (TMA zero fill, or leftovers of an earlier scan) and is cleared
+ * first.  A causal scan ends at sample len-1; an anticausal scan STARTS there, with the history it was
+ * given (a carry from beyond, or the closed-border rule).  Taken by edge CTAs only.  (Inlined on purpose: a
+ * call would force the register line of the common path into local memory.)
+ */
+template <typename CT, int R, int N, bool CAUSAL>
+__device__ __forceinline__ void scan_line_partial(CT (&v)[N], CT (&h)[R], const CT (&a)[R + 1], const bool clampb, const int len)
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) if (i >= len) v[i] = (CT)0;
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+        const int i = CAUSAL ? p : N - 1 - p;              // compile-time: the line stays in registers
+        if (i < len) {
+            const bool first = CAUSAL ? (i == 0) : (i == len - 1);
+            if (first && clampb) {
+                const CT x0 = v[i] * a[0];
+#pragma unroll
+                for (int k = 0; k < R; ++k) h[k] = x0;
+            }
+            CT acc = v[i];
+#pragma unroll
+            for (int k = R; k >= 1; --k) acc = fmadd(a[k], h[k - 1], acc);
+#pragma unroll
+            for (int k = R - 1; k >= 1; --k) h[k] = h[k - 1];
+            h[0] = acc;
+            if (first && clampb) {
+#pragma unroll
+                for (int k = 1; k < R; ++k) h[k] = acc;
+            }
+            v[i] = acc;
+        }
+    }
+}
+template <typename CT, int R, int N, bool RAGGED>
+__device__ __forceinline__ void scan_any(CT (&v)[N], CT (&h)[R], const CT (&a)[R + 1], const bool causal, const bool clampb,
+                                         const int len)
+{
+    if (!RAGGED || len == N) {                               // every CTA but the edge ones
+        if (causal) scan_line<CT, R, N, true >(v, h, a, clampb);
+        else        scan_line<CT, R, N, false>(v, h, a, clampb);
+    } else {
+        if (causal) scan_line_partial<CT, R, N, true >(v, h, a, clampb, len);
+        else        scan_line_partial<CT, R, N, false>(v, h, a, clampb, len);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): the kernels of a pass are launched back to back with
 // cudaLaunchAttributeProgrammaticStreamSerialization; a kernel lets its successor start launching
@@ -173,7 +222,9 @@ __device__ __forceinline__ void cp_async_wait_all()
 // thread-per-column accesses (32 lanes = the 32 words of one row) and the thread-per-row 128-bit
 // accesses (8 lanes = 8 different chunks) are both bank-conflict free, without padding.
 // ---------------------------------------------------------------------------------------------
-template <typename CT, int R, int TS, int MODE>
+// RAGGED: the pass has partial tiles (extents that are not multiples of TS); the instantiation without them is
+// the exact full-tile kernel (the partial-tile code costs the common path ~15 % when it is compiled in)
+template <typename CT, int R, int TS, int MODE, bool RAGGED>
 __global__ void __launch_bounds__(TS, (TS == 128 ? 3 : 6))
 fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_constant__ CUtensorMap tm_in,
                   const __grid_constant__ CUtensorMap tm_out)
@@ -193,6 +244,11 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     const int64_t o = b / p.nbd;
     const int x0 = bx * TS;
     const int y0 = (int)(o * p.Nd + (int64_t)bd * TS);                  // row of the [No*Nd][Nx] matrix
+
+    // partial tiles of a ragged extent: lenx / lend real samples per line, threads beyond them own padding lines
+    const int lenx = RAGGED ? (int)min((int64_t)TS, p.Nx - x0) : TS;
+    const int lend = (RAGGED && !p.signal) ? (int)min((int64_t)TS, p.Nd - (int64_t)bd * TS) : TS;
+    const bool col_valid = !RAGGED || tid < lenx, row_valid = !RAGGED || tid < lend;
 
     pdl_launch_dependents();
     // does an x scan start at a closed border in the row of this thread?  (signal mode: a row continues the
@@ -230,6 +286,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         for (int s = 0; s < p.md; ++s) {
             const bool closed = p.sd.causal[s] ? (bd == 0 && p.d_lo_closed) : (bd == p.nbd - 1 && p.d_hi_closed);
             if (closed) continue;
+            if (!col_valid) continue;
             const int64_t idx0 = ((int64_t)s * R * p.nbd + bd) * p.nly + o * p.Nx + (int64_t)bx * TS + tid;
 #pragma unroll
             for (int k = 0; k < R; ++k) cp_async4(cbuf + (s * R + k) * TS + tid, p.CY + idx0 + k * (int64_t)p.nbd * p.nly);
@@ -237,6 +294,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         for (int s = 0; s < p.mx; ++s) {
             const bool closed = x_closed(p.sx.causal[s] != 0);
             if (closed) continue;
+            if (!row_valid) continue;
             const int64_t idx0 = ((int64_t)s * R * p.nbx + bx) * p.nlx + o * p.Nd + (int64_t)bd * TS + tid;
 #pragma unroll
             for (int k = 0; k < R; ++k) cp_async4(cbuf + ((p.md + s) * R + k) * TS + tid, p.CX + idx0 + k * (int64_t)p.nbx * p.nlx);
@@ -252,7 +310,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             const bool causal = p.sd.causal[s] != 0;
             const bool closed = causal ? (bd == 0 && p.d_lo_closed) : (bd == p.nbd - 1 && p.d_hi_closed);
 #pragma unroll
-            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? cbuf[(s * R + k) * TS + tid] : (CT)0;
+            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed && col_valid) ? cbuf[(s * R + k) * TS + tid] : (CT)0;
         };
         const uint32_t cbase = smem_u32(tile) + (tid >> 5) * BOX_BYTES + (((tid & 31) >> 2) << 4) + ((tid & 3) << 2);
         mbar_wait(bar, 0);
@@ -273,9 +331,8 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
 #pragma unroll
             for (int k = 0; k < R; ++k) h[k] = hn[k];
             if (MODE == FMODE_P2 && s + 1 < p.md) load_cy(s + 1);
-            if (causal) scan_line<CT, R, TS, true >(v, h, a, closed && p.clamp);
-            else        scan_line<CT, R, TS, false>(v, h, a, closed && p.clamp);
-            if (MODE == FMODE_P1) {
+            scan_any<CT, R, TS, RAGGED>(v, h, a, causal, closed && p.clamp, lend);
+            if (MODE == FMODE_P1 && col_valid) {
                 const int64_t idx0 = ((int64_t)s * R * p.nbd + bd) * p.nly + ly;
 #pragma unroll
                 for (int k = 0; k < R; ++k) p.TY[idx0 + k * kstride] = h[k];
@@ -299,7 +356,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         auto load_cx = [&](int s) {
             const bool closed = x_closed(p.sx.causal[s] != 0);
 #pragma unroll
-            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed) ? cbuf[((p.md + s) * R + k) * TS + tid] : (CT)0;
+            for (int k = 0; k < R; ++k) hn[k] = (MODE == FMODE_P2 && !closed && row_valid) ? cbuf[((p.md + s) * R + k) * TS + tid] : (CT)0;
         };
         if (p.md > 0) __syncthreads(); else mbar_wait(bar, 0);
         load_cx(0);
@@ -325,9 +382,8 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
 #pragma unroll
             for (int k = 0; k < R; ++k) h[k] = hn[k];
             if (MODE == FMODE_P2 && s + 1 < p.mx) load_cx(s + 1);
-            if (causal) scan_line<CT, R, TS, true >(v, h, a, closed && p.clamp);
-            else        scan_line<CT, R, TS, false>(v, h, a, closed && p.clamp);
-            if (MODE == FMODE_P1) {
+            scan_any<CT, R, TS, RAGGED>(v, h, a, causal, closed && p.clamp, lenx);
+            if (MODE == FMODE_P1 && row_valid) {
                 const int64_t idx0 = ((int64_t)s * R * p.nbx + bx) * p.nlx + lx;
 #pragma unroll
                 for (int k = 0; k < R; ++k) p.TX[idx0 + k * kstride] = h[k];
@@ -743,7 +799,8 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
         for (int k = 0; k < R; ++k)
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
-                cy[sd][k][c] = sd < p.Sd ? p.CY[((int64_t)sd * R * p.nbd + bd) * p.nly + k * kstride_y + ly0 + c * 32] : (CT)0;
+                cy[sd][k][c] = (sd < p.Sd && (int64_t)bx * TS + lane + c * 32 < p.Nx)      // columns of a partial tile
+                                   ? p.CY[((int64_t)sd * R * p.nbd + bd) * p.nly + k * kstride_y + ly0 + c * 32] : (CT)0;
 #pragma unroll
     for (int sd = 0; sd < FMAX_SCANS; ++sd)
 #pragma unroll

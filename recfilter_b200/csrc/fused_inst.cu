@@ -30,7 +30,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <typename CT, int R, int TS>
+template <typename CT, int R, int TS, bool RAGGED>
 static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void* in, void* out, int mode,
                                         cudaStream_t st)
 {
@@ -41,10 +41,10 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e;
-        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P1, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)fused_tile_smem_bytes(TS));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)fused_tile_smem_bytes(TS, 2 * FMAX_SCANS * R * TS));
         if (e != cudaSuccess) return e;
         attr_set = true;
@@ -59,11 +59,11 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     cudaError_t e = make_tile_map(&tm_in, in, p.Nx, p.No * p.Nd, TS, is_float);
     if (e != cudaSuccess) return e;
     if (mode == FMODE_P1) {
-        return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P1>, dim3((unsigned)nblocks), dim3(TS), smem, st, pp, tm_in, tm_in);
+        return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P1, RAGGED>, dim3((unsigned)nblocks), dim3(TS), smem, st, pp, tm_in, tm_in);
     } else {
         e = make_tile_map(&tm_out, out, p.Nx, p.No * p.Nd, TS, is_float);
         if (e != cudaSuccess) return e;
-        return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P2>, dim3((unsigned)nblocks), dim3(TS), smem, st, pp, tm_in, tm_out);
+        return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P2, RAGGED>, dim3((unsigned)nblocks), dim3(TS), smem, st, pp, tm_in, tm_out);
     }
 }
 
@@ -71,8 +71,11 @@ template <typename CT, int R>
 static cudaError_t launch_fused_tile_T(const FusedParams<CT, R>& p, const void* in, void* out, int mode, int ts,
                                        cudaStream_t st)
 {
-    if (ts == 128) return launch_fused_tile_TS<CT, R, 128>(p, in, out, mode, st);
-    if (ts == 64)  return launch_fused_tile_TS<CT, R, 64>(p, in, out, mode, st);
+    const bool ragged = !p.signal && (p.Nx % ts != 0 || p.Nd % ts != 0);
+    if (ts == 128) return ragged ? launch_fused_tile_TS<CT, R, 128, true>(p, in, out, mode, st)
+                                 : launch_fused_tile_TS<CT, R, 128, false>(p, in, out, mode, st);
+    if (ts == 64)  return ragged ? launch_fused_tile_TS<CT, R, 64, true>(p, in, out, mode, st)
+                                 : launch_fused_tile_TS<CT, R, 64, false>(p, in, out, mode, st);
     return cudaErrorInvalidValue;
 }
 

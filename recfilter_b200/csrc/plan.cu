@@ -1339,7 +1339,7 @@ static int make_fused_pass(rf_plan* plan, const std::vector<HostScan>& sx, const
     if (!ps) return fail(RF_ENOMEM, "out of host memory");
     ps->sx = sx; ps->sd = sd; ps->ts = ts;
     auto geom = [ts](DimGeom& g, int64_t n, int nscans) {
-        g.n = n; g.t = ts; g.nb = (int)(n / ts); g.len_last = ts;
+        g.n = n; g.t = ts; g.nb = (int)((n + ts - 1) / ts); g.len_last = (int)(n - (int64_t)(g.nb - 1) * ts);   // ragged: partial last tile
         g.nscans = nscans; g.lo_closed = 1; g.hi_closed = 1;
     };
     geom(ps->gx, Nx, (int)sx.size());
@@ -1415,10 +1415,18 @@ static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx,
             } else if (cvt_coeff<uint32_t>(h.coeff[0]) != 1u) return 0;
         }
     const char* force = getenv("RFB_FUSED_TS");          // development knob: force a tile size
+    static const bool ragged_ok = !(getenv("RFB_NO_RAGGED") && atoi(getenv("RFB_NO_RAGGED")) != 0);
+    const bool sharded = opt.open_lo || opt.open_hi;
     for (int ts : { 128, 64 }) {
         if (force && atoi(force) != ts) continue;
-        if (Nx % ts || Nd % ts) continue;
-        const int64_t nbx = Nx / ts, nbd = Nd / ts;
+        if (Nx % ts || Nd % ts) {
+            // ragged extents: the last tile of a dimension is partial (TMA zero-fills / clips it, the kernels
+            // mask the padding).  Needs a 16-byte row pitch for the tensor map, one image per launch along d
+            // (a partial tile of a stack would reach into the next image) and unsharded strips.
+            if (!ragged_ok || sharded || Nx % 4 || Nx < ts || Nd < ts) continue;
+            if (Nd % ts && No != 1) continue;
+        }
+        const int64_t nbx = (Nx + ts - 1) / ts, nbd = (Nd + ts - 1) / ts;
         if (!sx.empty() && nbx > 16 * FCHAIN_L) continue;
         if (!sd.empty() && nbd > 16 * FCHAIN_L) continue;
         if (nbx * nbd * No > 0x7fffffffLL) continue;
@@ -1426,8 +1434,9 @@ static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx,
         if ((int64_t)std::max(sx.size(), sd.size()) * plan->R * std::max(nbx * Nd, nbd * Nx) * No > 0x7fffffffLL) continue;   // 32-bit carry offsets
         // few tiles per SM: 64x64 tiles balance the machine better; with first-order scans (summed-area tables) their
         // extra tails are cheap, so the switch comes later (measured: C2 4096^2 SAT 45.2 -> 41.8 us)
-        if (!force && ts == 128 && nbx * nbd * No < (plan->R == 1 ? 8 : 2) * 148 && Nx % 64 == 0 && Nd % 64 == 0 &&
-            (sx.empty() || Nx / 64 <= 16 * FCHAIN_L) && (sd.empty() || Nd / 64 <= 16 * FCHAIN_L))
+        if (!force && ts == 128 && nbx * nbd * No < (plan->R == 1 ? 8 : 2) * 148 && Nx >= 64 && Nd >= 64 &&
+            (Nx % 64 == 0 || Nx % 128 != 0) && (Nd % 64 == 0 || Nd % 128 != 0) &&
+            (sx.empty() || (Nx + 63) / 64 <= 16 * FCHAIN_L) && (sd.empty() || (Nd + 63) / 64 <= 16 * FCHAIN_L))
             continue;                       // small problem: smaller tiles fill the machine better
         return ts;
     }

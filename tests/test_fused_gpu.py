@@ -100,7 +100,7 @@ def test_integer_feedforward_not_one_takes_generic_engine():
     with pytest.raises(RecFilterError, match="not eligible"):
         Plan((128, 128), "u32", [Scan(0, True, [2, 1])], engine="fused")
     with pytest.raises(RecFilterError, match="not eligible"):
-        Plan((100, 128), "f32", [Scan(0, True, [1.0, 0.5])], engine="fused")
+        Plan((102, 128), "f32", [Scan(0, True, [1.0, 0.5])], engine="fused")      # row pitch not a multiple of 16 bytes
     with pytest.raises(RecFilterError, match="not eligible"):
         Plan((128, 128), "f32", [Scan(0, True, [1.0] + [0.1] * 5)], engine="fused")
 
@@ -338,3 +338,31 @@ def test_box_filter_from_summed_table_bit_exact_on_integers(oracle):
             ref += pad[dy:dy + n, dx:dx + n]
     inner = (slice(B + 1, n - B - 1),) * 2
     np.testing.assert_array_equal(out[inner], ref[inner].astype(np.float32))
+
+
+# ---- ragged extents on the fused path: partial last tiles (TMA zero fill / clipping, masked padding) ----
+@pytest.mark.parametrize("shape", [(1080, 1920), (130, 260), (129, 132), (255, 388), (200, 1024), (1024, 200), (136, 128)])
+@pytest.mark.parametrize("border", ["clamp", "zero"])
+def test_ragged_extents_take_the_fused_path(oracle, shape, border):
+    a = rand_image(shape, np.float32, 1300 + shape[0])
+    out = check_float(oracle, a, C3, border)                       # engine="fused": fails if the pass is not eligible
+    gen = run(a, C3, border, engine="generic")
+    assert rel_err(out, gen) < 2 * TOL
+
+
+def test_ragged_integer_and_mixed_scans_bit_exact(oracle):
+    for shape in [(130, 196), (257, 132), (1000, 520)]:
+        a = rand_image(shape, np.uint32, 1400 + shape[0])
+        check_int(oracle, a, [(0, True, [1, 1]), (1, True, [1, 1])])
+        check_int(oracle, a, [(0, True, [1, 1]), (1, False, [1, -1, 3]), (0, False, [1, 1]), (1, True, [1, 2, -1])], "clamp")
+        check_int(oracle, a, [(1, False, [1, 3, 1, -2, 1]), (0, True, [1, -1])], "clamp")
+
+
+def test_ragged_single_dimension_and_volume(oracle):
+    a = rand_image((200, 300), np.float32, 1500)
+    check_float(oracle, a, [(0, True, G3), (0, False, G3)], "clamp")              # x only, ragged in both
+    check_float(oracle, a, [(1, False, G2), (1, True, G3)], "zero")               # d only
+    v = rand_image((150, 128, 192), np.float32, 1501)                             # ragged z (150), full x, y
+    sc = [(0, True, W2[0]), (0, False, W2[1]), (1, True, W2[2]), (1, False, W2[3]), (2, True, W2[4]), (2, False, W2[5])]
+    check_float(oracle, v, sc)
+    check_float(oracle, v, sc, "clamp")
