@@ -94,7 +94,9 @@ template <typename CT, int R, int S>
 static cudaError_t launch_fchain_S(const FChainParams<CT, R>& p, unsigned grid, dim3 block, size_t smem, cudaStream_t st)
 {
     static const bool small_off = getenv("RFB_CHAIN_NO256") && atoi(getenv("RFB_CHAIN_NO256")) != 0;
-    if (block.x * block.y <= 256 && !small_off) return launch_fchain_M<CT, R, S, 256>(p, grid, block, smem, st);
+    // measured on C3: with one wave of blocks (one 8192^2 image: 256 blocks) the register-rich instantiation is
+    // faster (182 vs 190 us per image); the three-blocks-per-SM one pays off once there are several waves
+    if (block.x * block.y <= 256 && grid >= 3 * 148 && !small_off) return launch_fchain_M<CT, R, S, 256>(p, grid, block, smem, st);
     return launch_fchain_M<CT, R, S, 512>(p, grid, block, smem, st);
 }
 

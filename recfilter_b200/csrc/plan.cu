@@ -1569,8 +1569,8 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
                                       : make_signal_pass_R<uint32_t>(plan.get(), R, sx[0], Nx, Nd * No);
             }
             if (!fts && opt.engine == RF_ENGINE_FUSED)
-                return fail(RF_EUNSUPPORTED, "engine=fused requested but a pass is not eligible (needs order <= 4, "
-                            "extents that are multiples of 64, non-zero float / unit integer feed-forward)");
+                return fail(RF_EUNSUPPORTED, "engine=fused requested but a pass is not eligible (needs order <= 4, a row pitch that is a multiple of 16 bytes, "
+                            "extents of at least one tile, non-zero float / unit integer feed-forward)");
             int rc;
             if (fts) rc = plan->is_float ? make_fused_pass_R<float>(plan.get(), R, sx, sd, Nx, Nd, No, fts, shard)
                                          : make_fused_pass_R<uint32_t>(plan.get(), R, sx, sd, Nx, Nd, No, fts, shard);
