@@ -48,3 +48,10 @@ def test_descriptor_struct_matches_header():
     assert ctypes.sizeof(_Scan) == 3 * 4 + 33 * 4
     assert ctypes.sizeof(_Options) == (4 + 5 + 8) * 4
     assert ctypes.sizeof(_Desc) == 8 + 32 + 12 + 64 * ctypes.sizeof(_Scan) + ctypes.sizeof(_Options)
+
+
+def test_tap_struct_matches_header():
+    # rf_tap in include/recfilter_b200.h: float weight; int32 source; int32 offset[4], lo[4], hi[4]
+    from recfilter_b200.capi import _Tap
+    assert ctypes.sizeof(_Tap) == 4 + 4 + 3 * 4 * 4
+    assert _Tap.offset.offset == 8 and _Tap.lo.offset == 24 and _Tap.hi.offset == 40
