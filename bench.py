@@ -165,7 +165,11 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step": 1},
+        # the GPU arm's N = 1 configuration; the CPU sample of it is one image per step
+        "config": {"workload": WORKLOAD, "images_per_step": BATCH, "sharding": "none",
+                   "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % BATCH,
+                   "tile": "128x128 register tiles (fused engine)", "streams": "1",
+                   "sample": "bounded CPU sample: one 8192x8192 image per step"},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
                          "sample": "one full 8192x8192 image per step, oracle/oracle.c serial recurrence loops, "
                                    "OpenMP over independent lines (Halide x86 JIT of the reference cannot be built here)"},
