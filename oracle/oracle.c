@@ -20,11 +20,18 @@
  *       type T; integer T truncates them and integer arithmetic wraps.
  *   tests/test_generic_xyz.cpp:56-116, apps/summed_table/summed_table.cpp:67-82,
  *   apps/bspline/bicubic_filter.cpp:124-156 are the reference's own inline loops
- *   of exactly this recurrence; oracle/pin (see oracle/Makefile) runs those
- *   programs against this file and checks "Max relative error = 0".
+ *   of exactly this recurrence; oracle/Makefile compiles those programs unchanged
+ *   (_ref/pin/<prog>) and pin_reference.py runs them against this file.
  *
- * Parity status: pinned against the reference tests' inline loops by
- * oracle/pin_reference.py (results in tests/golden/PIN_REPORT.json).
+ * Parity status: pinned.  oracle/pin_reference.py (results in tests/golden/PIN_REPORT.json):
+ *   zero border, ff = 1 : nine programs of tests/*.cpp, bit exact in the test loops' summation order;
+ *   clamped border      : apps/bspline/bicubic_filter (unit gain {1+a,-a}: error 0) and
+ *                         apps/bspline/biquintic_cascaded_filter ({1+a,-a,0.1}: gain 1.1, order 2; its check
+ *                         applies the scans in another, commuting, order: 4.3e-5 % = fp32 rounding), at widths
+ *                         64 and 256; biquintic_overlapped_filter dies in gpu_auto_schedule() with the
+ *                         reference's own assertion (lib/recfilter.cpp:699-704), as it does on the reference.
+ *   Every pin uses the reference's all-ones input (lib/recfilter.h:695-696); the Gaussian / audio / box apps
+ *   carry no check in the reference.
  *
  * Layout: dense, dimension 0 contiguous (Halide::Image layout,
  * lib/recfilter.cpp:970-981).  Arithmetic is done in T with separate multiply

@@ -36,6 +36,14 @@ TESTS = ["test_type_invariance", "test_repeated_causal", "test_repeated_anticaus
 # test_overlap_filter_order compares two library results (cascade vs overlapped filter): it pins
 # overlap_to_higher_order_filter, but its "Reference" is not the output of an inline loop -> no golden vector
 NO_GOLDEN = {"test_overlap_filter_order"}
+# apps/bspline: the reference's only checks of the CLAMPED border (lib/recfilter.cpp:330-336) and of feed-forward
+# coefficients != 1.  bicubic_filter {1+a,-a} has unit gain; the biquintic apps use {1+a,-a,0.1} (gain 1.1, order 2).
+# Their check() applies the scans as +x,+y,-x,-y while the filter is +x,-x,+y,-y (the +y / -x swap commutes
+# mathematically, not in fp32 rounding), so the biquintic pin is to fp32 rounding, not bit exact.
+# biquintic_overlapped_filter calls gpu_auto_schedule() without RecFilter::set_max_threads_per_cuda_warp(): the
+# reference dies there with its own assertion (lib/recfilter.cpp:699-704) and so must this build.
+CLAMPED_APPS = {"bicubic_filter": 0.0, "biquintic_cascaded_filter": 1e-4}
+CLAMPED_DIES = {"biquintic_overlapped_filter": "set_max_threads_per_cuda_warp"}
 
 
 def parse_block(text, title, nvals):
@@ -59,7 +67,7 @@ def parse_block(text, title, nvals):
     return vals[:nvals] if len(vals) >= nvals else None
 
 
-def run(prog, order, dump=None):
+def run(prog, order, dump=None, args=()):
     env = dict(os.environ)
     if order == "tests":
         env["ORACLE_SUM_ORDER"] = "tests"
@@ -67,7 +75,7 @@ def run(prog, order, dump=None):
         if os.path.exists(dump):
             os.remove(dump)
         env["RECFILTER_DUMP_FILTER"] = dump
-    p = subprocess.run([os.path.join(HERE, "_ref", "pin", prog)], capture_output=True, text=True, env=env, timeout=120)
+    p = subprocess.run([os.path.join(HERE, "_ref", "pin", prog), *args], capture_output=True, text=True, env=env, timeout=120)
     out = p.stdout + p.stderr
     m = re.search(r"Max\s+relative error = (\S+) %", out)
     return (float(m.group(1)) if m else None), out, p.returncode
@@ -99,6 +107,23 @@ def main():
                             "stages": filt["stages"], "reference_output": ref,
                             "note": "printed by the reference test's own inline loops, 6 significant digits"}
         print(f"{prog:32s} library order {e_lib} %   test-loop order {e_tst} %   {'ok' if verdict else 'FAIL'}")
+    for prog, tol in CLAMPED_APPS.items():
+        errs = {}
+        for width in (64, 256):
+            for order in ("library", "tests"):
+                e, _, rc = run(prog, order, args=("-w", str(width), "-t", "32"))
+                errs[f"w{width}_{order}_order"] = e if rc == 0 else None
+        verdict = all(v is not None and v <= tol for v in errs.values())
+        ok &= verdict
+        report[prog] = {"border": "clamp", "max_rel_err_percent": errs, "tolerance_percent": tol,
+                        "bit_exact": all(v == 0.0 for v in errs.values()), "pass": verdict}
+        print(f"{prog:32s} clamped border  {errs}   {'ok' if verdict else 'FAIL'}")
+    for prog, msg in CLAMPED_DIES.items():
+        _, out, rc = run(prog, "library", args=("-w", "64"))
+        verdict = rc != 0 and msg in out
+        ok &= verdict
+        report[prog] = {"expected": "dies with the reference's own assertion (lib/recfilter.cpp:699-704)", "pass": verdict}
+        print(f"{prog:32s} dies as the reference does: {'ok' if verdict else 'FAIL'}")
     report["_summary"] = {"all_pass": ok, "reference": "mit-gfx/recfilter tests/*.cpp compiled unchanged (oracle/Makefile)",
                           "oracle": "oracle/oracle.c through oracle/capi_oracle.c",
                           "expected": "bit exact in test-loop summation order except test_causal_anticausal_xy "
