@@ -59,7 +59,8 @@ enum rf_border { RF_BORDER_ZERO = 0, RF_BORDER_CLAMP = 1 };
 /* tile engines: the fused fast path (128x128 / 64x64 register tiles, orders <= 4 -- 8 for single-scan long
  * signals --, partial last tiles when the row pitch is a multiple of 16 bytes) and the generic engine (any
  * order <= 32, any extents, honoured split() tiles) */
-enum rf_engine { RF_ENGINE_AUTO = 0, RF_ENGINE_GENERIC = 1, RF_ENGINE_FUSED = 2 };
+enum rf_engine { RF_ENGINE_AUTO = 0, RF_ENGINE_GENERIC = 1, RF_ENGINE_FUSED = 2,
+                 RF_ENGINE_TWOPASS = 3   /* fused tile engine, but never the single-pass look-back kernels */ };
 
 /* error codes */
 enum rf_status {
@@ -68,7 +69,8 @@ enum rf_status {
     RF_EUNSUPPORTED  = -2,   /* valid request this engine does not implement */
     RF_ECUDA         = -3,   /* CUDA runtime error (message has the CUDA string) */
     RF_ENOMEM        = -4,
-    RF_ENODEVICE     = -5    /* no CUDA device: there is no CPU fallback */
+    RF_ENODEVICE     = -5,   /* no CUDA device: there is no CPU fallback */
+    RF_EINTERNAL     = -6    /* a kernel reported an internal failure (rf_plan_check) */
 };
 
 /* one scan = one RecFilter::add_filter call (lib/recfilter.cpp:264-392) */
@@ -126,6 +128,13 @@ int    rf_plan_describe(const rf_plan* plan, char* buf, size_t n);
  * void* (NULL = default stream).  Asynchronous with respect to the host.
  */
 int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stream);
+
+/*
+ * Wait for the device and report whether any kernel of the plan flagged an internal failure since the plan was
+ * created (the single-pass look-back kernels give up, instead of hanging, when a predecessor tile never
+ * publishes its carry).  RF_OK, or RF_EINTERNAL.  The host-buffer entry points and rf_plan_profile call it.
+ */
+int rf_plan_check(rf_plan* plan);
 
 /* Host buffers: H2D + execute + D2H, synchronous (the realize() path). */
 int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host);

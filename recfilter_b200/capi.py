@@ -26,7 +26,7 @@ DTYPES = {
     "f32": (0, np.float32), "i32": (2, np.int32), "u32": (3, np.uint32),
     "i16": (4, np.int16), "u16": (5, np.uint16), "i8": (6, np.int8), "u8": (7, np.uint8),
 }
-ENGINES = {"auto": 0, "generic": 1, "fused": 2}
+ENGINES = {"auto": 0, "generic": 1, "fused": 2, "twopass": 3}
 _NP_TO_NAME = {np.dtype(v[1]): k for k, v in DTYPES.items()}
 
 
@@ -90,6 +90,7 @@ def lib():
     L.rf_plan_num_launches.argtypes = [vp]
     L.rf_plan_describe.argtypes = [vp, C.c_char_p, sz]
     L.rf_plan_execute.argtypes = [vp, vp, vp, vp]
+    L.rf_plan_check.argtypes = [vp]
     L.rf_plan_execute_host.argtypes = [vp, vp, vp]
     L.rf_plan_execute_host_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.rf_plan_profile.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_float)]
@@ -244,6 +245,10 @@ class Plan:
         st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
         self.execute_ptr(src.data_ptr(), dst.data_ptr(), st)
         return dst
+
+    def check(self):
+        """Synchronise and raise if a kernel of the plan flagged an internal failure (rf_plan_check)."""
+        _check(lib().rf_plan_check(self._h), "rf_plan_check")
 
     def _check_tensor(self, t):
         if not t.is_cuda or not t.is_contiguous():

@@ -25,6 +25,7 @@ namespace rfb {
 
 constexpr int TILE = 64;          // register tile: samples per thread per scan
 constexpr int MAX_SCANS_DIM = 32; // scans along one dimension in one pass
+constexpr int RFB_MAX_DEVICES = 64; // per-device caches of function attributes
 
 // tile position classes along one dimension
 enum Variant { V_FIRST = 0, V_INTERIOR = 1, V_LAST = 2, V_SINGLE = 3, V_COUNT = 4 };

@@ -24,6 +24,7 @@
 #include <vector>
 #include "engine.h"
 #include "fused_params.h"
+#include "lookback_params.h"
 
 namespace rfb {
 
@@ -61,6 +62,25 @@ template <typename CT, int R> struct FLaunch;
         static cudaError_t cross(const FCrossParams<uint32_t, RR>& p, int ts, cudaStream_t s) { return launch_fcross_u##RR(p, ts, s); } \
     };
 RFB_FOR_EACH_FR(DEFINE_FLAUNCH_TRAITS)
+
+// single-pass look-back kernels (lookback_inst.cu)
+#define DECLARE_LBLAUNCHERS(RR)                                                                     \
+    cudaError_t launch_lb_tile_f##RR(const LBTileParams<float, RR>&, const void*, void*, int, cudaStream_t);      \
+    cudaError_t launch_lb_tile_u##RR(const LBTileParams<uint32_t, RR>&, const void*, void*, int, cudaStream_t);   \
+    cudaError_t launch_lb_signal_f##RR(const LBSignalParams<float, RR>&, const void*, void*, cudaStream_t);       \
+    cudaError_t launch_lb_signal_u##RR(const LBSignalParams<uint32_t, RR>&, const void*, void*, cudaStream_t);
+RFB_FOR_EACH_FR(DECLARE_LBLAUNCHERS)
+template <typename CT, int R> struct LBLaunch;
+#define DEFINE_LBLAUNCH_TRAITS(RR)                                                                  \
+    template <> struct LBLaunch<float, RR> {                                                        \
+        static cudaError_t tile(const LBTileParams<float, RR>& p, const void* i, void* o, int ts, cudaStream_t s) { return launch_lb_tile_f##RR(p, i, o, ts, s); } \
+        static cudaError_t signal(const LBSignalParams<float, RR>& p, const void* i, void* o, cudaStream_t s) { return launch_lb_signal_f##RR(p, i, o, s); } \
+    };                                                                                              \
+    template <> struct LBLaunch<uint32_t, RR> {                                                     \
+        static cudaError_t tile(const LBTileParams<uint32_t, RR>& p, const void* i, void* o, int ts, cudaStream_t s) { return launch_lb_tile_u##RR(p, i, o, ts, s); } \
+        static cudaError_t signal(const LBSignalParams<uint32_t, RR>& p, const void* i, void* o, cudaStream_t s) { return launch_lb_signal_u##RR(p, i, o, s); } \
+    };
+RFB_FOR_EACH_FR(DEFINE_LBLAUNCH_TRAITS)
 
 template <typename CT, int R> struct Launch;
 #define DEFINE_LAUNCH_TRAITS(RR)                                                                    \
@@ -466,6 +486,8 @@ struct PassBase {
     virtual int shard_resolve_lines(const void* gathered, int nshards, int64_t nlines, void* ext_all, cudaStream_t st) = 0;
     virtual int shard_vectors() const = 0;
     virtual const void* ext_buffer() const = 0;
+    // device word a kernel of the pass sets when it gave up waiting (look-back kernels), or null
+    virtual const uint32_t* error_flag() const { return nullptr; }
 };
 
 template <typename CT, int R>
@@ -1138,6 +1160,224 @@ struct SignalPass : PassBase {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// single-pass passes (kernels in lookback.cuh): every tile is read once and written once, the
+// inter-tile carries travel by decoupled look-back inside the one kernel.  Eligible: at most one
+// scan per dimension (any direction), full tiles, unsharded.
+// ---------------------------------------------------------------------------------------------
+template <typename CT, int R>
+struct LookbackBase : PassBase {
+    using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
+    DevBuf dCtl;                                   // [0] ticket counter, [1] error flag
+    uint32_t epoch = 0;
+    bool needs_carries() const override { return false; }
+    bool d_open() const override { return false; }
+    const void* ext_buffer() const override { return nullptr; }
+    size_t shard_tail_elems() const override { return 0; }
+    int shard_resolve(const void*, int, int, cudaStream_t) override { return RF_OK; }
+    int shard_resolve_lines(const void*, int, int64_t, void*, cudaStream_t) override { return RF_OK; }
+    int shard_vectors() const override { return 0; }
+    int launches() const override { return 1; }
+    int run_tails(const void*, void*, cudaStream_t) override { return RF_OK; }
+    int run_carries(const void*, void*, cudaStream_t, int) override { return RF_OK; }
+    const uint32_t* error_flag() const override { return dCtl.p ? (const uint32_t*)dCtl.p + 1 : nullptr; }
+    int init_ctl()
+    {
+        CUDA_TRY(dCtl.alloc(2 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemset(dCtl.p, 0, 2 * sizeof(uint32_t)));
+        return RF_OK;
+    }
+    // transition of one tile of `ts` samples (unit feed-forward form), raw basis
+    static std::vector<HT> tile_transition(const HostScan& sc, int ts, bool clamp)
+    {
+        DimGeom g; g.n = 4 * (int64_t)ts; g.t = ts; g.nb = 4; g.len_last = ts; g.nscans = 1; g.lo_closed = 1; g.hi_closed = 1;
+        DimTables<HT> tab;
+        build_dim_tables<HT>(tab, std::vector<HostScan>(1, sc), g, R, clamp, 0, 0, false, true, ts);
+        return std::vector<HT>(tab.P.begin() + (size_t)V_INTERIOR * R * R, tab.P.begin() + (size_t)(V_INTERIOR + 1) * R * R);
+    }
+    static std::vector<HT> identity()
+    {
+        std::vector<HT> m((size_t)R * R, (HT)0);
+        for (int k = 0; k < R; ++k) m[k * R + k] = (HT)1;
+        return m;
+    }
+    static std::vector<HT> mat_pow(const std::vector<HT>& m, int64_t e)       // m^e by squaring
+    {
+        std::vector<HT> acc = identity(), base = m, tmp;
+        while (e > 0) {
+            if (e & 1) { matmul_rr<HT>(tmp, base.data(), acc.data(), R); acc = tmp; }
+            e >>= 1;
+            if (e) { matmul_rr<HT>(tmp, base.data(), base.data(), R); base = tmp; }
+        }
+        return acc;
+    }
+    // m^0 .. m^(n-1), concatenated
+    static std::vector<HT> mat_powers(const std::vector<HT>& m, int n)
+    {
+        std::vector<HT> out, acc = identity(), tmp;
+        for (int j = 0; j < n; ++j) {
+            out.insert(out.end(), acc.begin(), acc.end());
+            matmul_rr<HT>(tmp, m.data(), acc.data(), R); acc = tmp;
+        }
+        return out;
+    }
+    template <size_t N>
+    static void to_device_consts(CT (&dst)[N], std::vector<HT> m)           // difference basis, rounded once
+    {
+        FusedPass<CT, R>::conjugate_blocks(m);
+        for (size_t i = 0; i < N && i < m.size(); ++i) dst[i] = (CT)m[i];
+    }
+};
+
+template <typename CT, int R>
+struct LookbackPass : LookbackBase<CT, R> {
+    using Base = LookbackBase<CT, R>;
+    using HT = typename Base::HT;
+    LBTileParams<CT, R> lp;
+    int ts = 128;
+    std::vector<HostScan> sx, sd;
+    DevBuf dPpow[2], dAgg[2], dInc[2], dStat[2];
+
+    size_t workspace() const override
+    {
+        size_t n = this->dCtl.bytes;
+        for (int i = 0; i < 2; ++i) n += dPpow[i].bytes + dAgg[i].bytes + dInc[i].bytes + dStat[i].bytes;
+        return n;
+    }
+    int init_dim(LBDim<CT, R>& dm, const std::vector<HostScan>& sc, int nb, int64_t ntiles, bool clamp, int slot, double& gain, uint32_t& gain_u)
+    {
+        std::memset(&dm, 0, sizeof(dm));
+        dm.nscan = (int)sc.size();
+        if (sc.empty()) return RF_OK;
+        dm.causal = sc[0].causal;
+        const std::vector<HT> c = coeff_vec<HT>(sc[0], R, true);
+        for (int k = 0; k <= R; ++k) dm.a[k] = (CT)c[k];
+        gain *= (double)sc[0].coeff[0];
+        gain_u *= cvt_coeff<uint32_t>(sc[0].coeff[0]);
+        const std::vector<HT> P = Base::tile_transition(sc[0], ts, clamp);
+        Base::to_device_consts(dm.P, P);
+        std::vector<HT> pw = Base::mat_powers(P, std::max(nb, 1));
+        FusedPass<CT, R>::conjugate_blocks(pw);
+        CUDA_TRY((upload<HT, CT>(dPpow[slot], pw)));
+        const size_t n = (size_t)ntiles * R * ts * sizeof(CT);
+        CUDA_TRY(dAgg[slot].alloc(n)); CUDA_TRY(dInc[slot].alloc(n));
+        CUDA_TRY(dStat[slot].alloc((size_t)ntiles * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemset(dStat[slot].p, 0, (size_t)ntiles * sizeof(uint32_t)));
+        dm.Ppow = (const CT*)dPpow[slot].p; dm.agg = (CT*)dAgg[slot].p; dm.inc = (CT*)dInc[slot].p;
+        dm.status = (uint32_t*)dStat[slot].p;
+        return RF_OK;
+    }
+    int init(int64_t Nx, int64_t Nd, int64_t No, bool clamp)
+    {
+        std::memset(&lp, 0, sizeof(lp));
+        lp.Nx = Nx; lp.Nd = Nd; lp.No = No;
+        lp.nbx = (int)(Nx / ts); lp.nbd = (int)(Nd / ts);
+        lp.clamp = clamp ? 1 : 0;
+        int rc = this->init_ctl();
+        if (rc) return rc;
+        const int64_t ntiles = (int64_t)lp.nbx * lp.nbd * No;
+        double gain = 1.0; uint32_t gain_u = 1u;
+        if ((rc = init_dim(lp.x, sx, lp.nbx, ntiles, clamp, 0, gain, gain_u))) return rc;
+        if ((rc = init_dim(lp.d, sd, lp.nbd, ntiles, clamp, 1, gain, gain_u))) return rc;
+        lp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
+        lp.ticket = (uint32_t*)this->dCtl.p; lp.err = (uint32_t*)this->dCtl.p + 1;
+        return RF_OK;
+    }
+    int run_final(const void* in, void* out, cudaStream_t st) override
+    {
+        cudaEvent_t ev = this->timer ? this->timer->begin(st, ST_FINAL) : nullptr;
+        lp.epoch = ++this->epoch & 0x3fffffffu;
+        CUDA_TRY((LBLaunch<CT, R>::tile(lp, in, out, ts, st)));
+        if (this->timer) this->timer->end(st, ev);
+        return RF_OK;
+    }
+    std::string describe() const override
+    {
+        char b[512];
+        snprintf(b, sizeof(b),
+                 "  single-pass look-back view [%lld][%lld][%lld]: %dx%d register tiles, d scans %d (%d tiles, %s) then x scans %d "
+                 "(%d tiles, %s), order<=%d, unit feed-forward, 1 launch, 8 B/sample\n",
+                 (long long)lp.No, (long long)lp.Nd, (long long)lp.Nx, ts, ts, lp.d.nscan, lp.nbd, lp.d.causal ? "causal" : "anticausal",
+                 lp.x.nscan, lp.nbx, lp.x.causal ? "causal" : "anticausal", R);
+        return b;
+    }
+};
+
+template <typename CT, int R>
+struct SignalLookbackPass : LookbackBase<CT, R> {
+    using Base = LookbackBase<CT, R>;
+    using HT = typename Base::HT;
+    static constexpr int ts = 128;
+    LBSignalParams<CT, R> sp;
+    HostScan scan;
+    int64_t nsig = 1, M = 1;
+    DevBuf dPlane, dQpow, dAgg, dInc, dStat;
+
+    static bool eligible(int64_t Nx, int64_t rows)
+    {
+        if (Nx % ((int64_t)ts * ts) != 0) return false;                       // whole tiles of 128 rows x 128 samples per signal
+        const int64_t tiles = (Nx / ((int64_t)ts * ts)) * rows;
+        return tiles > 0 && tiles <= 0x7fffffffLL && (Nx / ts) * rows <= 0x7fffffffLL;
+    }
+    size_t workspace() const override { return this->dCtl.bytes + dPlane.bytes + dQpow.bytes + dAgg.bytes + dInc.bytes + dStat.bytes; }
+
+    // [n][R][R] matrices -> [R*R][32] (lane fastest), difference basis
+    static std::vector<HT> lane_table(std::vector<HT> mats)
+    {
+        FusedPass<CT, R>::conjugate_blocks(mats);
+        std::vector<HT> out((size_t)R * R * 32, (HT)0);
+        for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < R * R; ++i) out[(size_t)i * 32 + l] = mats[(size_t)l * R * R + i];
+        return out;
+    }
+    int init(int64_t Nx, int64_t rows, bool clamp)
+    {
+        M = Nx / ts; nsig = rows;
+        std::memset(&sp, 0, sizeof(sp));
+        sp.rows = M * nsig;
+        sp.tiles_per_signal = (int)(M / ts);
+        sp.causal = scan.causal; sp.clamp = clamp ? 1 : 0;
+        const std::vector<HT> c = coeff_vec<HT>(scan, R, true);
+        for (int k = 0; k <= R; ++k) sp.a[k] = (CT)c[k];
+        sp.gain = std::is_same<CT, float>::value ? (CT)(double)scan.coeff[0] : (CT)cvt_coeff<uint32_t>(scan.coeff[0]);
+        int rc = this->init_ctl();
+        if (rc) return rc;
+        const std::vector<HT> P = Base::tile_transition(scan, ts, clamp);     // one row of 128 samples
+        for (int i = 0; i < 5; ++i) Base::to_device_consts(sp.Pstep[i], Base::mat_pow(P, 1 << i));
+        Base::to_device_consts(sp.Pwarp, Base::mat_pow(P, 32));
+        const std::vector<HT> Q = Base::mat_pow(P, ts);
+        Base::to_device_consts(sp.Q, Q);
+        Base::to_device_consts(sp.Q32, Base::mat_pow(Q, 32));
+        CUDA_TRY((upload<HT, CT>(dPlane, lane_table(Base::mat_powers(P, 32)))));
+        CUDA_TRY((upload<HT, CT>(dQpow, lane_table(Base::mat_powers(Q, 32)))));
+        const int64_t ntiles = sp.rows / ts;
+        CUDA_TRY(dAgg.alloc((size_t)ntiles * R * sizeof(CT))); CUDA_TRY(dInc.alloc((size_t)ntiles * R * sizeof(CT)));
+        CUDA_TRY(dStat.alloc((size_t)ntiles * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemset(dStat.p, 0, (size_t)ntiles * sizeof(uint32_t)));
+        sp.Plane = (const CT*)dPlane.p; sp.Qpow = (const CT*)dQpow.p;
+        sp.agg = (CT*)dAgg.p; sp.inc = (CT*)dInc.p; sp.status = (uint32_t*)dStat.p;
+        sp.ticket = (uint32_t*)this->dCtl.p; sp.err = (uint32_t*)this->dCtl.p + 1;
+        return RF_OK;
+    }
+    int run_final(const void* in, void* out, cudaStream_t st) override
+    {
+        cudaEvent_t ev = this->timer ? this->timer->begin(st, ST_FINAL) : nullptr;
+        sp.epoch = ++this->epoch & 0x3fffffffu;
+        CUDA_TRY((LBLaunch<CT, R>::signal(sp, in, out, st)));
+        if (this->timer) this->timer->end(st, ev);
+        return RF_OK;
+    }
+    std::string describe() const override
+    {
+        char b[512];
+        snprintf(b, sizeof(b),
+                 "  single-pass look-back signal pass: %lld signals x %lld rows of %d samples (thread per row, 128 rows per CTA, "
+                 "%d CTAs per signal), 1 %s scan of order<=%d, 1 launch, 8 B/sample\n",
+                 (long long)nsig, (long long)M, ts, sp.tiles_per_signal, scan.causal ? "causal" : "anticausal", R);
+        return b;
+    }
+};
+
 // narrow integer types are widened to the 32-bit compute ring on entry and truncated on exit
 // (arithmetic mod 2^16 / 2^8 is a quotient of arithmetic mod 2^32, so this is exact)
 template <typename ST>
@@ -1363,6 +1603,100 @@ static int make_signal_pass(rf_plan* plan, const HostScan& sc, int64_t Nx, int64
     return RF_OK;
 }
 
+template <typename CT, int R>
+static int make_lookback_pass(rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                              int64_t Nx, int64_t Nd, int64_t No, int ts)
+{
+    auto ps = std::unique_ptr<LookbackPass<CT, R>>(new (std::nothrow) LookbackPass<CT, R>());
+    if (!ps) return fail(RF_ENOMEM, "out of host memory");
+    ps->sx = sx; ps->sd = sd; ps->ts = ts;
+    int rc = ps->init(Nx, Nd, No, plan->desc.border == RF_BORDER_CLAMP);
+    if (rc) return rc;
+    plan->passes.push_back(std::move(ps));
+    return RF_OK;
+}
+template <typename CT>
+static int make_lookback_pass_R(rf_plan* plan, int R, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                                int64_t Nx, int64_t Nd, int64_t No, int ts)
+{
+    switch (R) {
+    case 1: return make_lookback_pass<CT, 1>(plan, sx, sd, Nx, Nd, No, ts);
+    case 2: return make_lookback_pass<CT, 2>(plan, sx, sd, Nx, Nd, No, ts);
+    case 3: return make_lookback_pass<CT, 3>(plan, sx, sd, Nx, Nd, No, ts);
+    case 4: return make_lookback_pass<CT, 4>(plan, sx, sd, Nx, Nd, No, ts);
+    }
+    return fail(RF_EUNSUPPORTED, "the single-pass tile kernel supports orders <= 4");
+}
+template <typename CT, int R>
+static int make_signal_lookback_pass(rf_plan* plan, const HostScan& sc, int64_t Nx, int64_t rows)
+{
+    auto ps = std::unique_ptr<SignalLookbackPass<CT, R>>(new (std::nothrow) SignalLookbackPass<CT, R>());
+    if (!ps) return fail(RF_ENOMEM, "out of host memory");
+    ps->scan = sc;
+    int rc = ps->init(Nx, rows, plan->desc.border == RF_BORDER_CLAMP);
+    if (rc) return rc;
+    plan->passes.push_back(std::move(ps));
+    return RF_OK;
+}
+template <typename CT>
+static int make_signal_lookback_pass_R(rf_plan* plan, int R, const HostScan& sc, int64_t Nx, int64_t rows)
+{
+    switch (R) {
+    case 1: return make_signal_lookback_pass<CT, 1>(plan, sc, Nx, rows);
+    case 2: return make_signal_lookback_pass<CT, 2>(plan, sc, Nx, rows);
+    case 3: return make_signal_lookback_pass<CT, 3>(plan, sc, Nx, rows);
+    case 4: return make_signal_lookback_pass<CT, 4>(plan, sc, Nx, rows);
+    case 8: return make_signal_lookback_pass<CT, 8>(plan, sc, Nx, rows);
+    }
+    return fail(RF_EUNSUPPORTED, "the single-pass signal kernel supports orders <= 8");
+}
+
+// single-pass kernels allowed?  (RF_ENGINE_TWOPASS / RFB_NO_LOOKBACK=1 keep the multi-pass kernels, for comparison)
+static bool lookback_allowed(const rf_plan* plan)
+{
+    const rf_options& opt = plan->desc.opt;
+    if (opt.engine == RF_ENGINE_GENERIC || opt.engine == RF_ENGINE_TWOPASS || opt.honor_tile) return false;
+    if (opt.open_lo || opt.open_hi) return false;
+    if (const char* e = getenv("RFB_NO_LOOKBACK")) if (atoi(e)) return false;
+    return true;
+}
+static bool unit_ff_ok(const rf_plan* plan, const HostScan& h)
+{
+    if (plan->is_float) {
+        const double inv = 1.0 / (double)h.coeff[0];
+        return h.coeff[0] != 0.f && std::isfinite((float)inv);
+    }
+    return cvt_coeff<uint32_t>(h.coeff[0]) == 1u;
+}
+// tile size of the single-pass 2-D kernel for this pass, or 0: at most one scan per dimension (8 B/sample instead
+// of the 12 B/sample of the two-sweep scheme -- fewer HBM bytes, so it is preferred whenever it applies)
+static int lookback_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                              int64_t Nx, int64_t Nd, int64_t No)
+{
+    if (!lookback_allowed(plan) || plan->R > 4) return 0;
+    if (sx.size() > 1 || sd.size() > 1 || (sx.empty() && sd.empty())) return 0;
+    for (const auto* v : { &sx, &sd })
+        for (const HostScan& h : *v) if (!unit_ff_ok(plan, h)) return 0;
+    const char* force = getenv("RFB_LB_TS");
+    for (int ts : { 128, 64 }) {
+        if (force && atoi(force) != ts) continue;
+        if (Nx % ts || Nd % ts) continue;
+        const int64_t ntiles = (Nx / ts) * (Nd / ts) * No;
+        if (ntiles > 0x7fffffffLL || Nx / ts > 0x7fffLL || Nd / ts > 0x7fffLL) continue;
+        // few tiles per SM: 64x64 tiles fill the machine better (3 CTAs of 128x128 per SM are resident)
+        if (!force && ts == 128 && ntiles < 8 * 3 * 148 && Nx % 64 == 0 && Nd % 64 == 0) continue;
+        return ts;
+    }
+    return 0;
+}
+static bool signal_lookback_eligible(const rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
+                                     int64_t Nx, int64_t rows)
+{
+    if (!lookback_allowed(plan) || plan->R > 8) return false;
+    if (!sd.empty() || sx.size() != 1 || !unit_ff_ok(plan, sx[0])) return false;
+    return SignalLookbackPass<float, 1>::eligible(Nx, rows);
+}
+
 // a pass with a single scan along the contiguous dimension of long lines: the signal pass (orders <= 8)
 static bool signal_eligible(const rf_plan* plan, const std::vector<HostScan>& sx, const std::vector<HostScan>& sd,
                             int64_t Nx, int64_t rows)
@@ -1563,12 +1897,21 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
 
         auto add = [&](const std::vector<HostScan>& sx, const std::vector<HostScan>& sd, int64_t Nx, int64_t Nd,
                        int64_t No, int tx, int td, bool fused, bool shard) -> int {
+            // fewest HBM bytes first: the single-pass look-back kernels move 8 B/sample, the two-sweep kernels 12
+            if (!shard) {
+                if (const int lts = lookback_tile_size(plan.get(), sx, sd, Nx, Nd, No))
+                    return plan->is_float ? make_lookback_pass_R<float>(plan.get(), R, sx, sd, Nx, Nd, No, lts)
+                                          : make_lookback_pass_R<uint32_t>(plan.get(), R, sx, sd, Nx, Nd, No, lts);
+            }
             const int fts = fused_tile_size(plan.get(), sx, sd, Nx, Nd, No);
+            if (!fts && !shard && signal_lookback_eligible(plan.get(), sx, sd, Nx, Nd * No))
+                return plan->is_float ? make_signal_lookback_pass_R<float>(plan.get(), R, sx[0], Nx, Nd * No)
+                                      : make_signal_lookback_pass_R<uint32_t>(plan.get(), R, sx[0], Nx, Nd * No);
             if (!fts && !shard && signal_eligible(plan.get(), sx, sd, Nx, Nd * No)) {
                 return plan->is_float ? make_signal_pass_R<float>(plan.get(), R, sx[0], Nx, Nd * No)
                                       : make_signal_pass_R<uint32_t>(plan.get(), R, sx[0], Nx, Nd * No);
             }
-            if (!fts && opt.engine == RF_ENGINE_FUSED)
+            if (!fts && (opt.engine == RF_ENGINE_FUSED || opt.engine == RF_ENGINE_TWOPASS))
                 return fail(RF_EUNSUPPORTED, "engine=fused requested but a pass is not eligible (needs order <= 4, a row pitch that is a multiple of 16 bytes, "
                             "extents of at least one tile, non-zero float / unit integer feed-forward)");
             int rc;
@@ -1725,7 +2068,7 @@ int rf_plan_execute_host_batch(rf_plan* plan, int n, const void* const* in_host,
         CUDA_TRY(cudaEventRecord(hp.down[b], hp.s_down));
     }
     CUDA_TRY(cudaStreamSynchronize(hp.s_down));
-    return RF_OK;
+    return rf_plan_check(plan);
 }
 
 int rf_plan_execute_host(rf_plan* plan, const void* in_host, void* out_host)
@@ -1778,7 +2121,7 @@ int rf_plan_profile(rf_plan* plan, const void* in_dev, void* out_dev, int iters,
     CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     *ms_per_iter = ms / iters;
-    return RF_OK;
+    return rf_plan_check(plan);
 }
 
 size_t rf_plan_shard_tail_bytes(const rf_plan* plan)
@@ -1863,6 +2206,20 @@ int rf_plan_stage2_ext(rf_plan* plan, const void* in_dev, void* out_dev, const v
         }
         if ((rc = p->run_final(src, out_dev, st))) return rc;
         src = out_dev;
+    }
+    return RF_OK;
+}
+
+int rf_plan_check(rf_plan* plan)
+{
+    if (!plan) return fail(RF_EINVAL, "null plan");
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& p : plan->passes) {
+        const uint32_t* flag = p->error_flag();
+        if (!flag) continue;
+        uint32_t v = 0;
+        CUDA_TRY(cudaMemcpy(&v, flag, sizeof(v), cudaMemcpyDeviceToHost));
+        if (v) return fail(RF_EINTERNAL, "a single-pass kernel gave up waiting for a predecessor tile (look-back spin limit)");
     }
     return RF_OK;
 }

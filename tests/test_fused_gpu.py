@@ -1,7 +1,9 @@
 """GPU parity tests of the fused fast path (recfilter_b200/csrc/fused.cuh) through the C ABI.
 
-Every case is run with engine="fused" (plan creation fails if a pass is not eligible, so a
-silent fall back to the generic engine cannot hide a bug), compared with the oracle exactly
+Every case is run with engine="twopass" (the two-sweep tile kernels + carry chains; plan creation fails if a
+pass is not eligible, so a silent fall back to the generic engine cannot hide a bug; the single-pass
+look-back kernels that "auto"/"fused" prefer for one-way filters have their own file,
+tests/test_lookback_gpu.py), compared with the oracle exactly
 like tests/test_parity_gpu.py, and -- where cheap -- also against the generic engine.
 Strip-sharded execution (rf_plan_stage1 / rf_plan_stage2) is checked with virtual strips on
 one device: the same kernels and the same tail exchange a multi-GPU run uses.
@@ -22,9 +24,9 @@ W2 = [[1.0, 0.5, 0.25], [1.0, 0.5, 0.125], [1.0, 0.5, 0.0625], [1.0, 0.5, 0.125]
 C3 = [(0, True, G3), (0, False, G3), (1, True, G3), (1, False, G3)]
 
 
-def run(a, scans, border="zero", engine="fused", **kw):
+def run(a, scans, border="zero", engine="twopass", **kw):
     plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in scans], border, engine=engine, **kw)
-    if engine == "fused":
+    if engine == "twopass":
         assert "fused pass" in plan.describe()
     out = plan.realize(a)
     plan.close()
@@ -277,9 +279,9 @@ def test_signal_pass_matches_oracle(oracle, n, rows, coeff, causal):
     a = rand_image((rows, n), np.float32, 77) - np.float32(0.5)
     scans = [(0, causal, coeff)]
     for border in ("zero", "clamp"):
-        plan = Plan((n, rows), "f32", [Scan(*s) for s in scans], border)
+        plan = Plan((n, rows), "f32", [Scan(*s) for s in scans], border, engine="twopass")
         if len(coeff) - 1 > 4 or n // 128 > 128:          # otherwise the 2-D fused pass takes it (few tiles per line)
-            assert "signal pass" in plan.describe(), plan.describe()
+            assert "signal pass" in plan.describe() and "look-back" not in plan.describe(), plan.describe()
         out = plan.realize(a)
         plan.close()
         truth = oracle.apply_filter(a.astype(np.float64), scans, border, threads=8)
@@ -291,7 +293,7 @@ def test_signal_pass_u32_prefix_sum_bit_exact(oracle):
     rng = np.random.default_rng(5)
     a = rng.integers(0, 1 << 32, size=(3, 128 * 128), dtype=np.uint32)          # wraps many times
     scans = [(0, True, [1, 1])]
-    plan = Plan((128 * 128, 3), "u32", [Scan(*s) for s in scans])
+    plan = Plan((128 * 128, 3), "u32", [Scan(*s) for s in scans], engine="twopass")
     # 3 signals x 128 rows = 384 rows: a multiple of the tile height, so the signal pass is eligible
     assert "signal pass" in plan.describe(), plan.describe()
     np.testing.assert_array_equal(plan.realize(a), oracle.apply_filter(a, scans))
