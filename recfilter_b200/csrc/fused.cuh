@@ -241,7 +241,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     int64_t b = p.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
     const int bx = (int)(b % p.nbx); b /= p.nbx;
     const int bd = (int)(b % p.nbd);
-    const int64_t o = b / p.nbd;
+    const int64_t o = b / p.nbd + p.o0;
     const int x0 = bx * TS;
     const int y0 = (int)(o * p.Nd + (int64_t)bd * TS);                  // row of the [No*Nd][Nx] matrix
 
@@ -271,7 +271,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             int64_t b2 = p.reverse ? (int64_t)gridDim.x - 1 - nxt : nxt;
             const int bx2 = (int)(b2 % p.nbx); b2 /= p.nbx;
             const int bd2 = (int)(b2 % p.nbd);
-            const int y2 = (int)((b2 / p.nbd) * p.Nd + (int64_t)bd2 * TS);
+            const int y2 = (int)((b2 / p.nbd + p.o0) * p.Nd + (int64_t)bd2 * TS);
 #pragma unroll
             for (int bb = 0; bb < NBOX; ++bb) tma_prefetch_2d(&tm_in, bx2 * TS + bb * 32, y2);
         }
@@ -531,9 +531,9 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
     CT* sT      = segtail + nseg * R * 32;                      // [S][L][slot]
     CT* sC      = sT;                                           // [S][L][slot]: the carries of a scan overwrite its tails in place
 
-    const int64_t l = (int64_t)blockIdx.x * 32 + lane;
-    const bool valid = l < p.nl;
-    const int64_t lc = valid ? l : p.nl - 1;                 // clamp: keep the barriers uniform
+    const int64_t l = p.l0 + (int64_t)blockIdx.x * 32 + lane;
+    const bool valid = l < p.l1;
+    const int64_t lc = valid ? l : p.l1 - 1;                 // clamp: keep the barriers uniform
     const int j0 = g * L;
     const int cnt = min(p.nb, j0 + L) - j0;                  // tiles of this thread (>= 1)
     const uint32_t plane32 = (uint32_t)p.nb * (uint32_t)p.nl;
@@ -596,8 +596,8 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
     pdl_wait();
     if (p.A) {
         // every line of the block lies in the same tile row: stage its A matrices (16 bytes per copy)
-        const int64_t o0 = ((int64_t)blockIdx.x * 32) / p.Nd;
-        const int bd0 = (int)((((int64_t)blockIdx.x * 32) - o0 * p.Nd) / p.ts);
+        const int64_t o0 = (p.l0 + (int64_t)blockIdx.x * 32) / p.Nd;
+        const int bd0 = (int)(((p.l0 + (int64_t)blockIdx.x * 32) - o0 * p.Nd) / p.ts);
         const CT* Arow = p.A + (o0 * p.nbd + bd0) * (int64_t)p.nb * S * R * p.sdk;
         const int n16 = p.nb * S * R * sdk4;
         for (int i = tid; i < n16; i += nthr)
@@ -778,11 +778,10 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 {
     constexpr int CPL = TS / 32;                 // columns per lane
     const int lane = threadIdx.x & 31;
-    const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t w = p.w0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     pdl_launch_dependents();
     pdl_wait();
-    if (w >= ntiles) return;
+    if (w >= p.w1) return;
     int64_t b = w;
     const int bx = (int)(b % p.nbx); b /= p.nbx;
     const int bd = (int)(b % p.nbd);

@@ -38,8 +38,11 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     if (nblocks <= 0) return cudaSuccess;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t smem = fused_tile_smem_bytes(TS, mode == FMODE_P2 ? (p.mx + p.md) * R * TS : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set_dev[RFB_MAX_DEVICES] = {};
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    const bool cacheable = dev >= 0 && dev < RFB_MAX_DEVICES;
+    if (!cacheable || !attr_set_dev[dev]) {
         cudaError_t e;
         e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P1, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)fused_tile_smem_bytes(TS));
@@ -47,7 +50,7 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
         e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)fused_tile_smem_bytes(TS, 2 * FMAX_SCANS * R * TS));
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (cacheable) attr_set_dev[dev] = true;
     }
     // L2 prefetch distance (blocks): about one wave of resident CTAs; RFB_PREFETCH overrides (0 = off)
     static const int prefetch_env = getenv("RFB_PREFETCH") ? atoi(getenv("RFB_PREFETCH")) : -1;
@@ -82,11 +85,15 @@ static cudaError_t launch_fused_tile_T(const FusedParams<CT, R>& p, const void* 
 template <typename CT, int R, int S, int MAXT>
 static cudaError_t launch_fchain_M(const FChainParams<CT, R>& p, unsigned grid, dim3 block, size_t smem, cudaStream_t st)
 {
-    static size_t attr_bytes = 0;
-    if (smem > 48u * 1024u && smem > attr_bytes) {
+    // the opt-in is per device: remember the largest size set on each
+    static size_t attr_bytes_dev[RFB_MAX_DEVICES] = {};
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    const bool cacheable = dev >= 0 && dev < RFB_MAX_DEVICES;
+    if (smem > 48u * 1024u && (!cacheable || smem > attr_bytes_dev[dev])) {
         cudaError_t e = cudaFuncSetAttribute(fchain_kernel<CT, R, S, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_bytes = smem;
+        if (cacheable) attr_bytes_dev[dev] = smem;
     }
     return launch_pdl(fchain_kernel<CT, R, S, MAXT>, dim3(grid), block, smem, st, p);
 }
@@ -101,12 +108,15 @@ static cudaError_t launch_fchain_S(const FChainParams<CT, R>& p, unsigned grid, 
 }
 
 template <typename CT, int R>
-static cudaError_t launch_fchain_T(const FChainParams<CT, R>& p, cudaStream_t st)
+static cudaError_t launch_fchain_T(const FChainParams<CT, R>& pin, cudaStream_t st)
 {
-    if (p.nl <= 0 || p.nb <= 0) return cudaSuccess;
+    FChainParams<CT, R> p = pin;
+    if (p.l1 == 0) { p.l0 = 0; p.l1 = p.nl; }
+    if (p.nl <= 0 || p.nb <= 0 || p.l1 <= p.l0) return cudaSuccess;
+    if (p.l0 % 32 != 0 || p.l1 > p.nl) return cudaErrorInvalidConfiguration;
     if (p.nseg < 1 || p.nseg > 16 || p.S < 1 || p.S > FMAX_SCANS || p.L < 1) return cudaErrorInvalidConfiguration;
     const dim3 block(32, p.nseg);
-    const unsigned grid = (unsigned)((p.nl + 31) / 32);
+    const unsigned grid = (unsigned)((p.l1 - p.l0 + 31) / 32);
     const size_t smem = fchain_smem_bytes(p.S, p.nseg, R, p.L, p.nb, p.A ? p.sdk : 0);
     if (smem > 227u * 1024u) return cudaErrorInvalidConfiguration;
     if ((int64_t)p.S * R * p.nb * p.nl > 0x7fffffffLL) return cudaErrorInvalidConfiguration;   // 32-bit offsets
@@ -125,9 +135,11 @@ static cudaError_t launch_fchain_T(const FChainParams<CT, R>& p, cudaStream_t st
 }
 
 template <typename CT, int R>
-static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& p, int ts, cudaStream_t st)
+static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& pin, int ts, cudaStream_t st)
 {
-    const int64_t ntiles = (int64_t)p.nbx * p.nbd * p.No;
+    FCrossParams<CT, R> p = pin;
+    if (p.w1 == 0) { p.w0 = 0; p.w1 = (int64_t)p.nbx * p.nbd * p.No; }
+    const int64_t ntiles = p.w1 - p.w0;
     if (ntiles <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((ntiles + 3) / 4);
     if (ts == 128) return launch_pdl(fcrossA_kernel<CT, R, 128>, dim3(grid), dim3(128), 0, st, p);

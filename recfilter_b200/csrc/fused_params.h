@@ -24,6 +24,7 @@ struct FusedScanTab {
 template <typename CT, int R>
 struct FusedParams {
     int64_t Nx, Nd, No;
+    int64_t o0;                   // first outer index of this launch (a slice of a stack; the grid covers No_slice images)
     int nbx, nbd;
     int clamp;
     int x_lo_closed, x_hi_closed, d_lo_closed, d_hi_closed;
@@ -47,6 +48,7 @@ template <typename CT, int R>
 struct FChainParams {
     const CT* T; CT* C;           // [s][k][j][l]
     int64_t nl; int nb; int S;
+    int64_t l0, l1;               // lines [l0, l1) are chained by this launch (l1 == 0: all nl lines); l0 a multiple of 32
     int nseg;                     // segments of L tiles (threadIdx.y)
     int L;                        // tiles per thread (4 or FCHAIN_L)
     int causal[FMAX_SCANS];
@@ -71,6 +73,7 @@ struct FCrossParams {
     CT* A;                        // [tile][sx][kx][sdk]  sdk = Sd * R rounded up to a multiple of 4
     const CT* L;                  // [V][Sx][R][TS]
     int64_t Nx, Nd, No; int nbx, nbd; int Sx, Sd; int sdk; int64_t nly, nlx;
+    int64_t w0, w1;               // tiles [w0, w1) are handled by this launch (w1 == 0: all of them)
 };
 
 // dynamic shared memory of one chain block (layout in fchain_kernel)

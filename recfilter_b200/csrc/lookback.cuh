@@ -35,38 +35,86 @@
 
 namespace rfb {
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-// payload loads bypass L1 (the line may have been cached before the producer wrote it)
-template <typename CT>
-__device__ __forceinline__ CT ld_cg(const CT* p)
-{
-    uint32_t r;
-    asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
-    return *reinterpret_cast<CT*>(&r);
-}
+/*
+ * Publication protocol: a carry vector travels as 16-byte chunks {3 values, tag}, tag = (epoch << 2) | state.
+ * An aligned 16-byte store / load is one transaction, so every chunk validates itself: no status word, no
+ * fence, no barrier between the payload and its flag.  A vector of R values takes (R + 2) / 3 chunks; a reader
+ * accepts a vector when all its chunks carry the same tag of this launch.  A record is ONE such vector: the
+ * owner first stores its aggregate there and later overwrites it with its inclusive vector (a reader that
+ * catches the overwrite half way sees different tags and polls again).  The epoch changes with every launch,
+ * so the records are never cleared: a chunk of an older launch reads as "nothing published".
+ */
+template <int R> struct LBChunks { static constexpr int N = (R + 2) / 3; };
 
-// wait until a tile of this launch has published something; returns its state (LB_AGGREGATE / LB_INCLUSIVE)
-__device__ __forceinline__ uint32_t lb_wait_status(const uint32_t* st, uint32_t epoch, uint32_t* err)
+__device__ __forceinline__ uint4 lb_ld_chunk(const uint4* p)
+{
+    uint4 r;                                  // volatile: served by L2, never by a stale L1 line
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void lb_st_chunk(uint4* p, uint4 v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <typename CT> __device__ __forceinline__ uint32_t lb_bits(CT x) { return *reinterpret_cast<uint32_t*>(&x); }
+template <typename CT> __device__ __forceinline__ CT lb_val(uint32_t x) { return *reinterpret_cast<CT*>(&x); }
+
+// write the vector h as chunks with the given tag
+template <typename CT, int R>
+__device__ __forceinline__ void lb_publish(uint4* rec, const CT (&h)[R], const uint32_t tag)
+{
+#pragma unroll
+    for (int c = 0; c < LBChunks<R>::N; ++c) {
+        uint4 q;
+        q.x = lb_bits<CT>(h[3 * c]);
+        q.y = 3 * c + 1 < R ? lb_bits<CT>(h[(3 * c + 1) % R]) : 0u;
+        q.z = 3 * c + 2 < R ? lb_bits<CT>(h[(3 * c + 2) % R]) : 0u;
+        q.w = tag;
+        lb_st_chunk(rec + c, q);
+    }
+}
+template <int R>
+__device__ __forceinline__ void lb_load_record(const uint4* rec, uint4 (&q)[LBChunks<R>::N])
+{
+#pragma unroll
+    for (int c = 0; c < LBChunks<R>::N; ++c) q[c] = lb_ld_chunk(rec + c);
+}
+// state of a loaded record (LB_NONE when it is not a complete vector of this launch); y gets the vector
+template <typename CT, int R>
+__device__ __forceinline__ uint32_t lb_decode(const uint4 (&q)[LBChunks<R>::N], CT (&y)[R], const uint32_t epoch)
+{
+    const uint32_t tag = q[0].w;
+    bool ok = (tag >> 2) == epoch && (tag & 3u) != LB_NONE;
+#pragma unroll
+    for (int c = 0; c < LBChunks<R>::N; ++c) {
+        ok = ok && q[c].w == tag;
+        y[3 * c] = lb_val<CT>(q[c].x);
+        if (3 * c + 1 < R) y[(3 * c + 1) % R] = lb_val<CT>(q[c].y);
+        if (3 * c + 2 < R) y[(3 * c + 2) % R] = lb_val<CT>(q[c].z);
+    }
+    return ok ? (tag & 3u) : (uint32_t)LB_NONE;
+}
+/*
+ * Wait until the record holds an aggregate or an inclusive vector of this launch; returns the state with the
+ * vector in y.  Never hangs the device: gives up after LB_SPIN_LIMIT polls (and at once when another thread
+ * already has), raising the error flag that rf_plan_check reports.
+ */
+template <typename CT, int R>
+__device__ __forceinline__ uint32_t lb_wait_record(const uint4* rec, CT (&y)[R], const uint32_t epoch, uint32_t* err)
 {
     uint32_t spins = 0;
     while (true) {
-        const uint32_t s = ld_acquire_u32(st);
-        if ((s >> 2) == epoch && (s & 3u) != LB_NONE) return s & 3u;
-        // never hang the device: give up after LB_SPIN_LIMIT polls, and at once when another CTA already has
+        uint4 q[LBChunks<R>::N];
+        lb_load_record<R>(rec, q);
+        const uint32_t state = lb_decode<CT, R>(q, y, epoch);
+        if (state != LB_NONE) return state;
         if (++spins > LB_SPIN_LIMIT || ((spins & 1023u) == 0u && *reinterpret_cast<volatile uint32_t*>(err) != 0u)) {
             *err = 1u;
+#pragma unroll
+            for (int k = 0; k < R; ++k) y[k] = (CT)0;
             return LB_INCLUSIVE;
         }
-        if (spins > 8) __nanosleep(40);
+        if (spins > 4) __nanosleep(32);
     }
 }
 
@@ -89,6 +137,17 @@ __device__ __forceinline__ void lb_matvec_acc(CT (&y)[R], const CT* m, const CT 
         y[k] = acc;
     }
 }
+// x <- M x
+template <typename CT, int R>
+__device__ __forceinline__ void lb_matvec_inplace(CT (&x)[R], const CT* m)
+{
+    CT n[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) n[k] = (CT)0;
+    lb_matvec_acc<CT, R>(n, m, x);
+#pragma unroll
+    for (int k = 0; k < R; ++k) x[k] = n[k];
+}
 
 // ---------------------------------------------------------------------------------------------
 // 2-D single pass
@@ -97,18 +156,24 @@ __device__ __forceinline__ void lb_matvec_acc(CT (&y)[R], const CT* m, const CT 
  * One dimension of a tile: on entry every thread holds its line of the tile in v (the column of thread tid
  * in the d phase, the row in the x phase); on return v is the line filtered with the carry that enters the
  * tile.  `reload` re-reads the line from shared memory (the unfiltered values: needed when the line was first
- * scanned with zero history for the aggregate).
- *   sidx    scan-order index of this tile, pstride the index distance to the previous tile of the line
+ * scanned with zero history for the aggregate).  Every line has its own record per tile (rec[tile][line]), so
+ * a thread depends on nobody but the thread that owns the same line in the tiles before: no barriers in here.
+ *   sidx    index of this tile in scan-order coordinates, pstride the index distance to the previous tile of the line
  *   j       position of the tile along the dimension in scan order (0 = starts at the closed border)
  */
 template <typename CT, int R, int TS, typename Reload>
 __device__ __forceinline__ void lb_phase(CT (&v)[TS], const LBDim<CT, R>& dm, const int j, const int nb, const uint32_t sidx,
                                          const uint32_t pstride, const uint32_t epoch, const bool clamp, uint32_t* err,
-                                         volatile uint32_t* sflag, const int tid, Reload reload)
+                                         const int tid, Reload reload)
 {
+    constexpr int NCH = LBChunks<R>::N;
+    constexpr int B = 8 / NCH;                           // predecessors fetched per round trip
     const bool causal = dm.causal != 0;
     const bool first = j == 0, last = j == nb - 1;
-    const uint32_t st_agg = (epoch << 2) | LB_AGGREGATE, st_inc = (epoch << 2) | LB_INCLUSIVE;
+    const uint32_t tag_agg = (epoch << 2) | LB_AGGREGATE, tag_inc = (epoch << 2) | LB_INCLUSIVE;
+    uint4* const recs = reinterpret_cast<uint4*>(dm.rec);
+    auto rec_of = [&](int q) -> uint4* { return recs + ((size_t)(sidx - (uint32_t)q * pstride) * TS + tid) * NCH; };
+    uint4* const mine = rec_of(0);
     CT a[R + 1];
 #pragma unroll
     for (int k = 0; k <= R; ++k) a[k] = dm.a[k];
@@ -118,51 +183,50 @@ __device__ __forceinline__ void lb_phase(CT (&v)[TS], const LBDim<CT, R>& dm, co
 
     bool have = first;
     if (!first) {
-        // the tile before this one may already be complete (usual along d: it started a tile row earlier)
-        if (tid == 0) sflag[1] = ld_acquire_u32(dm.status + (sidx - pstride)) == st_inc ? 1u : 0u;
-        __syncthreads();
-        have = sflag[1] != 0u;
+        // the tile before this one may already be complete; decided per warp, so that a warp scans once or
+        // twice as a whole
+        uint4 q[NCH];
+        lb_load_record<R>(rec_of(1), q);
+        CT y[R];
+        const bool ok = lb_decode<CT, R>(q, y, epoch) == LB_INCLUSIVE;
+        have = __all_sync(0xffffffffu, ok);
         if (have) {
-            const CT* src = dm.inc + (size_t)(sidx - pstride) * R * TS + tid;
 #pragma unroll
-            for (int k = 0; k < R; ++k) X[k] = ld_cg(src + k * TS);
+            for (int k = 0; k < R; ++k) X[k] = y[k];
         }
     }
     if (!have) {
-        // aggregate: the tile's own tail (zero history), published before anything is waited for
+        // aggregate: the line's own tail (zero history), published before anything is waited for
         CT h[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) h[k] = (CT)0;
         scan_dir<CT, R, TS>(v, h, a, causal, false);
         fdiff_fwd<CT, R>(h);
-        if (!last) {
-            CT* dst = dm.agg + (size_t)sidx * R * TS + tid;
+        if (!last) lb_publish<CT, R>(mine, h, tag_agg);
+        // look back: X = sum over the tiles before of P^(q-1) * (aggregate | inclusive), ended by the nearest
+        // inclusive; the records of B predecessors are fetched per round trip
+        bool done = false;
+        for (int q0 = 1; q0 <= j && !done; q0 += B) {
+            uint4 ch[B][NCH];
 #pragma unroll
-            for (int k = 0; k < R; ++k) dst[k * TS] = h[k];
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release_u32(dm.status + sidx, st_agg);
-        }
-        // look back (every warp walks on its own; the status of a tile is one word, so a warp is uniform)
-        for (int q = 1; q <= j; ++q) {
-            const uint32_t pidx = sidx - (uint32_t)q * pstride;
-            const uint32_t state = lb_wait_status(dm.status + pidx, epoch, err);
-            const CT* src = (state == LB_INCLUSIVE ? dm.inc : dm.agg) + (size_t)pidx * R * TS + tid;
-            CT y[R];
+            for (int i = 0; i < B; ++i)
+                if (q0 + i <= j) lb_load_record<R>(rec_of(q0 + i), ch[i]);
 #pragma unroll
-            for (int k = 0; k < R; ++k) y[k] = ld_cg(src + k * TS);
-            lb_matvec_acc<CT, R>(X, dm.Ppow + (size_t)(q - 1) * R * R, y);
-            if (state == LB_INCLUSIVE) break;
+            for (int i = 0; i < B; ++i) {
+                const int q = q0 + i;
+                if (!done && q <= j) {
+                    CT y[R];
+                    uint32_t state = lb_decode<CT, R>(ch[i], y, epoch);
+                    if (state == LB_NONE) state = lb_wait_record<CT, R>(rec_of(q), y, epoch, err);
+                    lb_matvec_acc<CT, R>(X, dm.Ppow + (size_t)(q - 1) * R * R, y);
+                    done = state == LB_INCLUSIVE;
+                }
+            }
         }
         if (!last) {
             // completed tail = aggregate + P * carry: successors need not wait for the re-scan
             lb_matvec_acc<CT, R>(h, dm.P, X);
-            CT* dst = dm.inc + (size_t)sidx * R * TS + tid;
-#pragma unroll
-            for (int k = 0; k < R; ++k) dst[k * TS] = h[k];
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release_u32(dm.status + sidx, st_inc);
+            lb_publish<CT, R>(mine, h, tag_inc);
         }
         reload();
     }
@@ -174,13 +238,18 @@ __device__ __forceinline__ void lb_phase(CT (&v)[TS], const LBDim<CT, R>& dm, co
     if (have && !last) {
         // the carry was known up front: one scan, its tail is the completed tail
         fdiff_fwd<CT, R>(hist);
-        CT* dst = dm.inc + (size_t)sidx * R * TS + tid;
-#pragma unroll
-        for (int k = 0; k < R; ++k) dst[k * TS] = hist[k];
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release_u32(dm.status + sidx, st_inc);
+        lb_publish<CT, R>(mine, hist, tag_inc);
     }
+}
+
+// ticket -> tile: tiles of an image are handed out along anti-diagonals (order[] lists the scan-order
+// coordinates, bxs | bds << 16), so the tiles a tile waits for (left, above) are a whole diagonal older
+__device__ __forceinline__ void lb_decode_ticket(const uint32_t t, const uint32_t* order, const uint32_t tiles_per_image,
+                                                 int& bxs, int& bds, int64_t& o)
+{
+    const uint32_t oi = t / tiles_per_image;
+    const uint32_t packed = __ldg(order + (t - oi * tiles_per_image));
+    bxs = (int)(packed & 0xffffu); bds = (int)(packed >> 16); o = oi;
 }
 
 template <typename CT, int R, int TS>
@@ -193,31 +262,41 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
     extern __shared__ __align__(16) unsigned char lbsmem_raw[];
     unsigned char* tile = lbsmem_raw + ((1024u - (smem_u32(lbsmem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tile + NBOX * BOX_BYTES);
-    volatile uint32_t* sflag = reinterpret_cast<volatile uint32_t*>(bar + 1);     // [0] ticket, [1] predecessor ready
+    volatile uint32_t* sflag = reinterpret_cast<volatile uint32_t*>(bar + 1);     // [0] ticket
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        sflag[0] = atomicInc(p.ticket, gridDim.x - 1);      // tiles in scan order; the last ticket resets the counter
+        sflag[0] = atomicInc(p.ticket, gridDim.x - 1);      // the last ticket resets the counter
         mbar_init(bar, 1);
     }
     __syncthreads();
     const uint32_t t = sflag[0];
     pdl_launch_dependents();
-    // scan-order coordinates (x fastest) and the tile they denote in memory
-    const int bxs = (int)(t % (uint32_t)p.nbx);
-    const uint32_t rest = t / (uint32_t)p.nbx;
-    const int bds = (int)(rest % (uint32_t)p.nbd);
-    const int64_t o = rest / (uint32_t)p.nbd;
+    // scan-order coordinates and the tile they denote in memory
+    const uint32_t tpi = (uint32_t)p.nbx * (uint32_t)p.nbd;
+    int bxs, bds; int64_t o;
+    lb_decode_ticket(t, p.order, tpi, bxs, bds, o);
     const int bx = (p.x.nscan && !p.x.causal) ? p.nbx - 1 - bxs : bxs;
     const int bd = (p.d.nscan && !p.d.causal) ? p.nbd - 1 - bds : bds;
     const int x0 = bx * TS;
     const int y0 = (int)(o * p.Nd + (int64_t)bd * TS);
+    const uint32_t sidx = ((uint32_t)o * (uint32_t)p.nbd + (uint32_t)bds) * (uint32_t)p.nbx + (uint32_t)bxs;
 
     pdl_wait();                                  // the input may come from the previous kernel; nothing is published before
     if (tid == 0) {
         mbar_expect_tx(bar, NBOX * BOX_BYTES);
 #pragma unroll
         for (int bb = 0; bb < NBOX; ++bb) tma_load_2d(tile + bb * BOX_BYTES, &tm_in, x0 + bb * 32, y0, bar);
+        // optional: the tile that will be handed out `prefetch` tickets from now starts its way into L2
+        const uint32_t t2 = t + (uint32_t)p.prefetch;
+        if (p.prefetch > 0 && t2 < gridDim.x) {
+            int bxs2, bds2; int64_t o2;
+            lb_decode_ticket(t2, p.order, tpi, bxs2, bds2, o2);
+            const int bx2 = (p.x.nscan && !p.x.causal) ? p.nbx - 1 - bxs2 : bxs2;
+            const int bd2 = (p.d.nscan && !p.d.causal) ? p.nbd - 1 - bds2 : bds2;
+#pragma unroll
+            for (int bb = 0; bb < NBOX; ++bb) tma_prefetch_2d(&tm_in, bx2 * TS + bb * 32, (int)(o2 * p.Nd + (int64_t)bd2 * TS));
+        }
     }
 
     CT v[TS];
@@ -249,7 +328,7 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
     if (p.d.nscan) {
         // ---- column phase: thread tid owns column tid; predecessors are the tiles above (scan order) ----
         load_col();
-        lb_phase<CT, R, TS>(v, p.d, bds, p.nbd, t, (uint32_t)p.nbx, p.epoch, p.clamp != 0, p.err, sflag, tid, load_col);
+        lb_phase<CT, R, TS>(v, p.d, bds, p.nbd, sidx, (uint32_t)p.nbx, p.epoch, p.clamp != 0, p.err, tid, load_col);
         const CT g = p.x.nscan ? (CT)1 : p.gain;
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
@@ -262,7 +341,7 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
         // ---- row phase on the d-complete tile: thread tid owns row tid; predecessors are the tiles before it ----
         if (p.d.nscan) __syncthreads();
         load_row();
-        lb_phase<CT, R, TS>(v, p.x, bxs, p.nbx, t, 1u, p.epoch, p.clamp != 0, p.err, sflag, tid, load_row);
+        lb_phase<CT, R, TS>(v, p.x, bxs, p.nbx, sidx, 1u, p.epoch, p.clamp != 0, p.err, tid, load_row);
 #pragma unroll
         for (int c4 = 0; c4 < TS / 4; ++c4) {
             uint4 q;
@@ -312,19 +391,28 @@ __device__ __forceinline__ CT lb_shfl_xor(CT x, int d)
     return *reinterpret_cast<const CT*>(&r);
 }
 
+/*
+ * One CTA = 128 consecutive rows of 128 samples of one signal (16384 samples), thread = row, thread order =
+ * scan order.  A row is scanned in four chunks of 32 samples straight from / to shared memory (small code, few
+ * registers); the same scan code runs twice (rolled loop): pass 0 with zero history for the row's tail, pass 1
+ * from the carry, storing.  Between the passes: Kogge-Stone over the rows of a warp, warps chained through
+ * shared memory, then the look-back over the tiles before -- by all four warps at once, warp w examining the
+ * tiles 32w+1 .. 32w+32 back (lane = tile), so one round trip covers 128 predecessors.
+ */
 template <typename CT, int R>
 __global__ void __launch_bounds__(128, 3)
 lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_constant__ CUtensorMap tm_in,
                  const __grid_constant__ CUtensorMap tm_out)
 {
     constexpr int TS = 128, NBOX = 4, BOX_BYTES = TS * 128;
+    constexpr int NCH = LBChunks<R>::N;
     extern __shared__ __align__(16) unsigned char lbsmem_raw[];
     unsigned char* tile = lbsmem_raw + ((1024u - (smem_u32(lbsmem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tile + NBOX * BOX_BYTES);
     volatile uint32_t* sflag = reinterpret_cast<volatile uint32_t*>(bar + 1);
     __shared__ CT swagg[4][R];        // inclusive tail of each warp's last row (zero carry into the warp)
-    __shared__ CT sE0[4][R];          // carry entering each warp when nothing enters the tile
-    __shared__ CT sX[R];              // carry entering the tile
+    __shared__ CT sS[4][R];           // look-back: partial sum of each warp's window
+    __shared__ uint32_t sI[4];        //            ... and whether the window held an inclusive vector
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) {
@@ -342,64 +430,90 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     // thread order = scan order: thread tid scans row `row`, after the row of thread tid - 1
     const int row = causal ? tid : TS - 1 - tid;
     const bool closed = pos == 0 && tid == 0;                     // the scan starts at the signal's border here
-    const uint32_t st_agg = (p.epoch << 2) | LB_AGGREGATE, st_inc = (p.epoch << 2) | LB_INCLUSIVE;
+    const uint32_t tag_agg = (p.epoch << 2) | LB_AGGREGATE, tag_inc = (p.epoch << 2) | LB_INCLUSIVE;
+    uint4* const recs = reinterpret_cast<uint4*>(p.rec);
 
     pdl_wait();
     if (tid == 0) {
         mbar_expect_tx(bar, NBOX * BOX_BYTES);
 #pragma unroll
         for (int bb = 0; bb < NBOX; ++bb) tma_load_2d(tile + bb * BOX_BYTES, &tm_in, bb * 32, y0, bar);
+        const uint32_t t2 = t + (uint32_t)p.prefetch;          // optional L2 prefetch of a tile handed out later
+        if (p.prefetch > 0 && t2 < gridDim.x) {
+            const uint32_t mt2 = causal ? t2 : gridDim.x - 1 - t2;
+#pragma unroll
+            for (int bb = 0; bb < NBOX; ++bb) tma_prefetch_2d(&tm_in, bb * 32, (int)(mt2 * TS));
+        }
     }
     CT a[R + 1];
 #pragma unroll
     for (int k = 0; k <= R; ++k) a[k] = p.a[k];
-    CT v[TS];
     const uint32_t rbase = smem_u32(tile) + row * 128;
     const uint32_t rx = (row & 7) << 4;
-    auto load_row = [&]() {
-#pragma unroll
-        for (int c4 = 0; c4 < TS / 4; ++c4) {
-            uint4 q;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-                         : "r"(rbase + (c4 >> 3) * BOX_BYTES + ((((c4 & 7) << 4)) ^ rx)));
-            v[c4 * 4 + 0] = *reinterpret_cast<const CT*>(&q.x);
-            v[c4 * 4 + 1] = *reinterpret_cast<const CT*>(&q.y);
-            v[c4 * 4 + 2] = *reinterpret_cast<const CT*>(&q.z);
-            v[c4 * 4 + 3] = *reinterpret_cast<const CT*>(&q.w);
-        }
-    };
     mbar_wait(bar, 0);
-    load_row();
 
-    // ---- the row's own tail, then an inclusive scan over the rows of the warp (Kogge-Stone) ----
+    CT h[R];                                                      // history entering the row (pass 1), tail leaving it
+#pragma unroll
+    for (int k = 0; k < R; ++k) h[k] = (CT)0;
     CT T[R];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        // ---- scan the row, 32 samples (one box) at a time ----
+#pragma unroll 1
+        for (int cc = 0; cc < NBOX; ++cc) {
+            const int c = causal ? cc : NBOX - 1 - cc;
+            CT v[32];
 #pragma unroll
-    for (int k = 0; k < R; ++k) T[k] = (CT)0;
-    scan_dir<CT, R, TS>(v, T, a, causal, closed && p.clamp);
-    fdiff_fwd<CT, R>(T);
+            for (int i = 0; i < 8; ++i) {
+                uint4 q;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                             : "r"(rbase + c * BOX_BYTES + ((i << 4) ^ rx)));
+                v[i * 4 + 0] = *reinterpret_cast<const CT*>(&q.x);
+                v[i * 4 + 1] = *reinterpret_cast<const CT*>(&q.y);
+                v[i * 4 + 2] = *reinterpret_cast<const CT*>(&q.z);
+                v[i * 4 + 3] = *reinterpret_cast<const CT*>(&q.w);
+            }
+            scan_dir<CT, R, 32>(v, h, a, causal, closed && p.clamp && cc == 0);
+            if (pass == 1) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        CT y[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) y[k] = lb_shfl_up<CT>(T[k], 1 << i);
-        if (lane >= (1 << i)) lb_matvec_acc<CT, R>(T, p.Pstep[i], y);
-    }
-    if (lane == 31) {
-#pragma unroll
-        for (int k = 0; k < R; ++k) swagg[w][k] = T[k];
-    }
-    __syncthreads();
+                for (int i = 0; i < 8; ++i) {
+                    uint4 q;
+                    *reinterpret_cast<CT*>(&q.x) = v[i * 4 + 0] * p.gain;
+                    *reinterpret_cast<CT*>(&q.y) = v[i * 4 + 1] * p.gain;
+                    *reinterpret_cast<CT*>(&q.z) = v[i * 4 + 2] * p.gain;
+                    *reinterpret_cast<CT*>(&q.w) = v[i * 4 + 3] * p.gain;
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
+                                 :: "r"(rbase + c * BOX_BYTES + ((i << 4) ^ rx)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+                }
+            }
+        }
+        if (pass == 1) break;
 
-    if (w == 0) {
-        // ---- carries entering the warps (zero carry into the tile), the tile's aggregate ----
-        CT E[R];
+        // ---- the row's own tail, then an inclusive scan over the rows of the warp (Kogge-Stone) ----
 #pragma unroll
-        for (int k = 0; k < R; ++k) E[k] = (CT)0;
+        for (int k = 0; k < R; ++k) T[k] = h[k];
+        fdiff_fwd<CT, R>(T);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            CT y[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) y[k] = lb_shfl_up<CT>(T[k], 1 << i);
+            if (lane >= (1 << i)) lb_matvec_acc<CT, R>(T, p.Pstep[i], y);
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) swagg[w][k] = T[k];
+        }
+        __syncthreads();
+        // ---- carry entering this thread's warp when nothing enters the tile (Ew), the tile's aggregate (E) ----
+        CT E[R], Ew[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { E[k] = (CT)0; Ew[k] = (CT)0; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (lane == 0) {
+            if (u == w) {
 #pragma unroll
-                for (int k = 0; k < R; ++k) sE0[u][k] = E[k];
+                for (int k = 0; k < R; ++k) Ew[k] = E[k];
             }
             CT n[R];
 #pragma unroll
@@ -408,111 +522,71 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
 #pragma unroll
             for (int k = 0; k < R; ++k) E[k] = n[k];
         }
-        // E is the aggregate of the tile
+        // ---- look back ----
         CT X[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) X[k] = (CT)0;
         if (pos != 0) {
-            if (!last_of_signal) {
-                if (lane < R) {
-                    CT mine = (CT)0;
-#pragma unroll
-                    for (int k = 0; k < R; ++k) if (lane == k) mine = E[k];
-                    p.agg[(size_t)t * R + lane] = mine;
-                }
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) st_release_u32(p.status + t, st_agg);
-            }
-            // ---- look back: lane k examines the tile k+1 (+32, +64 ...) before this one ----
-            for (uint32_t base = 1, win = 0; ; base += 32, ++win) {
-                const uint32_t dist = base + (uint32_t)lane;
+            if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
+            for (uint32_t round = 0; ; ++round) {
+                const uint32_t dist = round * 128u + (uint32_t)tid + 1u;
                 const bool active = dist <= pos;
                 uint32_t state = LB_NONE;
-                if (active) state = lb_wait_status(p.status + (t - dist), p.epoch, p.err);
+                CT y[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) y[k] = (CT)0;
+                if (active) state = lb_wait_record<CT, R>(recs + (size_t)(t - dist) * LB_SIGNAL_REC_CHUNKS, y, p.epoch, p.err);
                 const uint32_t incl = __ballot_sync(0xffffffffu, active && state == LB_INCLUSIVE);
                 const int firsti = incl ? __ffs(incl) - 1 : 32;                  // nearest complete predecessor of the window
                 CT c[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) c[k] = (CT)0;
-                if (active && lane <= firsti) {
-                    const CT* src = (state == LB_INCLUSIVE ? p.inc : p.agg) + (size_t)(t - dist) * R;
-                    CT y[R];
-#pragma unroll
-                    for (int k = 0; k < R; ++k) y[k] = ld_cg(src + k);
-                    lb_lane_matvec<CT, R>(c, p.Qpow, lane, y);                  // Q^lane * (aggregate | inclusive)
-                }
+                if (active && lane <= firsti) lb_lane_matvec<CT, R>(c, p.Qpow, lane, y);   // Q^lane * (aggregate | inclusive)
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
                     for (int k = 0; k < R; ++k) c[k] = c[k] + lb_shfl_xor<CT>(c[k], off);
-                for (uint32_t m = 0; m < win; ++m) {                            // the window lies 32 * win tiles back
-                    CT n[R];
+                if (lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < R; ++k) n[k] = (CT)0;
-                    lb_matvec_acc<CT, R>(n, p.Q32, c);
-#pragma unroll
-                    for (int k = 0; k < R; ++k) c[k] = n[k];
+                    for (int k = 0; k < R; ++k) sS[w][k] = c[k];
+                    sI[w] = incl;
                 }
+                __syncthreads();
+                // windows in order: Y = S_0 + Q32 (S_1 + Q32 (S_2 + Q32 S_3)), cut after the first window with an inclusive
+                int wl = 3;
 #pragma unroll
-                for (int k = 0; k < R; ++k) X[k] = X[k] + c[k];
-                if (incl || base + 31 >= pos) break;
+                for (int u = 3; u >= 0; --u) if (sI[u]) wl = u;
+                CT Y[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) Y[k] = sS[wl][k];
+                for (int u = wl - 1; u >= 0; --u) {
+                    lb_matvec_inplace<CT, R>(Y, p.Q32);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) Y[k] = Y[k] + sS[u][k];
+                }
+                for (uint32_t m = 0; m < 4 * round; ++m) lb_matvec_inplace<CT, R>(Y, p.Q32);   // the round lies 128 * round tiles back
+#pragma unroll
+                for (int k = 0; k < R; ++k) X[k] = X[k] + Y[k];
+                const bool done = (sI[0] | sI[1] | sI[2] | sI[3]) != 0u || round * 128u + 128u >= pos;
+                __syncthreads();                                                  // sS / sI are reused by the next round
+                if (done) break;
             }
         }
-        if (!last_of_signal) {
+        if (!last_of_signal && tid == 0) {
             lb_matvec_acc<CT, R>(E, p.Q, X);                                     // completed tail of the tile
-            if (lane < R) {
-                CT mine = (CT)0;
-#pragma unroll
-                for (int k = 0; k < R; ++k) if (lane == k) mine = E[k];
-                p.inc[(size_t)t * R + lane] = mine;
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release_u32(p.status + t, st_inc);
+            lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_inc);
         }
-        if (lane == 0) {
+        // ---- the carry entering this row: P^lane * (carry entering the warp) + inclusive tail of the row before ----
+        for (int u = 0; u < w; ++u) lb_matvec_inplace<CT, R>(X, p.Pwarp);
 #pragma unroll
-            for (int k = 0; k < R; ++k) sX[k] = X[k];
+        for (int k = 0; k < R; ++k) Ew[k] = Ew[k] + X[k];
+        lb_lane_matvec<CT, R>(h, p.Plane, lane, Ew);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const CT prev = lb_shfl_up<CT>(T[k], 1);
+            if (lane > 0) h[k] = h[k] + prev;
         }
-    }
-    __syncthreads();
-
-    // ---- the carry entering this row: P^lane * (carry entering the warp) + inclusive tail of the row before ----
-    CT Ew[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) Ew[k] = sX[k];
-    for (int u = 0; u < w; ++u) {
-        CT n[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) n[k] = (CT)0;
-        lb_matvec_acc<CT, R>(n, p.Pwarp, Ew);
-#pragma unroll
-        for (int k = 0; k < R; ++k) Ew[k] = n[k];
-    }
-#pragma unroll
-    for (int k = 0; k < R; ++k) Ew[k] = Ew[k] + sE0[w][k];
-    CT hist[R];
-    lb_lane_matvec<CT, R>(hist, p.Plane, lane, Ew);
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        const CT prev = lb_shfl_up<CT>(T[k], 1);
-        if (lane > 0) hist[k] = hist[k] + prev;
-    }
-    fdiff_inv<CT, R>(hist);
-
-    load_row();
-    scan_dir<CT, R, TS>(v, hist, a, causal, closed && p.clamp);
-#pragma unroll
-    for (int c4 = 0; c4 < TS / 4; ++c4) {
-        uint4 q;
-        *reinterpret_cast<CT*>(&q.x) = v[c4 * 4 + 0] * p.gain;
-        *reinterpret_cast<CT*>(&q.y) = v[c4 * 4 + 1] * p.gain;
-        *reinterpret_cast<CT*>(&q.z) = v[c4 * 4 + 2] * p.gain;
-        *reinterpret_cast<CT*>(&q.w) = v[c4 * 4 + 3] * p.gain;
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
-                     :: "r"(rbase + (c4 >> 3) * BOX_BYTES + ((((c4 & 7) << 4)) ^ rx)),
-                        "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+        fdiff_inv<CT, R>(h);
     }
     fence_async_smem();
     __syncthreads();

@@ -10,10 +10,11 @@
 
 namespace rfb {
 
-// status word of a tile: (epoch << 2) | state.  The epoch changes with every launch, so the arrays are
-// never cleared: a word of an older epoch reads as "nothing published".
+// tag of a published chunk: (epoch << 2) | state (see lookback.cuh).  The epoch changes with every launch, so the
+// records are never cleared: a chunk of an older epoch reads as "nothing published".
 enum { LB_NONE = 0, LB_AGGREGATE = 1, LB_INCLUSIVE = 2 };
 
+constexpr int LB_SIGNAL_REC_CHUNKS = 4;           // 64 bytes per tile (3 chunks used at order 8)
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 22;     // polls before a CTA gives up and raises the error flag (no hang)
 
 // one dimension of the 2-D look-back kernel: at most one scan
@@ -24,9 +25,9 @@ struct LBDim {
     CT  a[R + 1];                 // a[0]: clamp-history factor (1/b0), a[1..R]: feedback (unit feed-forward form)
     CT  P[R * R];                 // response of a tile's tail to the carry entering it (difference basis)
     const CT* Ppow;               // [nb][R][R]: P^j, j = 0 .. nb-1 (difference basis)
-    CT* agg;                      // [tile][R][TS]  tail of the tile scanned with zero history (difference basis)
-    CT* inc;                      // [tile][R][TS]  completed tail = the carry entering the next tile
-    uint32_t* status;             // [tile]
+    void* rec;                    // [tile][line] records of (R + 2) / 3 16-byte chunks {3 values, tag}: the line's
+                                  // aggregate (tail of the tile scanned with zero history), later overwritten by its
+                                  // inclusive (completed tail = the carry entering the next tile); difference basis
 };
 
 template <typename CT, int R>
@@ -36,6 +37,8 @@ struct LBTileParams {
     int clamp;
     CT  gain;                     // product of the feed-forward coefficients, applied at the store
     uint32_t epoch;
+    int prefetch;                 // > 0: L2 prefetch of the tile `prefetch` tickets ahead
+    const uint32_t* order;        // [nbx * nbd] ticket -> scan-order tile coordinates (bxs | bds << 16), anti-diagonals
     uint32_t* ticket;             // tile counter (atomicInc, wraps to 0 with the last tile)
     uint32_t* err;                // set to 1 if a CTA ran into LB_SPIN_LIMIT
     LBDim<CT, R> x, d;
@@ -56,10 +59,9 @@ struct LBSignalParams {
     CT  Q32[R * R];               // Q^32: one look-back window
     const CT* Plane;              // [R*R][32]: P^lane
     const CT* Qpow;               // [R*R][32]: Q^k
-    CT* agg;                      // [tile][R]
-    CT* inc;                      // [tile][R]
-    uint32_t* status;             // [tile]
+    void* rec;                    // [tile] records of LB_SIGNAL_REC_CHUNKS 16-byte chunks ((R + 2) / 3 used): aggregate, then inclusive
     uint32_t epoch;
+    int prefetch;                 // > 0: L2 prefetch of the tile `prefetch` tickets ahead
     uint32_t* ticket;
     uint32_t* err;
 };

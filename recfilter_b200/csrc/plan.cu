@@ -1236,13 +1236,13 @@ struct LookbackPass : LookbackBase<CT, R> {
     LBTileParams<CT, R> lp;
     int ts = 128;
     std::vector<HostScan> sx, sd;
-    DevBuf dPpow[2], dAgg[2], dInc[2], dStat[2];
+    DevBuf dPpow[2], dRec[2], dOrder;
 
     size_t workspace() const override
     {
         size_t n = this->dCtl.bytes;
-        for (int i = 0; i < 2; ++i) n += dPpow[i].bytes + dAgg[i].bytes + dInc[i].bytes + dStat[i].bytes;
-        return n;
+        for (int i = 0; i < 2; ++i) n += dPpow[i].bytes + dRec[i].bytes;
+        return n + dOrder.bytes;
     }
     int init_dim(LBDim<CT, R>& dm, const std::vector<HostScan>& sc, int nb, int64_t ntiles, bool clamp, int slot, double& gain, uint32_t& gain_u)
     {
@@ -1259,12 +1259,11 @@ struct LookbackPass : LookbackBase<CT, R> {
         std::vector<HT> pw = Base::mat_powers(P, std::max(nb, 1));
         FusedPass<CT, R>::conjugate_blocks(pw);
         CUDA_TRY((upload<HT, CT>(dPpow[slot], pw)));
-        const size_t n = (size_t)ntiles * R * ts * sizeof(CT);
-        CUDA_TRY(dAgg[slot].alloc(n)); CUDA_TRY(dInc[slot].alloc(n));
-        CUDA_TRY(dStat[slot].alloc((size_t)ntiles * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemset(dStat[slot].p, 0, (size_t)ntiles * sizeof(uint32_t)));
-        dm.Ppow = (const CT*)dPpow[slot].p; dm.agg = (CT*)dAgg[slot].p; dm.inc = (CT*)dInc[slot].p;
-        dm.status = (uint32_t*)dStat[slot].p;
+        // per tile and line: one vector of (R + 2) / 3 self-validating 16-byte chunks (epoch 0 = nothing)
+        const size_t n = (size_t)ntiles * ts * ((R + 2) / 3) * 16;
+        CUDA_TRY(dRec[slot].alloc(n));
+        CUDA_TRY(cudaMemset(dRec[slot].p, 0, n));
+        dm.Ppow = (const CT*)dPpow[slot].p; dm.rec = dRec[slot].p;
         return RF_OK;
     }
     int init(int64_t Nx, int64_t Nd, int64_t No, bool clamp)
@@ -1281,12 +1280,32 @@ struct LookbackPass : LookbackBase<CT, R> {
         if ((rc = init_dim(lp.d, sd, lp.nbd, ntiles, clamp, 1, gain, gain_u))) return rc;
         lp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
         lp.ticket = (uint32_t*)this->dCtl.p; lp.err = (uint32_t*)this->dCtl.p + 1;
+        // tiles of an image are handed out along anti-diagonals of the scan-order grid: the tiles a tile waits for
+        // (before it along x, before it along d) are then a whole diagonal older (RFB_LB_ORDER=rows: row-major)
+        {
+            const bool rows_first = getenv("RFB_LB_ORDER") && !strcmp(getenv("RFB_LB_ORDER"), "rows");
+            std::vector<uint32_t> order;
+            order.reserve((size_t)lp.nbx * lp.nbd);
+            if (rows_first) {
+                for (int bd = 0; bd < lp.nbd; ++bd) for (int bx = 0; bx < lp.nbx; ++bx) order.push_back((uint32_t)bx | ((uint32_t)bd << 16));
+            } else {
+                for (int sdiag = 0; sdiag <= lp.nbx + lp.nbd - 2; ++sdiag)
+                    for (int bd = std::max(0, sdiag - (lp.nbx - 1)); bd <= std::min(lp.nbd - 1, sdiag); ++bd)
+                        order.push_back((uint32_t)(sdiag - bd) | ((uint32_t)bd << 16));
+            }
+            CUDA_TRY(dOrder.alloc(order.size() * sizeof(uint32_t)));
+            CUDA_TRY(cudaMemcpy(dOrder.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            lp.order = (const uint32_t*)dOrder.p;
+        }
+        // optional L2 prefetch distance in tickets (RFB_LB_PREFETCH; measured: no gain, off)
+        lp.prefetch = 0;
+        if (const char* e = getenv("RFB_LB_PREFETCH")) lp.prefetch = atoi(e);
         return RF_OK;
     }
     int run_final(const void* in, void* out, cudaStream_t st) override
     {
         cudaEvent_t ev = this->timer ? this->timer->begin(st, ST_FINAL) : nullptr;
-        lp.epoch = ++this->epoch & 0x3fffffffu;
+        lp.epoch = (++this->epoch % 0x3fffffffu) + 1u;
         CUDA_TRY((LBLaunch<CT, R>::tile(lp, in, out, ts, st)));
         if (this->timer) this->timer->end(st, ev);
         return RF_OK;
@@ -1311,7 +1330,7 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
     LBSignalParams<CT, R> sp;
     HostScan scan;
     int64_t nsig = 1, M = 1;
-    DevBuf dPlane, dQpow, dAgg, dInc, dStat;
+    DevBuf dPlane, dQpow, dRec;
 
     static bool eligible(int64_t Nx, int64_t rows)
     {
@@ -1319,7 +1338,7 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
         const int64_t tiles = (Nx / ((int64_t)ts * ts)) * rows;
         return tiles > 0 && tiles <= 0x7fffffffLL && (Nx / ts) * rows <= 0x7fffffffLL;
     }
-    size_t workspace() const override { return this->dCtl.bytes + dPlane.bytes + dQpow.bytes + dAgg.bytes + dInc.bytes + dStat.bytes; }
+    size_t workspace() const override { return this->dCtl.bytes + dPlane.bytes + dQpow.bytes + dRec.bytes; }
 
     // [n][R][R] matrices -> [R*R][32] (lane fastest), difference basis
     static std::vector<HT> lane_table(std::vector<HT> mats)
@@ -1351,18 +1370,19 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
         CUDA_TRY((upload<HT, CT>(dPlane, lane_table(Base::mat_powers(P, 32)))));
         CUDA_TRY((upload<HT, CT>(dQpow, lane_table(Base::mat_powers(Q, 32)))));
         const int64_t ntiles = sp.rows / ts;
-        CUDA_TRY(dAgg.alloc((size_t)ntiles * R * sizeof(CT))); CUDA_TRY(dInc.alloc((size_t)ntiles * R * sizeof(CT)));
-        CUDA_TRY(dStat.alloc((size_t)ntiles * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemset(dStat.p, 0, (size_t)ntiles * sizeof(uint32_t)));
+        CUDA_TRY(dRec.alloc((size_t)ntiles * LB_SIGNAL_REC_CHUNKS * 16));
+        CUDA_TRY(cudaMemset(dRec.p, 0, (size_t)ntiles * LB_SIGNAL_REC_CHUNKS * 16));
         sp.Plane = (const CT*)dPlane.p; sp.Qpow = (const CT*)dQpow.p;
-        sp.agg = (CT*)dAgg.p; sp.inc = (CT*)dInc.p; sp.status = (uint32_t*)dStat.p;
+        sp.rec = dRec.p;
         sp.ticket = (uint32_t*)this->dCtl.p; sp.err = (uint32_t*)this->dCtl.p + 1;
+        sp.prefetch = 0;                                                    // optional L2 prefetch distance (measured: no gain)
+        if (const char* e = getenv("RFB_LB_PREFETCH")) sp.prefetch = atoi(e);
         return RF_OK;
     }
     int run_final(const void* in, void* out, cudaStream_t st) override
     {
         cudaEvent_t ev = this->timer ? this->timer->begin(st, ST_FINAL) : nullptr;
-        sp.epoch = ++this->epoch & 0x3fffffffu;
+        sp.epoch = (++this->epoch % 0x3fffffffu) + 1u;
         CUDA_TRY((LBLaunch<CT, R>::signal(sp, in, out, st)));
         if (this->timer) this->timer->end(st, ev);
         return RF_OK;
