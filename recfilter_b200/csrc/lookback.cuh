@@ -164,7 +164,7 @@ __device__ __forceinline__ void lb_matvec_inplace(CT (&x)[R], const CT* m)
 template <typename CT, int R, int TS, typename Reload>
 __device__ __forceinline__ void lb_phase(CT (&v)[TS], const LBDim<CT, R>& dm, const int j, const int nb, const uint32_t sidx,
                                          const uint32_t pstride, const uint32_t epoch, const bool clamp, uint32_t* err,
-                                         const int tid, Reload reload)
+                                         const int tid, Reload reload, const uint4 (&peek)[LBChunks<R>::N])
 {
     constexpr int NCH = LBChunks<R>::N;
     constexpr int B = 8 / NCH;                           // predecessors fetched per round trip
@@ -183,12 +183,10 @@ __device__ __forceinline__ void lb_phase(CT (&v)[TS], const LBDim<CT, R>& dm, co
 
     bool have = first;
     if (!first) {
-        // the tile before this one may already be complete; decided per warp, so that a warp scans once or
-        // twice as a whole
-        uint4 q[NCH];
-        lb_load_record<R>(rec_of(1), q);
+        // the tile before this one may already be complete (`peek`: its record, fetched by the caller behind other
+        // work); decided per warp, so that a warp scans once or twice as a whole
         CT y[R];
-        const bool ok = lb_decode<CT, R>(q, y, epoch) == LB_INCLUSIVE;
+        const bool ok = lb_decode<CT, R>(peek, y, epoch) == LB_INCLUSIVE;
         have = __all_sync(0xffffffffu, ok);
         if (have) {
 #pragma unroll
@@ -242,14 +240,32 @@ __device__ __forceinline__ void lb_phase(CT (&v)[TS], const LBDim<CT, R>& dm, co
     }
 }
 
-// ticket -> tile: tiles of an image are handed out along anti-diagonals (order[] lists the scan-order
-// coordinates, bxs | bds << 16), so the tiles a tile waits for (left, above) are a whole diagonal older
-__device__ __forceinline__ void lb_decode_ticket(const uint32_t t, const uint32_t* order, const uint32_t tiles_per_image,
+// ticket -> tile: tiles of an image are handed out along anti-diagonals of the scan-order grid (diagonal s lists
+// its tiles by ascending bds), so the tiles a tile waits for (left, above) are a whole diagonal older.  Closed
+// form (no table, no memory latency on the critical path of a CTA): growing diagonals, full-length diagonals,
+// shrinking diagonals.
+__device__ __forceinline__ uint32_t lb_tri_inv(const uint32_t q)          // largest s with s (s + 1) / 2 <= q
+{
+    uint32_t s = (uint32_t)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+    while ((s + 1) * (s + 2) / 2 <= q) ++s;
+    while (s * (s + 1) / 2 > q) --s;
+    return s;
+}
+__device__ __forceinline__ void lb_decode_ticket(const uint32_t t, const int nbx, const int nbd, const bool rows_first,
                                                  int& bxs, int& bds, int64_t& o)
 {
-    const uint32_t oi = t / tiles_per_image;
-    const uint32_t packed = __ldg(order + (t - oi * tiles_per_image));
-    bxs = (int)(packed & 0xffffu); bds = (int)(packed >> 16); o = oi;
+    const uint32_t tpi = (uint32_t)nbx * (uint32_t)nbd;
+    const uint32_t oi = t / tpi, r = t - oi * tpi;
+    o = oi;
+    if (rows_first) { bds = (int)(r / (uint32_t)nbx); bxs = (int)(r - (uint32_t)bds * (uint32_t)nbx); return; }
+    const uint32_t m = (uint32_t)min(nbx, nbd), M = (uint32_t)max(nbx, nbd);
+    const uint32_t tri = m * (m - 1) / 2, mid = (M - m + 1) * m;
+    uint32_t sd, i;
+    if (r < tri) { sd = lb_tri_inv(r); i = r - sd * (sd + 1) / 2; }
+    else if (r < tri + mid) { const uint32_t q = r - tri; sd = m - 1 + q / m; i = q % m; }
+    else { const uint32_t q = tpi - 1 - r, s2 = lb_tri_inv(q); sd = (uint32_t)(nbx + nbd - 2) - s2; i = s2 - (q - s2 * (s2 + 1) / 2); }
+    bds = max(0, (int)sd - (nbx - 1)) + (int)i;
+    bxs = (int)sd - bds;
 }
 
 template <typename CT, int R, int TS>
@@ -273,9 +289,8 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
     const uint32_t t = sflag[0];
     pdl_launch_dependents();
     // scan-order coordinates and the tile they denote in memory
-    const uint32_t tpi = (uint32_t)p.nbx * (uint32_t)p.nbd;
     int bxs, bds; int64_t o;
-    lb_decode_ticket(t, p.order, tpi, bxs, bds, o);
+    lb_decode_ticket(t, p.nbx, p.nbd, p.rows_first != 0, bxs, bds, o);
     const int bx = (p.x.nscan && !p.x.causal) ? p.nbx - 1 - bxs : bxs;
     const int bd = (p.d.nscan && !p.d.causal) ? p.nbd - 1 - bds : bds;
     const int x0 = bx * TS;
@@ -291,7 +306,7 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
         const uint32_t t2 = t + (uint32_t)p.prefetch;
         if (p.prefetch > 0 && t2 < gridDim.x) {
             int bxs2, bds2; int64_t o2;
-            lb_decode_ticket(t2, p.order, tpi, bxs2, bds2, o2);
+            lb_decode_ticket(t2, p.nbx, p.nbd, p.rows_first != 0, bxs2, bds2, o2);
             const int bx2 = (p.x.nscan && !p.x.causal) ? p.nbx - 1 - bxs2 : bxs2;
             const int bd2 = (p.d.nscan && !p.d.causal) ? p.nbd - 1 - bds2 : bds2;
 #pragma unroll
@@ -324,11 +339,18 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
         }
     };
 
+    // the record of the tile before this one along d travels while the tile itself is still on its way
+    constexpr int NCH = LBChunks<R>::N;
+    uint4 peek[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) peek[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (p.d.nscan && bds > 0)
+        lb_load_record<R>(reinterpret_cast<const uint4*>(p.d.rec) + ((size_t)(sidx - (uint32_t)p.nbx) * TS + tid) * NCH, peek);
     mbar_wait(bar, 0);
     if (p.d.nscan) {
         // ---- column phase: thread tid owns column tid; predecessors are the tiles above (scan order) ----
         load_col();
-        lb_phase<CT, R, TS>(v, p.d, bds, p.nbd, sidx, (uint32_t)p.nbx, p.epoch, p.clamp != 0, p.err, tid, load_col);
+        lb_phase<CT, R, TS>(v, p.d, bds, p.nbd, sidx, (uint32_t)p.nbx, p.epoch, p.clamp != 0, p.err, tid, load_col, peek);
         const CT g = p.x.nscan ? (CT)1 : p.gain;
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
@@ -339,9 +361,11 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
     }
     if (p.x.nscan) {
         // ---- row phase on the d-complete tile: thread tid owns row tid; predecessors are the tiles before it ----
+        if (bxs > 0)                                      // (fetched behind the barrier and the row loads)
+            lb_load_record<R>(reinterpret_cast<const uint4*>(p.x.rec) + ((size_t)(sidx - 1u) * TS + tid) * NCH, peek);
         if (p.d.nscan) __syncthreads();
         load_row();
-        lb_phase<CT, R, TS>(v, p.x, bxs, p.nbx, sidx, 1u, p.epoch, p.clamp != 0, p.err, tid, load_row);
+        lb_phase<CT, R, TS>(v, p.x, bxs, p.nbx, sidx, 1u, p.epoch, p.clamp != 0, p.err, tid, load_row, peek);
 #pragma unroll
         for (int c4 = 0; c4 < TS / 4; ++c4) {
             uint4 q;
@@ -392,27 +416,27 @@ __device__ __forceinline__ CT lb_shfl_xor(CT x, int d)
 }
 
 /*
- * One CTA = 128 consecutive rows of 128 samples of one signal (16384 samples), thread = row, thread order =
- * scan order.  A row is scanned in four chunks of 32 samples straight from / to shared memory (small code, few
- * registers); the same scan code runs twice (rolled loop): pass 0 with zero history for the row's tail, pass 1
- * from the carry, storing.  Between the passes: Kogge-Stone over the rows of a warp, warps chained through
- * shared memory, then the look-back over the tiles before -- by all four warps at once, warp w examining the
- * tiles 32w+1 .. 32w+32 back (lane = tile), so one round trip covers 128 predecessors.
+ * One CTA = 32 * NW consecutive rows of 128 samples of one signal, thread = row, thread order = scan order
+ * (NW = warps per CTA: 4, 2 or 1 -- smaller tiles mean more independent CTAs per SM to hide the load and
+ * look-back latencies behind, at the same work per thread).  A row is scanned in four chunks of 32 samples
+ * straight from / to shared memory (small code, few registers): pass 0 with zero history for the row's tail,
+ * pass 1 from the carry, storing.  Between the passes: Kogge-Stone over the rows of a warp, warps chained
+ * through shared memory, then the look-back over the tiles before -- by all warps at once, warp w examining
+ * the tiles 32w+1 .. 32w+32 back (lane = tile), so one round trip covers 32 * NW predecessors.
  */
-template <typename CT, int R>
-__global__ void __launch_bounds__(128, 3)
+template <typename CT, int R, int NW>
+__global__ void __launch_bounds__(32 * NW, 12 / NW)
 lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_constant__ CUtensorMap tm_in,
                  const __grid_constant__ CUtensorMap tm_out)
 {
-    constexpr int TS = 128, NBOX = 4, BOX_BYTES = TS * 128;
-    constexpr int NCH = LBChunks<R>::N;
+    constexpr int ROWS = 32 * NW, NBOX = 4, BOX_BYTES = ROWS * 128;
     extern __shared__ __align__(16) unsigned char lbsmem_raw[];
     unsigned char* tile = lbsmem_raw + ((1024u - (smem_u32(lbsmem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tile + NBOX * BOX_BYTES);
     volatile uint32_t* sflag = reinterpret_cast<volatile uint32_t*>(bar + 1);
-    __shared__ CT swagg[4][R];        // inclusive tail of each warp's last row (zero carry into the warp)
-    __shared__ CT sS[4][R];           // look-back: partial sum of each warp's window
-    __shared__ uint32_t sI[4];        //            ... and whether the window held an inclusive vector
+    __shared__ CT swagg[NW][R];       // inclusive tail of each warp's last row (zero carry into the warp)
+    __shared__ CT sS[NW][R];          // look-back: partial sum of each warp's window
+    __shared__ uint32_t sI[NW];       //            ... and whether the window held an inclusive vector
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) {
@@ -426,9 +450,9 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     const uint32_t pos = t % (uint32_t)p.tiles_per_signal;        // tile of its signal, scan order
     const bool last_of_signal = pos == (uint32_t)p.tiles_per_signal - 1;
     const uint32_t mt = causal ? t : gridDim.x - 1 - t;           // the tile in memory
-    const int y0 = (int)(mt * TS);
+    const int y0 = (int)(mt * ROWS);
     // thread order = scan order: thread tid scans row `row`, after the row of thread tid - 1
-    const int row = causal ? tid : TS - 1 - tid;
+    const int row = causal ? tid : ROWS - 1 - tid;
     const bool closed = pos == 0 && tid == 0;                     // the scan starts at the signal's border here
     const uint32_t tag_agg = (p.epoch << 2) | LB_AGGREGATE, tag_inc = (p.epoch << 2) | LB_INCLUSIVE;
     uint4* const recs = reinterpret_cast<uint4*>(p.rec);
@@ -442,7 +466,7 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
         if (p.prefetch > 0 && t2 < gridDim.x) {
             const uint32_t mt2 = causal ? t2 : gridDim.x - 1 - t2;
 #pragma unroll
-            for (int bb = 0; bb < NBOX; ++bb) tma_prefetch_2d(&tm_in, bb * 32, (int)(mt2 * TS));
+            for (int bb = 0; bb < NBOX; ++bb) tma_prefetch_2d(&tm_in, bb * 32, (int)(mt2 * ROWS));
         }
     }
     CT a[R + 1];
@@ -452,13 +476,8 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     const uint32_t rx = (row & 7) << 4;
     mbar_wait(bar, 0);
 
-    CT h[R];                                                      // history entering the row (pass 1), tail leaving it
-#pragma unroll
-    for (int k = 0; k < R; ++k) h[k] = (CT)0;
-    CT T[R];
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        // ---- scan the row, 32 samples (one box) at a time ----
+    // scan the row from / to shared memory, 32 samples (one box) at a time; h: history in, tail out
+    auto scan_row = [&](CT (&h)[R], auto store) {
 #pragma unroll 1
         for (int cc = 0; cc < NBOX; ++cc) {
             const int c = causal ? cc : NBOX - 1 - cc;
@@ -474,7 +493,7 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
                 v[i * 4 + 3] = *reinterpret_cast<const CT*>(&q.w);
             }
             scan_dir<CT, R, 32>(v, h, a, causal, closed && p.clamp && cc == 0);
-            if (pass == 1) {
+            if constexpr (decltype(store)::value) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     uint4 q;
@@ -487,76 +506,91 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
                 }
             }
         }
-        if (pass == 1) break;
+    };
 
-        // ---- the row's own tail, then an inclusive scan over the rows of the warp (Kogge-Stone) ----
+    CT h[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) T[k] = h[k];
-        fdiff_fwd<CT, R>(T);
+    for (int k = 0; k < R; ++k) h[k] = (CT)0;
+    scan_row(h, std::false_type());                               // pass 0: the row's own tail
+
+    // ---- inclusive scan over the rows of the warp (Kogge-Stone), difference basis ----
+    CT T[R];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            CT y[R];
+    for (int k = 0; k < R; ++k) T[k] = h[k];
+    fdiff_fwd<CT, R>(T);
 #pragma unroll
-            for (int k = 0; k < R; ++k) y[k] = lb_shfl_up<CT>(T[k], 1 << i);
-            if (lane >= (1 << i)) lb_matvec_acc<CT, R>(T, p.Pstep[i], y);
-        }
+    for (int i = 0; i < 5; ++i) {
+        CT y[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) y[k] = lb_shfl_up<CT>(T[k], 1 << i);
+        if (lane >= (1 << i)) lb_matvec_acc<CT, R>(T, p.Pstep[i], y);
+    }
+    // ---- carry entering this thread's warp when nothing enters the tile (Ew), the tile's aggregate (E) ----
+    CT E[R], Ew[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) { E[k] = (CT)0; Ew[k] = (CT)0; }
+    if constexpr (NW > 1) {
         if (lane == 31) {
 #pragma unroll
             for (int k = 0; k < R; ++k) swagg[w][k] = T[k];
         }
         __syncthreads();
-        // ---- carry entering this thread's warp when nothing enters the tile (Ew), the tile's aggregate (E) ----
-        CT E[R], Ew[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) { E[k] = (CT)0; Ew[k] = (CT)0; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NW; ++u) {
             if (u == w) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) Ew[k] = E[k];
             }
-            CT n[R];
+            if (u <= w || w == 0) {                                // warp w needs E_w; warp 0 also the tile's aggregate
+                CT n[R];
 #pragma unroll
-            for (int k = 0; k < R; ++k) n[k] = swagg[u][k];
-            lb_matvec_acc<CT, R>(n, p.Pwarp, E);
+                for (int k = 0; k < R; ++k) n[k] = swagg[u][k];
+                lb_matvec_acc<CT, R>(n, p.Pwarp, E);
 #pragma unroll
-            for (int k = 0; k < R; ++k) E[k] = n[k];
+                for (int k = 0; k < R; ++k) E[k] = n[k];
+            }
         }
-        // ---- look back ----
-        CT X[R];
+    } else {
 #pragma unroll
-        for (int k = 0; k < R; ++k) X[k] = (CT)0;
-        if (pos != 0) {
-            if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
-            for (uint32_t round = 0; ; ++round) {
-                const uint32_t dist = round * 128u + (uint32_t)tid + 1u;
-                const bool active = dist <= pos;
-                uint32_t state = LB_NONE;
-                CT y[R];
+        for (int k = 0; k < R; ++k) E[k] = lb_val<CT>(__shfl_sync(0xffffffffu, lb_bits<CT>(T[k]), 31));   // one warp: its last row's tail
+    }
+    // ---- look back ----
+    CT X[R];
 #pragma unroll
-                for (int k = 0; k < R; ++k) y[k] = (CT)0;
-                if (active) state = lb_wait_record<CT, R>(recs + (size_t)(t - dist) * LB_SIGNAL_REC_CHUNKS, y, p.epoch, p.err);
-                const uint32_t incl = __ballot_sync(0xffffffffu, active && state == LB_INCLUSIVE);
-                const int firsti = incl ? __ffs(incl) - 1 : 32;                  // nearest complete predecessor of the window
-                CT c[R];
+    for (int k = 0; k < R; ++k) X[k] = (CT)0;
+    if (pos != 0) {
+        if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
+        for (uint32_t round = 0; ; ++round) {
+            const uint32_t dist = round * (uint32_t)ROWS + (uint32_t)tid + 1u;
+            const bool active = dist <= pos;
+            uint32_t state = LB_NONE;
+            CT y[R];
 #pragma unroll
-                for (int k = 0; k < R; ++k) c[k] = (CT)0;
-                if (active && lane <= firsti) lb_lane_matvec<CT, R>(c, p.Qpow, lane, y);   // Q^lane * (aggregate | inclusive)
+            for (int k = 0; k < R; ++k) y[k] = (CT)0;
+            if (active) state = lb_wait_record<CT, R>(recs + (size_t)(t - dist) * LB_SIGNAL_REC_CHUNKS, y, p.epoch, p.err);
+            const uint32_t incl = __ballot_sync(0xffffffffu, active && state == LB_INCLUSIVE);
+            const int firsti = incl ? __ffs(incl) - 1 : 32;                  // nearest complete predecessor of the window
+            CT c[R];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
+            for (int k = 0; k < R; ++k) c[k] = (CT)0;
+            if (active && lane <= firsti) lb_lane_matvec<CT, R>(c, p.Qpow, lane, y);   // Q^lane * (aggregate | inclusive)
 #pragma unroll
-                    for (int k = 0; k < R; ++k) c[k] = c[k] + lb_shfl_xor<CT>(c[k], off);
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < R; ++k) c[k] = c[k] + lb_shfl_xor<CT>(c[k], off);
+            CT Y[R];
+            bool any_incl;
+            if constexpr (NW > 1) {
                 if (lane == 0) {
 #pragma unroll
                     for (int k = 0; k < R; ++k) sS[w][k] = c[k];
                     sI[w] = incl;
                 }
                 __syncthreads();
-                // windows in order: Y = S_0 + Q32 (S_1 + Q32 (S_2 + Q32 S_3)), cut after the first window with an inclusive
-                int wl = 3;
+                // windows in order: Y = S_0 + Q32 (S_1 + Q32 (S_2 + ...)), cut after the first window with an inclusive
+                int wl = NW - 1;
 #pragma unroll
-                for (int u = 3; u >= 0; --u) if (sI[u]) wl = u;
-                CT Y[R];
+                for (int u = NW - 1; u >= 0; --u) if (sI[u]) wl = u;
 #pragma unroll
                 for (int k = 0; k < R; ++k) Y[k] = sS[wl][k];
                 for (int u = wl - 1; u >= 0; --u) {
@@ -564,30 +598,38 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
 #pragma unroll
                     for (int k = 0; k < R; ++k) Y[k] = Y[k] + sS[u][k];
                 }
-                for (uint32_t m = 0; m < 4 * round; ++m) lb_matvec_inplace<CT, R>(Y, p.Q32);   // the round lies 128 * round tiles back
+                any_incl = false;
 #pragma unroll
-                for (int k = 0; k < R; ++k) X[k] = X[k] + Y[k];
-                const bool done = (sI[0] | sI[1] | sI[2] | sI[3]) != 0u || round * 128u + 128u >= pos;
-                __syncthreads();                                                  // sS / sI are reused by the next round
-                if (done) break;
+                for (int u = 0; u < NW; ++u) any_incl = any_incl || sI[u] != 0u;
+                __syncthreads();                                              // sS / sI are reused by the next round
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) Y[k] = c[k];
+                any_incl = incl != 0u;
             }
-        }
-        if (!last_of_signal && tid == 0) {
-            lb_matvec_acc<CT, R>(E, p.Q, X);                                     // completed tail of the tile
-            lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_inc);
-        }
-        // ---- the carry entering this row: P^lane * (carry entering the warp) + inclusive tail of the row before ----
-        for (int u = 0; u < w; ++u) lb_matvec_inplace<CT, R>(X, p.Pwarp);
+            for (uint32_t m = 0; m < (uint32_t)NW * round; ++m) lb_matvec_inplace<CT, R>(Y, p.Q32);   // the round lies 32 * NW * round tiles back
 #pragma unroll
-        for (int k = 0; k < R; ++k) Ew[k] = Ew[k] + X[k];
-        lb_lane_matvec<CT, R>(h, p.Plane, lane, Ew);
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const CT prev = lb_shfl_up<CT>(T[k], 1);
-            if (lane > 0) h[k] = h[k] + prev;
+            for (int k = 0; k < R; ++k) X[k] = X[k] + Y[k];
+            if (any_incl || round * (uint32_t)ROWS + (uint32_t)ROWS >= pos) break;
         }
-        fdiff_inv<CT, R>(h);
     }
+    if (!last_of_signal && tid == 0) {
+        lb_matvec_acc<CT, R>(E, p.Q, X);                                     // completed tail of the tile
+        lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_inc);
+    }
+    // ---- the carry entering this row: P^lane * (carry entering the warp) + inclusive tail of the row before ----
+    for (int u = 0; u < w; ++u) lb_matvec_inplace<CT, R>(X, p.Pwarp);
+#pragma unroll
+    for (int k = 0; k < R; ++k) Ew[k] = Ew[k] + X[k];
+    lb_lane_matvec<CT, R>(h, p.Plane, lane, Ew);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const CT prev = lb_shfl_up<CT>(T[k], 1);
+        if (lane > 0) h[k] = h[k] + prev;
+    }
+    fdiff_inv<CT, R>(h);
+
+    scan_row(h, std::true_type());                                // pass 1: from the carry, scaled, stored
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {

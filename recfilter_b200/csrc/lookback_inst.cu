@@ -74,23 +74,34 @@ static cudaError_t launch_lb_tile_T(const LBTileParams<CT, R>& p, const void* in
     }
 }
 
-template <typename CT, int R>
-static cudaError_t launch_lb_signal_T(const LBSignalParams<CT, R>& p, const void* in, void* out, cudaStream_t st)
+template <typename CT, int R, int NW>
+static cudaError_t launch_lb_signal_NW(const LBSignalParams<CT, R>& p, const void* in, void* out, cudaStream_t st)
 {
-    const int64_t nblocks = p.rows / 128;
+    constexpr int ROWS = 32 * NW;
+    const int64_t nblocks = p.rows / ROWS;
     if (nblocks <= 0) return cudaSuccess;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const size_t smem = lb_tile_smem_bytes(128);
+    const size_t smem = (size_t)ROWS * 512 + 1024 + 64;
     static bool done[RFB_MAX_DEVICES] = {};
-    cudaError_t e = lb_ensure_smem(lb_signal_kernel<CT, R>, smem, done);
+    cudaError_t e = lb_ensure_smem(lb_signal_kernel<CT, R, NW>, smem, done);
     if (e != cudaSuccess) return e;
     const bool is_float = std::is_same<CT, float>::value;
     CUtensorMap tm_in, tm_out;
-    e = make_tile_map(&tm_in, in, 128, p.rows, 128, is_float);
+    e = make_tile_map(&tm_in, in, 128, p.rows, ROWS, is_float);
     if (e != cudaSuccess) return e;
-    e = make_tile_map(&tm_out, out, 128, p.rows, 128, is_float);
+    e = make_tile_map(&tm_out, out, 128, p.rows, ROWS, is_float);
     if (e != cudaSuccess) return e;
-    return lb_launch_pdl(lb_signal_kernel<CT, R>, dim3((unsigned)nblocks), dim3(128), smem, st, p, tm_in, tm_out);
+    return lb_launch_pdl(lb_signal_kernel<CT, R, NW>, dim3((unsigned)nblocks), dim3(ROWS), smem, st, p, tm_in, tm_out);
+}
+template <typename CT, int R>
+static cudaError_t launch_lb_signal_T(const LBSignalParams<CT, R>& p, const void* in, void* out, cudaStream_t st)
+{
+    switch (p.tile_rows) {
+    case 128: return launch_lb_signal_NW<CT, R, 4>(p, in, out, st);
+    case 64:  return launch_lb_signal_NW<CT, R, 2>(p, in, out, st);
+    case 32:  return launch_lb_signal_NW<CT, R, 1>(p, in, out, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 #define RFB_CAT_(a, b) a##b

@@ -38,7 +38,7 @@ struct LBTileParams {
     CT  gain;                     // product of the feed-forward coefficients, applied at the store
     uint32_t epoch;
     int prefetch;                 // > 0: L2 prefetch of the tile `prefetch` tickets ahead
-    const uint32_t* order;        // [nbx * nbd] ticket -> scan-order tile coordinates (bxs | bds << 16), anti-diagonals
+    int rows_first;               // 1: tiles are handed out row-major instead of along anti-diagonals
     uint32_t* ticket;             // tile counter (atomicInc, wraps to 0 with the last tile)
     uint32_t* err;                // set to 1 if a CTA ran into LB_SPIN_LIMIT
     LBDim<CT, R> x, d;
@@ -48,6 +48,7 @@ struct LBTileParams {
 template <typename CT, int R>
 struct LBSignalParams {
     int64_t rows;                 // rows in total (signals x rows per signal)
+    int tile_rows;                // rows per CTA: 128, 64 or 32
     int tiles_per_signal;         // CTAs per signal
     int causal;
     int clamp;
@@ -55,7 +56,7 @@ struct LBSignalParams {
     CT  a[R + 1];
     CT  Pstep[5][R * R];          // P^(1,2,4,8,16): row transitions of the intra-warp scan (difference basis)
     CT  Pwarp[R * R];             // P^32
-    CT  Q[R * R];                 // P^TS: transition of a whole tile
+    CT  Q[R * R];                 // P^tile_rows: transition of a whole tile
     CT  Q32[R * R];               // Q^32: one look-back window
     const CT* Plane;              // [R*R][32]: P^lane
     const CT* Qpow;               // [R*R][32]: Q^k

@@ -1236,13 +1236,13 @@ struct LookbackPass : LookbackBase<CT, R> {
     LBTileParams<CT, R> lp;
     int ts = 128;
     std::vector<HostScan> sx, sd;
-    DevBuf dPpow[2], dRec[2], dOrder;
+    DevBuf dPpow[2], dRec[2];
 
     size_t workspace() const override
     {
         size_t n = this->dCtl.bytes;
         for (int i = 0; i < 2; ++i) n += dPpow[i].bytes + dRec[i].bytes;
-        return n + dOrder.bytes;
+        return n;
     }
     int init_dim(LBDim<CT, R>& dm, const std::vector<HostScan>& sc, int nb, int64_t ntiles, bool clamp, int slot, double& gain, uint32_t& gain_u)
     {
@@ -1280,23 +1280,9 @@ struct LookbackPass : LookbackBase<CT, R> {
         if ((rc = init_dim(lp.d, sd, lp.nbd, ntiles, clamp, 1, gain, gain_u))) return rc;
         lp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
         lp.ticket = (uint32_t*)this->dCtl.p; lp.err = (uint32_t*)this->dCtl.p + 1;
-        // tiles of an image are handed out along anti-diagonals of the scan-order grid: the tiles a tile waits for
-        // (before it along x, before it along d) are then a whole diagonal older (RFB_LB_ORDER=rows: row-major)
-        {
-            const bool rows_first = getenv("RFB_LB_ORDER") && !strcmp(getenv("RFB_LB_ORDER"), "rows");
-            std::vector<uint32_t> order;
-            order.reserve((size_t)lp.nbx * lp.nbd);
-            if (rows_first) {
-                for (int bd = 0; bd < lp.nbd; ++bd) for (int bx = 0; bx < lp.nbx; ++bx) order.push_back((uint32_t)bx | ((uint32_t)bd << 16));
-            } else {
-                for (int sdiag = 0; sdiag <= lp.nbx + lp.nbd - 2; ++sdiag)
-                    for (int bd = std::max(0, sdiag - (lp.nbx - 1)); bd <= std::min(lp.nbd - 1, sdiag); ++bd)
-                        order.push_back((uint32_t)(sdiag - bd) | ((uint32_t)bd << 16));
-            }
-            CUDA_TRY(dOrder.alloc(order.size() * sizeof(uint32_t)));
-            CUDA_TRY(cudaMemcpy(dOrder.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            lp.order = (const uint32_t*)dOrder.p;
-        }
+        // tiles of an image are handed out along anti-diagonals of the scan-order grid (the tiles a tile waits for are
+        // then a whole diagonal older; measured on the 8192^2 table: 134 vs 143 us); RFB_LB_ORDER=rows: row-major
+        lp.rows_first = (getenv("RFB_LB_ORDER") && !strcmp(getenv("RFB_LB_ORDER"), "rows")) ? 1 : 0;
         // optional L2 prefetch distance in tickets (RFB_LB_PREFETCH; measured: no gain, off)
         lp.prefetch = 0;
         if (const char* e = getenv("RFB_LB_PREFETCH")) lp.prefetch = atoi(e);
@@ -1332,10 +1318,20 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
     int64_t nsig = 1, M = 1;
     DevBuf dPlane, dQpow, dRec;
 
+    int tile_rows = 128;                                                      // rows of 128 samples per CTA
+    // rows per CTA: the largest of 128 / 64 / 32 that cuts a signal into whole tiles (measured on C4: 2.07 / 2.31 /
+    // 2.83 ms -- the look-back cost per tile outweighs the extra CTAs per SM; RFB_LB_ROWS overrides)
+    static int pick_tile_rows(int64_t Nx)
+    {
+        if (const char* e = getenv("RFB_LB_ROWS")) { const int v = atoi(e); if ((v == 128 || v == 64 || v == 32) && Nx % ((int64_t)v * ts) == 0) return v; }
+        for (int v : { 128, 64, 32 }) if (Nx % ((int64_t)v * ts) == 0) return v;
+        return 0;
+    }
     static bool eligible(int64_t Nx, int64_t rows)
     {
-        if (Nx % ((int64_t)ts * ts) != 0) return false;                       // whole tiles of 128 rows x 128 samples per signal
-        const int64_t tiles = (Nx / ((int64_t)ts * ts)) * rows;
+        const int tr = pick_tile_rows(Nx);
+        if (!tr) return false;                                                // whole tiles of tr rows x 128 samples per signal
+        const int64_t tiles = (Nx / ((int64_t)tr * ts)) * rows;
         return tiles > 0 && tiles <= 0x7fffffffLL && (Nx / ts) * rows <= 0x7fffffffLL;
     }
     size_t workspace() const override { return this->dCtl.bytes + dPlane.bytes + dQpow.bytes + dRec.bytes; }
@@ -1353,8 +1349,10 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
     {
         M = Nx / ts; nsig = rows;
         std::memset(&sp, 0, sizeof(sp));
+        tile_rows = pick_tile_rows(Nx);
         sp.rows = M * nsig;
-        sp.tiles_per_signal = (int)(M / ts);
+        sp.tile_rows = tile_rows;
+        sp.tiles_per_signal = (int)(M / tile_rows);
         sp.causal = scan.causal; sp.clamp = clamp ? 1 : 0;
         const std::vector<HT> c = coeff_vec<HT>(scan, R, true);
         for (int k = 0; k <= R; ++k) sp.a[k] = (CT)c[k];
@@ -1364,12 +1362,12 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
         const std::vector<HT> P = Base::tile_transition(scan, ts, clamp);     // one row of 128 samples
         for (int i = 0; i < 5; ++i) Base::to_device_consts(sp.Pstep[i], Base::mat_pow(P, 1 << i));
         Base::to_device_consts(sp.Pwarp, Base::mat_pow(P, 32));
-        const std::vector<HT> Q = Base::mat_pow(P, ts);
+        const std::vector<HT> Q = Base::mat_pow(P, tile_rows);
         Base::to_device_consts(sp.Q, Q);
         Base::to_device_consts(sp.Q32, Base::mat_pow(Q, 32));
         CUDA_TRY((upload<HT, CT>(dPlane, lane_table(Base::mat_powers(P, 32)))));
         CUDA_TRY((upload<HT, CT>(dQpow, lane_table(Base::mat_powers(Q, 32)))));
-        const int64_t ntiles = sp.rows / ts;
+        const int64_t ntiles = sp.rows / tile_rows;
         CUDA_TRY(dRec.alloc((size_t)ntiles * LB_SIGNAL_REC_CHUNKS * 16));
         CUDA_TRY(cudaMemset(dRec.p, 0, (size_t)ntiles * LB_SIGNAL_REC_CHUNKS * 16));
         sp.Plane = (const CT*)dPlane.p; sp.Qpow = (const CT*)dQpow.p;
@@ -1391,9 +1389,9 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
     {
         char b[512];
         snprintf(b, sizeof(b),
-                 "  single-pass look-back signal pass: %lld signals x %lld rows of %d samples (thread per row, 128 rows per CTA, "
+                 "  single-pass look-back signal pass: %lld signals x %lld rows of %d samples (thread per row, %d rows per CTA, "
                  "%d CTAs per signal), 1 %s scan of order<=%d, 1 launch, 8 B/sample\n",
-                 (long long)nsig, (long long)M, ts, sp.tiles_per_signal, scan.causal ? "causal" : "anticausal", R);
+                 (long long)nsig, (long long)M, ts, tile_rows, sp.tiles_per_signal, scan.causal ? "causal" : "anticausal", R);
         return b;
     }
 };
@@ -1703,8 +1701,9 @@ static int lookback_tile_size(const rf_plan* plan, const std::vector<HostScan>& 
         if (Nx % ts || Nd % ts) continue;
         const int64_t ntiles = (Nx / ts) * (Nd / ts) * No;
         if (ntiles > 0x7fffffffLL || Nx / ts > 0x7fffLL || Nd / ts > 0x7fffLL) continue;
-        // few tiles per SM: 64x64 tiles fill the machine better (3 CTAs of 128x128 per SM are resident)
-        if (!force && ts == 128 && ntiles < 8 * 3 * 148 && Nx % 64 == 0 && Nd % 64 == 0) continue;
+        // less than one generation of resident CTAs (3 of 128x128 per SM): 64x64 tiles fill the machine better
+        // (measured: 2048^2 14.4 vs 15.0 us, 4096^2 45.5 vs 44.1 us, 8192^2 142 vs 130 us)
+        if (!force && ts == 128 && ntiles < 3 * 148 && Nx % 64 == 0 && Nd % 64 == 0) continue;
         return ts;
     }
     return 0;

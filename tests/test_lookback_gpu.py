@@ -160,11 +160,17 @@ def test_two_scans_per_dimension_keep_the_two_sweep_kernels():
 @pytest.mark.parametrize("n,rows", [(16384, 3), (131072, 4), (1 << 20, 1), (1 << 18, 5)])
 @pytest.mark.parametrize("coeff", [A8, B8, G3, [1.0, 1.0]], ids=["ref8", "stable8", "gauss3", "sum"])
 @pytest.mark.parametrize("causal", [True, False])
-def test_signal_lookback_matches_oracle(oracle, n, rows, coeff, causal):
+@pytest.mark.parametrize("tile_rows", [32, 64, 128])
+def test_signal_lookback_matches_oracle(oracle, n, rows, coeff, causal, tile_rows):
     a = rand_image((rows, n), np.float32, 77) - np.float32(0.5)
     scans = [(0, causal, coeff)]
     for border in ("zero", "clamp"):
-        plan = Plan((n, rows), "f32", [Scan(*s) for s in scans], border)
+        os.environ["RFB_LB_ROWS"] = str(tile_rows)          # rows of 128 samples per CTA (1, 2 or 4 warps)
+        try:
+            plan = Plan((n, rows), "f32", [Scan(*s) for s in scans], border)
+        finally:
+            os.environ.pop("RFB_LB_ROWS", None)
+        assert f"{tile_rows} rows per CTA" in plan.describe() or "look-back signal pass" not in plan.describe()
         if len(coeff) - 1 > 4 or n // 128 > 128:          # otherwise the 2-D kernel takes it (few tiles per line)
             assert "look-back signal pass" in plan.describe(), plan.describe()
         else:
