@@ -34,7 +34,7 @@ template <typename CT, int R, int TS, bool RAGGED>
 static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void* in, void* out, int mode,
                                         cudaStream_t st)
 {
-    const int64_t nblocks = (int64_t)p.nbx * p.nbd * p.No;
+    const int64_t nblocks = (int64_t)p.nbx * p.nbd * (p.No_launch > 0 ? p.No_launch : p.No);
     if (nblocks <= 0) return cudaSuccess;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t smem = fused_tile_smem_bytes(TS, mode == FMODE_P2 ? (p.mx + p.md) * R * TS : 0);

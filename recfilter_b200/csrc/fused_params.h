@@ -24,7 +24,8 @@ struct FusedScanTab {
 template <typename CT, int R>
 struct FusedParams {
     int64_t Nx, Nd, No;
-    int64_t o0;                   // first outer index of this launch (a slice of a stack; the grid covers No_slice images)
+    int64_t o0;                   // first outer index of this launch (a slice of a stack) ...
+    int64_t No_launch;            // ... and the images its grid covers (0: all No)
     int nbx, nbd;
     int clamp;
     int x_lo_closed, x_hi_closed, d_lo_closed, d_hi_closed;

@@ -488,6 +488,14 @@ struct PassBase {
     virtual const void* ext_buffer() const = 0;
     // device word a kernel of the pass sets when it gave up waiting (look-back kernels), or null
     virtual const uint32_t* error_flag() const { return nullptr; }
+    // the whole pass on one stream; a pass may overlap its own stages internally (FusedPass: stack slices)
+    virtual int run_all(const void* in, void* out, cudaStream_t st)
+    {
+        int rc;
+        if ((rc = run_tails(in, out, st))) return rc;
+        if ((rc = run_carries(nullptr, nullptr, st))) return rc;
+        return run_final(in, out, st);
+    }
 };
 
 template <typename CT, int R>
@@ -756,7 +764,7 @@ struct FusedPass : PassBase {
     {
         int n = 1;
         if (needs_carries()) n += 1 + (d_needs() ? 1 : 0) + (cross_needed() ? 1 : 0) + (x_needs() ? 1 : 0);
-        return n;
+        return n * nslices;
     }
 
     // difference basis of the fused carry algebra (fdiff_fwd / fdiff_inv in fused.cuh)
@@ -888,8 +896,12 @@ struct FusedPass : PassBase {
             CUDA_TRY(cudaMemset(dA.p, 0, n));
         }
         fp.TX = (CT*)TX.p; fp.CX = (const CT*)CX.p; fp.TY = (CT*)TY.p; fp.CY = (const CT*)CY.p;
-        return RF_OK;
+        return init_pipeline();
     }
+
+    // ---- stack slices: images [oa, ob) of the stack; oa == ob == 0 means the whole stack ----
+    int64_t sl_a = 0, sl_b = 0;
+    void set_slice(int64_t oa, int64_t ob) { sl_a = oa; sl_b = ob; fp.o0 = oa; fp.No_launch = ob - oa; }
 
     int run_tails(const void* in, void* out, cudaStream_t st) override
     {
@@ -899,6 +911,77 @@ struct FusedPass : PassBase {
         CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P1, ts, st)));
         if (timer) timer->end(st, ev);
         return RF_OK;
+    }
+
+    /*
+     * Pipelined stack (optional, RFB_PIPE_SLICES=n; OFF by default).  The carry stage is a chain of dependent,
+     * latency-bound launches that use a fraction of the machine (19 % of a C3 step when it runs alone).  The stack is
+     * cut into slices of whole images; the tile kernels of all slices run back to back on the caller's stream, the
+     * carry stage of slice i runs on a high-priority side stream beside the tile kernels of slice i+1 (P1) / i-1 (P2):
+     *     stream : P1(0) P1(1) P2(0) P1(2) P2(1) ... P2(n-1)
+     *     side   :       C(0)        C(1)  ...   C(n-1)
+     * Measured on B200 (scripts/c3_pipe.py, 4 x 8192^2): 158.9 us per image unsliced, 170.1 with 2 slices, 188.1 with 4
+     * -- the results are bit-identical but nothing overlaps: three resident tile CTAs use the whole register file of
+     * an SM (3 x 128 x 168), so a chain block (256 threads x 88 registers, 58-70 KB) only fits once the tile kernel
+     * drains, and every extra kernel boundary costs a ramp.  Kept for the record and for smaller tile kernels.
+     */
+    int nslices = 1;
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> ev_tails, ev_carries;
+    ~FusedPass()
+    {
+        for (cudaEvent_t e : ev_tails) cudaEventDestroy(e);
+        for (cudaEvent_t e : ev_carries) cudaEventDestroy(e);
+        if (side) cudaStreamDestroy(side);
+    }
+    int init_pipeline()
+    {
+        nslices = 1;
+        if (fp.No < 2 || !needs_carries() || d_open()) return RF_OK;
+        const int64_t tiles_per_image = (int64_t)gx.nb * gd.nb;
+        int want = 1;
+        if (const char* e = getenv("RFB_PIPE_SLICES")) want = atoi(e);
+        if (want < 2) return RF_OK;
+        // slice boundaries must fall on chain blocks (32 lines) and cross-residual blocks (4 tiles)
+        if ((fp.Nx % 32) || (fp.Nd % 32) || (tiles_per_image % 4)) return RF_OK;
+        nslices = (int)std::min<int64_t>(want, fp.No);
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));        // hi = greatest priority (numerically lowest)
+        CUDA_TRY(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+        ev_tails.resize(nslices); ev_carries.resize(nslices);
+        for (int i = 0; i < nslices; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_tails[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_carries[i], cudaEventDisableTiming));
+        }
+        return RF_OK;
+    }
+    int run_all(const void* in, void* out, cudaStream_t st) override
+    {
+        if (nslices < 2) return PassBase::run_all(in, out, st);
+        auto bounds = [&](int i, int64_t& a, int64_t& b) { a = fp.No * i / nslices; b = fp.No * (i + 1) / nslices; };
+        int rc = RF_OK;
+        int64_t a, b;
+        auto tails = [&](int i) -> int {
+            bounds(i, a, b); set_slice(a, b);
+            int r = run_tails(in, out, st);
+            if (r) return r;
+            CUDA_TRY(cudaEventRecord(ev_tails[i], st));
+            return RF_OK;
+        };
+        if ((rc = tails(0))) { set_slice(0, 0); return rc; }
+        for (int i = 0; i < nslices && !rc; ++i) {
+            if (i + 1 < nslices) rc = tails(i + 1);
+            if (rc) break;
+            bounds(i, a, b); set_slice(a, b);
+            cudaError_t e = cudaStreamWaitEvent(side, ev_tails[i], 0);
+            if (e == cudaSuccess) { rc = run_carries(nullptr, nullptr, side, 0); if (rc) break; }
+            if (e == cudaSuccess) e = cudaEventRecord(ev_carries[i], side);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev_carries[i], 0);
+            if (e != cudaSuccess) { rc = fail(RF_ECUDA, "pipelined stack: %s", cudaGetErrorString(e)); break; }
+            rc = run_final(in, out, st);
+        }
+        set_slice(0, 0);
+        return rc;
     }
 
     int run_chain(bool xdim, const void* ext_d, void* tail_out_d, cudaStream_t st, bool tails_only = false)
@@ -920,6 +1003,10 @@ struct FusedPass : PassBase {
         cp.ext = xdim ? nullptr : (const CT*)ext_d;
         cp.tail_out = xdim ? nullptr : (CT*)tail_out_d;
         cp.sJ = cp.nl; cp.sL = 1;
+        if (sl_b > sl_a) {                           // a slice of the stack: its lines only
+            const int64_t per_image = xdim ? fp.Nd : fp.Nx;
+            cp.l0 = sl_a * per_image; cp.l1 = sl_b * per_image;
+        }
         cp.no_store = tails_only ? 1 : 0;            // stage 1 of a sharded run wants the outgoing tails only
         if (xdim && cross_needed()) {
             cp.A = (const CT*)dA.p; cp.G = (const TT*)dG.p;
@@ -943,6 +1030,7 @@ struct FusedPass : PassBase {
             cr.Nx = fp.Nx; cr.Nd = fp.Nd; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md;
             cr.sdk = sdk();
             cr.nly = fp.nly; cr.nlx = fp.nlx;
+            if (sl_b > sl_a) { cr.w0 = sl_a * (int64_t)gx.nb * gd.nb; cr.w1 = sl_b * (int64_t)gx.nb * gd.nb; }
             cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
             CUDA_TRY((FLaunch<CT, R>::cross(cr, ts, st)));
             if (timer) timer->end(st, ev);
@@ -978,9 +1066,9 @@ struct FusedPass : PassBase {
         char b[512];
         snprintf(b, sizeof(b),
                  "  fused pass view [%lld][%lld][%lld]: %dx%d register tiles, d scans %d (%d tiles) then x scans %d "
-                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), launches %d\n",
+                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), launches %d%s\n",
                  (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
-                 launches());
+                 launches(), nslices > 1 ? (" (stack pipelined in " + std::to_string(nslices) + " slices: carry stages on a side stream)").c_str() : "");
         return b;
     }
 };
@@ -2031,9 +2119,7 @@ int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stre
         src = plan->stage.p; dst = plan->stage.p;
     }
     for (auto& p : plan->passes) {
-        if ((rc = p->run_tails(src, dst, st))) return rc;
-        if ((rc = p->run_carries(nullptr, nullptr, st))) return rc;
-        if ((rc = p->run_final(src, dst, st))) return rc;
+        if ((rc = p->run_all(src, dst, st))) return rc;
         src = dst;
     }
     if (plan->stage.p) return narrow_out(plan, out_dev, st);
