@@ -214,6 +214,29 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev,
                    const void* gathered_tails_dev, int nshards, int shard_rank, void* stream);
 
 /*
+ * Exchange windows for the strip tails (peer to peer over NVLink; no collective library, no host in the data
+ * path).  Every rank owns a window of two generations of [nranks][bytes_per_rank] in its device memory.
+ *   rf_xchg_put   copies this rank's tails into its slot of EVERY rank's window and then raises its arrival word
+ *                 there (stream ordered, asynchronous);
+ *   rf_xchg_wait  makes `stream` wait until all nranks slots of the current step have arrived and returns the
+ *                 gathered [nranks][bytes_per_rank] array (what rf_plan_stage2 takes).
+ * One process per GPU: pass the 64-byte rf_xchg_ipc_handle of every rank to rf_xchg_open_peer of every other
+ * rank once (any host channel).  One process, several GPUs: rf_xchg_set_peer.  The wait gives up after a bounded
+ * number of polls instead of hanging the device (rf_xchg_check reports it).
+ */
+typedef struct rf_xchg rf_xchg;
+int    rf_xchg_create(size_t bytes_per_rank, int nranks, int rank, rf_xchg** out);   /* on the current device */
+void   rf_xchg_destroy(rf_xchg* x);
+size_t rf_xchg_handle_bytes(void);
+int    rf_xchg_ipc_handle(rf_xchg* x, void* handle);
+int    rf_xchg_open_peer(rf_xchg* x, int peer, const void* handle);
+int    rf_xchg_set_peer(rf_xchg* x, int peer, rf_xchg* peer_window);
+int    rf_xchg_put(rf_xchg* x, const void* src_dev, size_t bytes, void* stream);
+int    rf_xchg_wait(rf_xchg* x, void* stream, void** gathered_dev);
+int    rf_xchg_check(rf_xchg* x);
+const char* rf_xchg_last_error(void);
+
+/*
  * Device-side stopwatch for a sequence of asynchronous calls on one stream (CUDA events):
  * what RecFilter::profile needs to time a chain of plans (lib/recfilter.cpp:998-1011, which uses
  * an unsynchronised wall clock).  rf_clock_end waits for the work, returns the elapsed

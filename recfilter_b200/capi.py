@@ -106,6 +106,17 @@ def lib():
     L.rf_plan_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), i32]
     L.rf_clock_begin.argtypes = [vp, C.POINTER(vp)]
     L.rf_clock_end.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.rf_xchg_create.argtypes = [sz, i32, i32, C.POINTER(vp)]
+    L.rf_xchg_destroy.argtypes = [vp]
+    L.rf_xchg_destroy.restype = None
+    L.rf_xchg_handle_bytes.restype = sz
+    L.rf_xchg_ipc_handle.argtypes = [vp, vp]
+    L.rf_xchg_open_peer.argtypes = [vp, i32, vp]
+    L.rf_xchg_set_peer.argtypes = [vp, i32, vp]
+    L.rf_xchg_put.argtypes = [vp, vp, sz, vp]
+    L.rf_xchg_wait.argtypes = [vp, vp, C.POINTER(vp)]
+    L.rf_xchg_check.argtypes = [vp]
+    L.rf_xchg_last_error.restype = C.c_char_p
     L.rf_malloc.argtypes = [C.POINTER(vp), sz]
     L.rf_free.argtypes = [vp]
     L.rf_memcpy_h2d.argtypes = [vp, vp, sz]
@@ -330,11 +341,75 @@ class Plan:
                                         C.c_void_p(ext.data_ptr()), C.c_void_p(st)), "rf_plan_stage2_ext")
 
     def stage2(self, src, dst, gathered, nshards: int, rank: int, stream=None):
+        """gathered: a tensor, or the device pointer of the gathered tails (Exchange.wait)."""
         import torch
         st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        gp = gathered if isinstance(gathered, int) else gathered.data_ptr()
         _check(lib().rf_plan_stage2(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
-                                    C.c_void_p(gathered.data_ptr()), int(nshards), int(rank), C.c_void_p(st)),
+                                    C.c_void_p(gp), int(nshards), int(rank), C.c_void_p(st)),
                "rf_plan_stage2")
+
+
+class Exchange:
+    """Peer-to-peer exchange window for strip tails (rf_xchg_*): one per rank, on the current CUDA device."""
+
+    def __init__(self, bytes_per_rank: int, nranks: int, rank: int):
+        self._h = C.c_void_p()
+        self.nranks, self.rank = nranks, rank
+        self._xcheck(lib().rf_xchg_create(int(bytes_per_rank), int(nranks), int(rank), C.byref(self._h)), "rf_xchg_create")
+
+    @staticmethod
+    def _xcheck(rc, what):
+        if rc != 0:
+            raise RecFilterError(f"{what} failed ({rc}): {lib().rf_xchg_last_error().decode()}")
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(int(lib().rf_xchg_handle_bytes()))
+        self._xcheck(lib().rf_xchg_ipc_handle(self._h, buf), "rf_xchg_ipc_handle")
+        return buf.raw
+
+    def open_peer(self, peer: int, handle: bytes):
+        self._xcheck(lib().rf_xchg_open_peer(self._h, int(peer), C.create_string_buffer(handle, len(handle))), "rf_xchg_open_peer")
+
+    def set_peer(self, peer: int, other: "Exchange"):
+        self._xcheck(lib().rf_xchg_set_peer(self._h, int(peer), other._h), "rf_xchg_set_peer")
+
+    def connect(self, group=None):
+        """One process per GPU: pass the IPC handles around once (torch.distributed object all-gather)."""
+        import torch.distributed as dist
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, self.ipc_handle(), group=group)
+        for p, h in enumerate(handles):
+            if p != self.rank:
+                self.open_peer(p, h)
+        dist.barrier(group=group)
+
+    def put(self, tails, stream=None):
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        self._xcheck(lib().rf_xchg_put(self._h, C.c_void_p(tails.data_ptr()), tails.numel() * tails.element_size(), C.c_void_p(st)),
+                     "rf_xchg_put")
+
+    def wait(self, stream=None) -> int:
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        out = C.c_void_p()
+        self._xcheck(lib().rf_xchg_wait(self._h, C.c_void_p(st), C.byref(out)), "rf_xchg_wait")
+        return int(out.value)
+
+    def check(self):
+        self._xcheck(lib().rf_xchg_check(self._h), "rf_xchg_check")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().rf_xchg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _Tap(C.Structure):

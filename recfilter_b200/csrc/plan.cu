@@ -384,6 +384,92 @@ struct StageTimer {
     void reset() { collect(); for (int i = 0; i < ST_COUNT; ++i) { ms[i] = 0; count[i] = 0; } }
 };
 
+// ---------------------------------------------------------------------------------------------
+// strip sharding without re-running the carry chain.  Stage 1 chains a strip with ZERO carries entering its
+// open faces and keeps those carries C0.  The carries are linear in what enters the strip:
+//     C_s[j] = C0_s[j] + sum_{q <= s} W[s][q][j] * ext_q          (j: tile of the strip, R x R blocks)
+// W is simulated once at plan creation (unit histories entering the strip, fp64, conjugated to the difference
+// basis of the fused carry algebra); after the exchange one elementwise kernel adds the second term.
+// ---------------------------------------------------------------------------------------------
+template <typename HT>
+static void build_strip_response(std::vector<HT>& W, const std::vector<HostScan>& scans, int64_t n, int ts, int nb,
+                                 int lo_closed, int hi_closed, int R, bool clamp, bool scaled)
+{
+    const int S = (int)scans.size();
+    W.assign((size_t)S * S * nb * R * R, (HT)0);
+    std::vector<std::vector<HT>> coef(S);
+    for (int s = 0; s < S; ++s) coef[s] = coeff_vec<HT>(scans[s], R, scaled);
+    const int len = (int)n;
+    auto closed = [&](int s) { return scans[s].causal ? lo_closed : hi_closed; };
+    // history entering tile j of scan s, read off the array after scan s (k = 0 newest)
+    auto entering = [&](const std::vector<HT>& v, int s, int j, int k) -> HT {
+        if (scans[s].causal) { const int i = j * ts - 1 - k; return i >= 0 ? v[i] : (HT)0; }
+        const int i = (j + 1) * ts + k; return i < len ? v[i] : (HT)0;
+    };
+    for (int q = 0; q < S; ++q) {
+        if (closed(q)) continue;                     // nothing enters the strip for this scan
+        for (int kk = 0; kk < R; ++kk) {
+            std::vector<HT> v(len, (HT)0), h(R, (HT)0);
+            h[kk] = (HT)1;
+            sim_scan<HT>(v, len, h, coef[q], scans[q].causal != 0, false, scaled);
+            for (int j = 0; j < nb; ++j) {
+                const bool entry = scans[q].causal ? (j == 0) : (j == nb - 1);
+                for (int k = 0; k < R; ++k)
+                    W[((((size_t)q * S + q) * nb + j) * R + k) * R + kk] = entry ? (HT)(k == kk ? 1 : 0) : entering(v, q, j, k);
+            }
+            for (int s = q + 1; s < S; ++s) {
+                std::vector<HT> hs(R, (HT)0);
+                sim_scan<HT>(v, len, hs, coef[s], scans[s].causal != 0, clamp && closed(s), scaled);
+                for (int j = 0; j < nb; ++j)
+                    for (int k = 0; k < R; ++k)
+                        W[((((size_t)s * S + q) * nb + j) * R + k) * R + kk] = entering(v, s, j, k);
+            }
+        }
+    }
+}
+
+// CY[s][k][j][l] += D^-1 ( sum_{q <= s} W'[s][q][j] * D ext_q[.][l] ),  one thread per line
+template <typename CT, int R>
+__global__ void carry_fix_kernel(CT* __restrict__ CY, const CT* __restrict__ ext, const CT* __restrict__ Wd, int S, int nb, int64_t nl)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nl) return;
+    CT e[FMAX_SCANS][R];
+    for (int q = 0; q < S; ++q) {
+        CT h[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) h[k] = ext[((int64_t)q * R + k) * nl + l];
+#pragma unroll
+        for (int m = 1; m < R; ++m)
+#pragma unroll
+            for (int k = R - 1; k >= m; --k) h[k] = h[k - 1] - h[k];               // difference basis
+#pragma unroll
+        for (int k = 0; k < R; ++k) e[q][k] = h[k];
+    }
+    for (int s = 0; s < S; ++s)
+        for (int j = 0; j < nb; ++j) {
+            CT dc[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) dc[k] = (CT)0;
+            for (int q = 0; q <= s; ++q) {
+                const CT* w = Wd + (((size_t)s * S + q) * nb + j) * R * R;
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+#pragma unroll
+                    for (int kk = 0; kk < R; ++kk) dc[k] = dc[k] + w[k * R + kk] * e[q][kk];
+            }
+#pragma unroll
+            for (int m = R - 1; m >= 1; --m)
+#pragma unroll
+                for (int k = m; k < R; ++k) dc[k] = dc[k - 1] - dc[k];             // back to histories
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                CT* c = CY + (((int64_t)s * R + k) * nb + j) * nl + l;
+                *c = *c + dc[k];
+            }
+        }
+}
+
 // small kernel: strip-level carry resolution (host of the multi-GPU layer)
 template <typename CT, int R>
 __global__ void shard_resolve_kernel(const CT* __restrict__ tails, CT* __restrict__ ext, int64_t nl, int S,
@@ -743,7 +829,7 @@ struct FusedPass : PassBase {
     int Lx = FCHAIN_L, Ld = FCHAIN_L;            // tiles per chain thread
     DevBuf TX, CX, TY, CY, dA;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
-    DevBuf dExt, dTailOut;
+    DevBuf dExt, dTailOut, dW;              // dW: response of the strip's carries to what enters it (build_strip_response)
     DimTables<HT> tx_tab, td_tab;
     std::unique_ptr<ShardResolver<CT, R>> resolver;
     int sdk() const { return ((fp.md * R + 3) / 4) * 4; }     // entries of one A row, padded for 128-bit loads
@@ -758,7 +844,7 @@ struct FusedPass : PassBase {
     size_t workspace() const override
     {
         return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dA.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
-               dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes;
+               dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes + dW.bytes;
     }
     int launches() const override
     {
@@ -888,6 +974,10 @@ struct FusedPass : PassBase {
                 resolver.reset(new ShardResolver<CT, R>());
                 int rc = resolver->init(sd, gd.n, clamp, true);
                 if (rc) return rc;
+                std::vector<HT> Wv;
+                build_strip_response<HT>(Wv, sd, gd.n, ts, gd.nb, gd.lo_closed, gd.hi_closed, R, clamp, true);
+                conjugate_blocks(Wv);
+                CUDA_TRY((upload<HT, TT>(dW, Wv)));
             }
         }
         if (cross_needed()) {
@@ -1021,8 +1111,22 @@ struct FusedPass : PassBase {
     int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st, int stage) override
     {
         if (!needs_carries()) return RF_OK;
-        if (d_needs()) { int rc = run_chain(false, ext_d, tail_out_d, st, stage == 1); if (rc) return rc; }
-        if (stage == 1) return RF_OK;                // stage 1 of a sharded run: only the outgoing tails are needed
+        // strip sharding: stage 1 chains the strip with zero carries entering it, keeps those carries and emits the
+        // outgoing tails; stage 2 does NOT chain again -- the carries are corrected by W * ext (carry_fix_kernel)
+        static const bool rechain = getenv("RFB_SHARD_RECHAIN") && atoi(getenv("RFB_SHARD_RECHAIN")) != 0;   // old scheme, for comparison
+        if (stage == 2 && !rechain && d_needs() && dW.p) {
+            if (ext_d) {
+                cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
+                carry_fix_kernel<CT, R><<<(unsigned)((fp.nly + 127) / 128), 128, 0, st>>>((CT*)CY.p, (const CT*)ext_d, (const CT*)dW.p,
+                                                                                      fp.md, gd.nb, fp.nly);
+                CUDA_TRY(cudaGetLastError());
+                if (timer) timer->end(st, ev);
+            }
+        } else if (d_needs()) {
+            int rc = run_chain(false, ext_d, tail_out_d, st, stage == 1 && rechain);
+            if (rc) return rc;
+        }
+        if (stage == 1) return RF_OK;                // stage 1 of a sharded run: the exchange comes next
         if (cross_needed()) {
             FCrossParams<CT, R> cr;
             std::memset(&cr, 0, sizeof(cr));

@@ -7,10 +7,13 @@ dimensions are strip local.  For the scans along the cut dimension every rank
   stage 1   filters its strip with zero incoming carries (rf_plan_stage1) and obtains, per line
             crossing the cut, the order-r tail of every scan: `shard_tail_bytes` bytes
             (2 scans x r=3 x 8192 columns x 4 B = 196 KB for the headline Gaussian);
-  exchange  ONE all-gather of those tails (NCCL over NVLink; gloo in the CPU tests);
+  exchange  the tails of every strip reach every rank: by default peer to peer over NVLink, straight from
+            device memory into the other ranks' exchange windows (rf_xchg_put / rf_xchg_wait: CUDA IPC
+            mappings, no collective library and no host in the data path); alternatively ONE NCCL
+            all-gather, or two column-chunked all-to-alls (gloo in the CPU tests);
   stage 2   resolves the carries entering its strip from the gathered tails with the whole-strip
-            transition matrices (a tiny kernel, redundantly on every rank) and finishes the filter
-            (rf_plan_stage2).
+            transition matrices (a tiny kernel, redundantly on every rank), corrects the stage-1 carries of
+            the strip with them (no second carry chain) and finishes the filter (rf_plan_stage2).
 
 No image data crosses the link.  Batches of independent images need no exchange at all.
 """
@@ -21,7 +24,7 @@ from typing import Sequence
 import torch
 import torch.distributed as dist
 
-from .capi import Plan, Scan
+from .capi import Exchange, Plan, Scan
 
 
 def exchange_tails(my_tails: torch.Tensor, world: int, group=None) -> torch.Tensor:
@@ -83,10 +86,11 @@ class ShardedFilter:
         overlap=g > 1 (stacked only): the stack is split into g sub-stacks, each with its own plan (carry
         workspace) and CUDA stream, so the latency-bound carry stage of one sub-stack runs beside the
         bandwidth-bound tile kernels of another.
-        exchange: "allgather" (every rank receives the tails of all shards and resolves its own carries),
+        exchange: "p2p" (every rank writes its tails straight into every other rank's exchange window over
+        NVLink -- rf_xchg_put / rf_xchg_wait, no NCCL call per step), "allgather" (one NCCL all-gather),
         "alltoall" (column-chunked: every rank resolves 1/world of the lines for all shards; 2 small all-to-alls
-        instead of one all-gather whose volume grows with world) or "auto" (alltoall from 4 ranks on when the
-        all-gather would deliver 8 MB or more per rank)."""
+        instead of one all-gather whose volume grows with world) or "auto" (p2p on CUDA devices; the collectives
+        otherwise)."""
         self.rank, self.world, self.group, self.batch = rank, world, group, batch
         self.stacked = stacked and batch > 1
         self.groups = overlap if (self.stacked and overlap > 1 and batch % overlap == 0) else 1
@@ -116,11 +120,23 @@ class ShardedFilter:
         # measured on 4 and 8 B200s (profiles/): the two all-to-alls win once the all-gather would deliver >= ~8 MB
         # per rank; below that its single collective is faster
         big = self.tail_elems * 4 * world >= (8 << 20)
-        self.chunked = chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4 and big))
+        self.p2p = world > 1 and exchange in ("p2p", "auto") and torch.cuda.is_available()
+        self.chunked = (not self.p2p) and chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4 and big))
+        self.windows = []
+        if self.p2p:
+            # one exchange window per plan in flight; CUDA IPC handles travel once, here
+            for _ in self.plans:
+                x = Exchange(self.tail_elems * 4, world, rank)
+                x.connect(group)
+                self.windows.append(x)
 
     def _finish(self, plan, src, dst, tails):
         """Exchange the strip tails and finish the filter (stage 2) for one plan."""
-        if self.chunked:
+        if self.p2p:
+            x = self.windows[self.plans.index(plan)]
+            x.put(tails)
+            plan.stage2(src, dst, x.wait(), self.world, self.rank)
+        elif self.chunked:
             recv = scatter_tail_chunks(tails, self.vectors, self.world, self.group)
             ext_all = torch.empty_like(recv)
             plan.shard_resolve_lines(recv, self.world, recv.shape[2], ext_all)
@@ -175,15 +191,27 @@ class ShardedFilter:
             self._tails = torch.empty((self.batch, self.tail_elems), device=srcs[0].device, dtype=dt)
         for i, (s, d) in enumerate(zip(srcs, dsts)):
             self.plans[i].stage1(s, d, self._tails[i])
+        if self.p2p:
+            for i, (s, d) in enumerate(zip(srcs, dsts)):
+                self._finish(self.plans[i], s, d, self._tails[i])
+            return
         gathered = exchange_tails(self._tails, self.world, self.group)
         for i, (s, d) in enumerate(zip(srcs, dsts)):
             self.plans[i].stage2(s, d, gathered[i], self.world, self.rank)
 
     @property
     def launches_per_image(self) -> int:
-        n = self.plans[0].num_launches + (2 if self.world > 1 else 0)     # strip resolve + the d chain runs twice
+        # strip resolve + carry correction; p2p: + the two one-warp arrival kernels
+        n = self.plans[0].num_launches + ((2 + (2 if self.p2p else 0)) if self.world > 1 else 0)
         return n * self.groups / self.batch if self.stacked else n
 
     def close(self):
+        if self.windows:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)       # nobody unmaps a window a peer may still write to
+            for x in self.windows:
+                x.close()
+            self.windows = []
         for p in self.plans:
             p.close()
