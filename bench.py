@@ -127,6 +127,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU path (oracle): the reference-arm and the cpu_baseline leg
 # ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Host cores this process may use.  Passed to the oracle explicitly (an OpenMP num_threads clause): torchrun
+    exports OMP_NUM_THREADS=1, which must not shrink the CPU arm."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_rate(rows: int, reps: int, threads: int):
     """Gsamples/s of the serial recurrence loops on a `rows` x 8192 strip of the workload."""
     from oracle import oracle
@@ -149,7 +158,7 @@ def run_reference(args, rank: int):
         return
     from oracle import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     rng = np.random.default_rng(2)
     rows = H
     img = rng.random((rows, W), dtype=np.float32)
@@ -171,8 +180,10 @@ def run_reference(args, rank: int):
                    "tile": "128x128 register tiles (fused engine)", "streams": "1",
                    "sample": "bounded CPU sample: one 8192x8192 image per step"},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
                          "sample": "one full 8192x8192 image per step, oracle/oracle.c serial recurrence loops, "
-                                   "OpenMP over independent lines (Halide x86 JIT of the reference cannot be built here)"},
+                                   f"OpenMP over independent lines with an explicit num_threads({threads}) "
+                                   "(Halide x86 JIT of the reference cannot be built here)"},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,6 +203,90 @@ def ncu_traffic_per_launch():
         return None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs (C1, C2, C4, C5) beside the headline one: device time, inputs resident
+# ------------------------------------------------------------------------------------------------
+W2 = [[1.0, 0.5, 0.25], [1.0, 0.5, 0.125], [1.0, 0.5, 0.0625], [1.0, 0.5, 0.125], [1.0, 0.5, 0.25], [1.0, 0.5, 0.0625]]   # tests/test_generic_xyz.cpp:24-30
+A8 = [1.0] + [0.01] * 8                                                                                                  # apps/audio/audio_filter_high_order.cpp:41-42
+
+
+def _time_calls(fn, iters, barrier, dist, world):
+    import torch
+    for _ in range(3):
+        fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / iters], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def other_configs(N, rank, barrier, peak, exchange):
+    """C1 / C2 (one GPU: replicas only), C4 (channels split over the ranks, no collective), C5 (z slabs,
+    one tail exchange): Gsamples/s over all ranks, fraction of N x the HBM peak by the 8 B/sample measure."""
+    import torch
+    import torch.distributed as dist
+    from recfilter_b200 import Plan, Scan
+    from recfilter_b200.sharded import ShardedFilter
+    out = {}
+
+    def entry(name, samples, ms, gpus, how, launches):
+        out[name] = {"value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "us": ms * 1e3, "n_gpus": gpus,
+                     "hbm_frac_of_peak": 8.0 * samples / (ms * 1e-3) / 1e9 / (peak * gpus), "launches_per_call": launches, "how": how}
+
+    sat = [Scan(0, True, [1, 1]), Scan(1, True, [1, 1])]
+    if N == 1:
+        for name, ext, dt, tdt in (("C1 summed-area table 2048^2 u32", (2048, 2048), "u32", torch.int32),
+                                   ("C2 box-filter integral image 4096^2 f32", (4096, 4096), "f32", torch.float32)):
+            plan = Plan(ext, dt, sat)
+            n = ext[0] * ext[1]
+            # several distinct inputs in turn, together larger than L2 (C1 / C2 alone would sit in the 126 MB L2)
+            reps = max(2, int(300e6 // (4 * n)) + 1)
+            src = [(torch.rand(n, device="cuda") if dt == "f32" else torch.randint(0, 256, (n,), device="cuda", dtype=tdt)) for _ in range(reps)]
+            dst = [torch.empty_like(x) for x in src]
+            state = {"i": 0}
+
+            def call():
+                i = state["i"] = (state["i"] + 1) % reps
+                plan.execute(src[i], dst[i])
+            ms = _time_calls(call, 40, barrier, dist, 1)
+            plan.check()
+            entry(name, n, ms, 1, plan.describe().splitlines()[1].strip()[:120] + f" ({reps} inputs in turn, > L2)", plan.num_launches)
+            plan.close()
+            del src, dst
+    # C4: 64 channels x 2^24 samples, order 8, channels split over the ranks (no collective)
+    ch = 64 // N
+    plan = Plan((1 << 24, ch), "f32", [Scan(0, True, A8)])
+    src = torch.rand((ch, 1 << 24), device="cuda") * 2 - 1
+    dst = torch.empty_like(src)
+    ms = _time_calls(lambda: plan.execute(src, dst), 5, barrier, dist, N)
+    plan.check()
+    entry("C4 audio 64 ch x 2^24 r=8", 64 * (1 << 24), ms, N,
+          (f"{ch} channels per GPU, no collective; " if N > 1 else "") + plan.describe().splitlines()[1].strip()[:140], plan.num_launches)
+    plan.close()
+    del src, dst
+    # C5: 512^3, six order-2 scans, z slabs over the ranks
+    sc5 = [Scan(0, True, W2[0]), Scan(0, False, W2[1]), Scan(1, True, W2[2]), Scan(1, False, W2[3]), Scan(2, True, W2[4]), Scan(2, False, W2[5])]
+    flt = ShardedFilter((512, 512, 512), "f32", sc5, "zero", rank=rank, world=N, shard_dim=2, batch=1, exchange=exchange)
+    z = flt.local_extents[2]
+    src = torch.rand((z, 512, 512), device="cuda")
+    dst = torch.empty_like(src)
+    ms = _time_calls(lambda: flt.run([src], [dst]), 10, barrier, dist, N)
+    entry("C5 volume 512^3 r=2 xyz", 512 ** 3, ms, N,
+          (f"z slabs of {z} planes per GPU, order-2 plane tails exchanged once per call ({'p2p windows' if flt.p2p else 'NCCL'}); " if N > 1 else "") +
+          " | ".join(l.strip()[:60] for l in flt.plans[0].describe().splitlines()[1:]), flt.plans[0].num_launches)
+    flt.close()
+    del src, dst
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,11 +295,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C2 / C4 / C5 figures")
     ap.add_argument("--overlap", type=int, default=1,
                     help="sub-stacks of a step that run on their own CUDA streams (carry stage of one beside the tile "
                          "kernels of another); 1 = one stream")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "alltoall"],
-                    help="N > 1: how the strip tails travel (auto: column-chunked all-to-all from 4 ranks on)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "allgather", "alltoall"],
+                    help="N > 1: how the strip tails travel (auto = p2p: peer-to-peer exchange windows over NVLink; "
+                         "allgather / alltoall: NCCL collectives)")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="1 (default): a step is captured once in a CUDA graph and replayed (a sharded step is a dozen short "
+                         "launches: from 4 ranks on the host cannot issue them as fast as the GPUs finish them); 0: eager launches")
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: keep --batch images per step (strong scaling) instead of --batch x N (weak scaling)")
     args = ap.parse_args()
@@ -244,7 +344,7 @@ def main():
     # outermost dimension carries no scans (the reference allows that: lib/split.cpp:1888-1898): one launch
     # sequence -- and, sharded, one tail exchange -- per step
     flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=B, stacked=B > 1,
-                        overlap=args.overlap, exchange=args.exchange)
+                        overlap=args.overlap, exchange=args.exchange, graph=bool(args.graph))
     rows = flt.local_extents[1]
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     src_stack = torch.rand((B, rows, W), device="cuda", dtype=torch.float32, generator=gen)
@@ -291,6 +391,7 @@ def main():
     ksteps = max(2, min(args.steps, 5))
     for p in flt.plans:
         p.stage_timing(True)
+    use_graph, flt.use_graph = flt.use_graph, False          # per-kernel events need eager launches
     for _ in range(ksteps):
         step()
     torch.cuda.synchronize()
@@ -300,6 +401,7 @@ def main():
             s = stage.setdefault(k, {"ms": 0.0, "launches": 0})
             s["ms"] += v["ms"]; s["launches"] += v["launches"]
         p.stage_timing(False)
+    flt.use_graph = use_graph
     peak, peak_src = measured_peaks()
     fin = stage["tile_final"]
     k_ms = fin["ms"] / max(fin["launches"], 1)
@@ -318,7 +420,8 @@ def main():
                 "stage_us_per_image": {k: v["ms"] * 1e3 / (ksteps * B) for k, v in stage.items() if v["launches"]},
                 "images_per_launch": imgs_per_launch,
                 "kernel_timing": f"CUDA events around every launch on the plan's stream, {ksteps} steps after the timed region",
-                "whole_filter_frac_of_peak": (8.0 * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / peak}
+                # whole filter, all launches: algorithmic bytes of the step / step time, per GPU, over one GPU's peak
+                "whole_filter_frac_of_peak": (8.0 * samples_per_step * args.steps / (ms * 1e-3) / 1e9) / (peak * N)}
 
     # ---- end to end: pinned host buffers, H2D + filter + D2H inside the timed region ----------------------
     e2e_steps = max(2, min(args.steps, 5))
@@ -332,18 +435,46 @@ def main():
         from recfilter_b200 import Plan as _Plan
         img_plan = _Plan((W, H), "f32", scans, "clamp")          # per-image plan: frames stream through realize()
 
+    # N > 1: the step's strips stream through the GPU in G groups: H2D of group g+1 and D2H of group g-1 run beside the
+    # kernels and the tail exchange of group g (three streams, a ring of three device buffers per rank)
+    G = 4 if (N > 1 and B % 4 == 0) else 1
+    if N > 1:
+        gb = B // G
+        gflt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=gb, stacked=gb > 1,
+                             exchange=args.exchange)
+        ring = [torch.empty((gb, rows, W), device="cuda", dtype=torch.float32) for _ in range(3)]
+        s_up, s_run, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        ev_up = [torch.cuda.Event() for _ in range(3)]
+        ev_run = [torch.cuda.Event() for _ in range(3)]
+        ev_down = [torch.cuda.Event() for _ in range(3)]
+
     def e2e_step():
         if N == 1:
-            # rf_plan_execute_host_batch: the realize() path for a batch of frames, copies pipelined with the kernels
+            # rf_plan_execute_host_batch: a batch of frames through the host-buffer entry point of the C ABI, copies
+            # pipelined with the kernels (three device buffers)
             img_plan.realize_batch_ptr([h.data_ptr() for h in host_in], [h.data_ptr() for h in host_out])
-        else:
-            for i in range(B):
-                srcs[i].copy_(host_in[i], non_blocking=True)
-            step()
-            for i in range(B):
-                host_out[i].copy_(dsts[i], non_blocking=True)
-            torch.cuda.synchronize()
-
+            return
+        for g in range(G):
+            b = g % 3
+            with torch.cuda.stream(s_up):
+                if g >= 3:
+                    s_up.wait_event(ev_down[b])                          # ring buffer b is free again
+                for i in range(gb):
+                    ring[b][i].copy_(host_in[g * gb + i], non_blocking=True)
+                ev_up[b].record(s_up)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_up[b])
+                if gflt.stacked:
+                    gflt.run_stacked(ring[b], ring[b])
+                else:
+                    gflt.run([ring[b][0]], [ring[b][0]])
+                ev_run[b].record(s_run)
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_run[b])
+                for i in range(gb):
+                    host_out[g * gb + i].copy_(ring[b][i], non_blocking=True)
+                ev_down[b].record(s_down)
+        s_down.synchronize()
 
     e2e_step()
     barrier()
@@ -359,15 +490,19 @@ def main():
     e2e_value = e2e_steps * samples_per_step / dt / 1e9
     e2e = {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 4 * samples_per_step,
            "d2h_bytes_per_step": 4 * samples_per_step, "steps": e2e_steps,
-           "api": "rf_plan_execute_host_batch (RecFilter::realize path, one call per step of %d images; H2D / kernels / D2H "
-                  "pipelined over 3 device buffers), pinned host buffers" % B if N == 1 else
-                  "pinned H2D + rf_plan_stage1 / all_gather / rf_plan_stage2 + D2H"}
+           "api": ("rf_plan_execute_host_batch (host-buffer entry point of the C ABI, one call per step of %d images; H2D / "
+                   "kernels / D2H pipelined over 3 device buffers), pinned host buffers" % B) if N == 1 else
+                  ("per rank: pinned H2D / rf_plan_stage1 + tail exchange + rf_plan_stage2 / D2H of %d groups of %d strips "
+                   "pipelined on three streams over a ring of 3 device buffers" % (G, B // G))}
+    if N > 1:
+        gflt.close()
+        del ring
 
     # ---- N > 1, weak run: the strong-scaling figure (fixed --batch images per step) beside it -----------------
     strong = None
     if weak:
         sflt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=N, shard_dim=1, batch=args.batch,
-                             stacked=args.batch > 1, exchange=args.exchange)
+                             stacked=args.batch > 1, exchange=args.exchange, graph=bool(args.graph))
         ssrc, sdst = src_stack[:args.batch].contiguous(), dst_stack[:args.batch].contiguous()
 
         def sstep():
@@ -420,11 +555,17 @@ def main():
         del bsrc, bdst
         bplan.close()
 
+    # ---- the other BASELINE configs -----------------------------------------------------------------------
+    del src_stack, dst_stack, srcs, dsts, host_in, host_out
+    torch.cuda.empty_cache()
+    others = None
+    if not args.no_other_configs:
+        others = other_configs(N, rank, barrier, peak, args.exchange)
+
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        th = oracle.max_threads()
+        th = host_threads()
         v_all, _ = cpu_rate(H, 3, th)
         v_one, _ = cpu_rate(H // 4, 2, 1)
         cpu = {"value": v_all, "unit": "Gsamples/s", "cores": th, "kind": "port",
@@ -441,13 +582,14 @@ def main():
             "config": {"workload": WORKLOAD, "images_per_step": B,
                        "sharding": "none" if N == 1 else
                                    f"every image cut into {N} row strips, one per GPU; the order-3 strip tails travel once per step "
-                                   f"({'two column-chunked all-to-alls' if flt.chunked else 'one all-gather'}); "
+                                   f"({'peer-to-peer exchange windows over NVLink (rf_xchg_put / rf_xchg_wait)' if flt.p2p else 'two column-chunked NCCL all-to-alls' if flt.chunked else 'one NCCL all-gather'}); "
                                    f"{args.batch} images' worth of samples per GPU per step",
                        "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
                        "tile": "128x128 register tiles (fused engine)",
+                       "launch": "one CUDA graph per step (captured once, replayed)" if flt.use_graph else "eager launches",
                        "streams": f"{flt.groups} sub-stacks of {flt.sub} images on their own CUDA streams" if flt.stacked else "1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "batch_sharded": batch_sharded,
-            "strip_sharded_strong": strong,
+            "strip_sharded_strong": strong, "other_configs": others,
             "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,
             "hbm_roofline_pct": 100.0 * (8.0 * value) / (peak * N),
             "hbm_roofline_pct_of_8TBs": 100.0 * (8.0 * value) / (8000.0 * N),

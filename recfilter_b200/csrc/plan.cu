@@ -428,12 +428,18 @@ static void build_strip_response(std::vector<HT>& W, const std::vector<HostScan>
     }
 }
 
-// CY[s][k][j][l] += D^-1 ( sum_{q <= s} W'[s][q][j] * D ext_q[.][l] ),  one thread per line
+// CY[s][k][j][l] += D^-1 ( sum_{q <= s} W'[s][q][j] * D ext_q[.][l] ): one thread per (line, tile).  active[s * nb + j]
+// is 0 where every entry of W[s][.][j] rounds to zero in the compute type (a short-memory filter only reaches the
+// first few tiles of the strip: those blocks are skipped, which changes nothing).
 template <typename CT, int R>
-__global__ void carry_fix_kernel(CT* __restrict__ CY, const CT* __restrict__ ext, const CT* __restrict__ Wd, int S, int nb, int64_t nl)
+__global__ void carry_fix_kernel(CT* __restrict__ CY, const CT* __restrict__ ext, const CT* __restrict__ Wd,
+                                 const unsigned char* __restrict__ active, int S, int nb, int64_t nl)
 {
+    const int j = blockIdx.y;
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nl) return;
+    bool any = false;
+    for (int s = 0; s < S; ++s) any = any || active[s * nb + j];
+    if (!any || l >= nl) return;
     CT e[FMAX_SCANS][R];
     for (int q = 0; q < S; ++q) {
         CT h[R];
@@ -446,28 +452,28 @@ __global__ void carry_fix_kernel(CT* __restrict__ CY, const CT* __restrict__ ext
 #pragma unroll
         for (int k = 0; k < R; ++k) e[q][k] = h[k];
     }
-    for (int s = 0; s < S; ++s)
-        for (int j = 0; j < nb; ++j) {
-            CT dc[R];
+    for (int s = 0; s < S; ++s) {
+        if (!active[s * nb + j]) continue;
+        CT dc[R];
 #pragma unroll
-            for (int k = 0; k < R; ++k) dc[k] = (CT)0;
-            for (int q = 0; q <= s; ++q) {
-                const CT* w = Wd + (((size_t)s * S + q) * nb + j) * R * R;
+        for (int k = 0; k < R; ++k) dc[k] = (CT)0;
+        for (int q = 0; q <= s; ++q) {
+            const CT* w = Wd + (((size_t)s * S + q) * nb + j) * R * R;
 #pragma unroll
-                for (int k = 0; k < R; ++k)
+            for (int k = 0; k < R; ++k)
 #pragma unroll
-                    for (int kk = 0; kk < R; ++kk) dc[k] = dc[k] + w[k * R + kk] * e[q][kk];
-            }
-#pragma unroll
-            for (int m = R - 1; m >= 1; --m)
-#pragma unroll
-                for (int k = m; k < R; ++k) dc[k] = dc[k - 1] - dc[k];             // back to histories
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                CT* c = CY + (((int64_t)s * R + k) * nb + j) * nl + l;
-                *c = *c + dc[k];
-            }
+                for (int kk = 0; kk < R; ++kk) dc[k] = dc[k] + __ldg(w + k * R + kk) * e[q][kk];
         }
+#pragma unroll
+        for (int m = R - 1; m >= 1; --m)
+#pragma unroll
+            for (int k = m; k < R; ++k) dc[k] = dc[k - 1] - dc[k];                 // back to histories
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            CT* c = CY + (((int64_t)s * R + k) * nb + j) * nl + l;
+            *c = *c + dc[k];
+        }
+    }
 }
 
 // small kernel: strip-level carry resolution (host of the multi-GPU layer)
@@ -829,7 +835,7 @@ struct FusedPass : PassBase {
     int Lx = FCHAIN_L, Ld = FCHAIN_L;            // tiles per chain thread
     DevBuf TX, CX, TY, CY, dA;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
-    DevBuf dExt, dTailOut, dW;              // dW: response of the strip's carries to what enters it (build_strip_response)
+    DevBuf dExt, dTailOut, dW, dWact;       // dW: response of the strip's carries to what enters it (build_strip_response)
     DimTables<HT> tx_tab, td_tab;
     std::unique_ptr<ShardResolver<CT, R>> resolver;
     int sdk() const { return ((fp.md * R + 3) / 4) * 4; }     // entries of one A row, padded for 128-bit loads
@@ -844,7 +850,7 @@ struct FusedPass : PassBase {
     size_t workspace() const override
     {
         return TX.bytes + CX.bytes + TY.bytes + CY.bytes + dA.bytes + dPx.bytes + dMx.bytes + dPsegx.bytes + dL.bytes +
-               dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes + dW.bytes;
+               dPd.bytes + dMd.bytes + dPsegd.bytes + dG.bytes + dExt.bytes + dTailOut.bytes + dW.bytes + dWact.bytes;
     }
     int launches() const override
     {
@@ -978,6 +984,15 @@ struct FusedPass : PassBase {
                 build_strip_response<HT>(Wv, sd, gd.n, ts, gd.nb, gd.lo_closed, gd.hi_closed, R, clamp, true);
                 conjugate_blocks(Wv);
                 CUDA_TRY((upload<HT, TT>(dW, Wv)));
+                // tiles whose response blocks all round to zero in the compute type are skipped by the kernel
+                std::vector<unsigned char> act((size_t)fp.md * gd.nb, 0);
+                for (int s2 = 0; s2 < fp.md; ++s2)
+                    for (int q = 0; q <= s2; ++q)
+                        for (int j = 0; j < gd.nb; ++j)
+                            for (int i = 0; i < R * R; ++i)
+                                if ((TT)Wv[((((size_t)s2 * fp.md + q) * gd.nb + j) * R * R) + i] != (TT)0) act[(size_t)s2 * gd.nb + j] = 1;
+                CUDA_TRY(dWact.alloc(act.size()));
+                CUDA_TRY(cudaMemcpy(dWact.p, act.data(), act.size(), cudaMemcpyHostToDevice));
             }
         }
         if (cross_needed()) {
@@ -1117,8 +1132,8 @@ struct FusedPass : PassBase {
         if (stage == 2 && !rechain && d_needs() && dW.p) {
             if (ext_d) {
                 cudaEvent_t ev = timer ? timer->begin(st, ST_CHAIN) : nullptr;
-                carry_fix_kernel<CT, R><<<(unsigned)((fp.nly + 127) / 128), 128, 0, st>>>((CT*)CY.p, (const CT*)ext_d, (const CT*)dW.p,
-                                                                                      fp.md, gd.nb, fp.nly);
+                carry_fix_kernel<CT, R><<<dim3((unsigned)((fp.nly + 127) / 128), (unsigned)gd.nb), 128, 0, st>>>(
+                    (CT*)CY.p, (const CT*)ext_d, (const CT*)dW.p, (const unsigned char*)dWact.p, fp.md, gd.nb, fp.nly);
                 CUDA_TRY(cudaGetLastError());
                 if (timer) timer->end(st, ev);
             }

@@ -79,7 +79,7 @@ class ShardedFilter:
 
     def __init__(self, extents: Sequence[int], dtype, scans: Sequence[Scan], border: str, *, rank: int, world: int,
                  shard_dim: int | None = None, batch: int = 1, engine: str = "auto", group=None, stacked: bool = False,
-                 overlap: int = 1, exchange: str = "auto"):
+                 overlap: int = 1, exchange: str = "auto", graph: bool = False):
         """stacked=True: the `batch` images are one dense stack [batch][...] and are filtered as ONE filter with
         an extra outermost dimension that carries no scans (allowed by the reference: lib/split.cpp:1888-1898,
         it is how apps/audio batches channels): one launch sequence and one tail exchange per stack.
@@ -89,8 +89,12 @@ class ShardedFilter:
         exchange: "p2p" (every rank writes its tails straight into every other rank's exchange window over
         NVLink -- rf_xchg_put / rf_xchg_wait, no NCCL call per step), "allgather" (one NCCL all-gather),
         "alltoall" (column-chunked: every rank resolves 1/world of the lines for all shards; 2 small all-to-alls
-        instead of one all-gather whose volume grows with world) or "auto" (p2p on CUDA devices; the collectives
-        otherwise)."""
+        instead of one all-gather whose volume grows with world) or "auto" (the collectives: all-gather, all-to-all
+        from 4 ranks on when the all-gather would deliver 8 MB or more per rank -- measured on 8 B200s the
+        peer-to-peer windows tie with the NCCL all-gather, and only the collectives can be captured in a CUDA graph).
+        graph=True (stacked only): the whole step -- stage 1, the exchange, stage 2 -- is captured once per
+        (src, dst) pair in a CUDA graph and replayed: a sharded step is a dozen short launches, and from 4 ranks on
+        the host cannot issue them as fast as the GPUs finish them."""
         self.rank, self.world, self.group, self.batch = rank, world, group, batch
         self.stacked = stacked and batch > 1
         self.groups = overlap if (self.stacked and overlap > 1 and batch % overlap == 0) else 1
@@ -120,7 +124,9 @@ class ShardedFilter:
         # measured on 4 and 8 B200s (profiles/): the two all-to-alls win once the all-gather would deliver >= ~8 MB
         # per rank; below that its single collective is faster
         big = self.tail_elems * 4 * world >= (8 << 20)
-        self.p2p = world > 1 and exchange in ("p2p", "auto") and torch.cuda.is_available()
+        self.p2p = world > 1 and exchange == "p2p" and torch.cuda.is_available()
+        self.use_graph = bool(graph) and self.stacked and not self.p2p and torch.cuda.is_available()
+        self._graphs = {}
         self.chunked = (not self.p2p) and chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4 and big))
         self.windows = []
         if self.p2p:
@@ -149,6 +155,20 @@ class ShardedFilter:
         """Filter a dense stack [batch][local extents...] (stacked=True)."""
         if not self.stacked:
             raise ValueError("run_stacked needs stacked=True")
+        if not self.use_graph:
+            return self._run_stacked(src, dst)
+        key = (src.data_ptr(), dst.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            self._run_stacked(src, dst)              # lazy initialisations (function attributes, NCCL) stay outside the capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_stacked(src, dst)
+            self._graphs[key] = g
+        g.replay()
+
+    def _run_stacked(self, src: torch.Tensor, dst: torch.Tensor):
         G, sub = self.groups, self.sub
         if self.world > 1 and self._tails is None:
             dt = torch.float32 if src.dtype == torch.float32 else torch.int32
@@ -206,6 +226,7 @@ class ShardedFilter:
         return n * self.groups / self.batch if self.stacked else n
 
     def close(self):
+        self._graphs = {}
         if self.windows:
             torch.cuda.synchronize()
             if dist.is_initialized():
