@@ -625,8 +625,17 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     if (!identity) {
         if (merged.size() > RF_MAX_TAPS) die("RecFilter " + c.name + ": too many taps in the definition");
         if (c.type.bytes() != 4) die("RecFilter " + c.name + ": stencil definitions need a 32-bit element type");
-        // factor the first weight out: "(a - b - c + d) / area" becomes unit taps and one scale after the sum
-        const double w0 = merged[0].w != 0.0 ? merged[0].w : 1.0;
+        // factor the first weight out: "(a - b - c + d) / area" becomes unit taps and one scale after the sum.
+        // Integer filters: weights are ring elements, nothing is factored out, and a weight that is not an exact
+        // integer (a scale such as "/ area": Halide's integer division is not a linear scale) is refused instead of
+        // being rounded silently.
+        const bool integral = !c.type.is_float();
+        if (integral)
+            for (const LinTap& t : merged)
+                if (t.w != std::floor(t.w) || std::fabs(t.w) > 2147483647.0)
+                    die("RecFilter " + c.name + ": an integer definition needs integer weights (division and fractional "
+                        "scales of an integer filter are not supported: convert to float first)");
+        const double w0 = integral ? 1.0 : (merged[0].w != 0.0 ? merged[0].w : 1.0);
         c.stencil_scale = (float)w0;
         for (const LinTap& t : merged) {
             rf_tap rt;

@@ -176,3 +176,29 @@ def test_reference_audio_apps_on_b200(tmp_path):
         rc, out = run("gpu", prog, ["-w", "65536", "-t", "1024", "-iter", "1"], cwd=tmp_path)
         assert rc == 0, out[-2000:]
         assert "ms per iteration" in out
+
+
+def _int_stencil_check(kind, tmp_path):
+    # tests/cpp/int_stencil_check.cpp: integer definitions go to the stencil epilogue with ring weights (bit exact);
+    # "/ area" on an integer filter is refused (message + assert) instead of being rounded silently
+    rc, out = run(kind, "int_stencil_check", [], cwd=tmp_path)
+    assert rc == 0 and out.count(": 0 mismatches") == 2, out[-2000:]
+    rc, out = run(kind, "int_stencil_check", ["--div"], cwd=tmp_path)
+    assert rc != 0 and "integer definition needs integer weights" in out, out[-2000:]
+
+
+def test_integer_stencils_on_oracle_backend(tmp_path):
+    _int_stencil_check("pin", tmp_path)
+
+
+@pytest.mark.gpu
+def test_integer_stencils_on_b200(tmp_path):
+    _int_stencil_check("gpu", tmp_path)
+
+
+@pytest.mark.parametrize("prog,args", [("bicubic_filter", ["-w", "256", "-t", "32"]), ("biquintic_cascaded_filter", ["-w", "256", "-t", "32"])])
+@pytest.mark.parametrize("kind", ["pin", pytest.param("gpu", marks=pytest.mark.gpu)])
+def test_reference_bspline_apps_clamped_border(kind, prog, args, tmp_path):
+    # apps/bspline: the reference's own checks of the CLAMPED border (lib/recfilter.cpp:330-336), feed-forward != 1
+    rc, out = run(kind, prog, args, cwd=tmp_path)
+    assert rc == 0 and max_error(out) is not None and max_error(out) <= MAX_PERCENT, out[-2000:]
