@@ -214,6 +214,22 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev,
                    const void* gathered_tails_dev, int nshards, int shard_rank, void* stream);
 
 /*
+ * One filter over several GPUs of ONE process (what RecFilter::realize / profile use with RECFILTER_GPUS=n; no
+ * reference equivalent: lib/recfilter.cpp:932-1016 drives one device).  The outermost dimension is cut into n equal
+ * parts: independent parts when it carries no scans (stacks of images, audio channels -- nothing is exchanged),
+ * strips otherwise (rf_plan_stage1, the order-r boundary tails pulled from the peers with cudaMemcpyPeerAsync over
+ * NVLink, rf_plan_stage2).  Host buffers are dense, the whole array.
+ */
+typedef struct rf_mgpu rf_mgpu;
+int  rf_mgpu_create(const rf_desc* desc, int ngpus, rf_mgpu** out);
+void rf_mgpu_destroy(rf_mgpu* m);
+int  rf_mgpu_ngpus(const rf_mgpu* m);
+int  rf_mgpu_describe(const rf_mgpu* m, char* buf, size_t n);
+int  rf_mgpu_execute_host(rf_mgpu* m, const void* in_host, void* out_host);           /* H2D + filter + D2H, synchronous */
+int  rf_mgpu_profile(rf_mgpu* m, const void* in_host, int iters, float* ms_per_iter); /* device-resident, slowest GPU */
+const char* rf_mgpu_last_error(void);
+
+/*
  * Exchange windows for the strip tails (peer to peer over NVLink; no collective library, no host in the data
  * path).  Every rank owns a window of two generations of [nranks][bytes_per_rank] in its device memory.
  *   rf_xchg_put   copies this rank's tails into its slot of EVERY rank's window and then raises its arrival word

@@ -175,3 +175,29 @@ int rf_memset(void* d, int v, size_t n) { memset(d, v, n); return RF_OK; }
 int rf_malloc_host(void** p, size_t bytes) { return rf_malloc(p, bytes); }
 int rf_free_host(void* p) { free(p); return RF_OK; }
 int rf_synchronize(void) { return RF_OK; }
+
+/* entry points added in round 2: the oracle backend is one CPU "device" -- no look-back kernels to check, no peers */
+int rf_plan_check(rf_plan* p) { (void)p; return RF_OK; }
+int rf_mgpu_create(const rf_desc* d, int n, rf_mgpu** out)
+{
+    (void)d; (void)n;
+    if (out) *out = 0;
+    snprintf(g_err, sizeof(g_err), "the oracle backend is a single CPU device");
+    return RF_EUNSUPPORTED;
+}
+void rf_mgpu_destroy(rf_mgpu* m) { (void)m; }
+int rf_mgpu_ngpus(const rf_mgpu* m) { (void)m; return 1; }
+int rf_mgpu_describe(const rf_mgpu* m, char* buf, size_t n) { (void)m; if (buf && n) buf[0] = 0; return RF_EUNSUPPORTED; }
+int rf_mgpu_execute_host(rf_mgpu* m, const void* i, void* o) { (void)m; (void)i; (void)o; return RF_EUNSUPPORTED; }
+int rf_mgpu_profile(rf_mgpu* m, const void* i, int it, float* ms) { (void)m; (void)i; (void)it; (void)ms; return RF_EUNSUPPORTED; }
+const char* rf_mgpu_last_error(void) { return g_err; }
+size_t rf_xchg_handle_bytes(void) { return 64; }
+int rf_xchg_create(size_t b, int n, int r, rf_xchg** out) { (void)b; (void)n; (void)r; if (out) *out = 0; return RF_EUNSUPPORTED; }
+void rf_xchg_destroy(rf_xchg* x) { (void)x; }
+int rf_xchg_ipc_handle(rf_xchg* x, void* h) { (void)x; (void)h; return RF_EUNSUPPORTED; }
+int rf_xchg_open_peer(rf_xchg* x, int p, const void* h) { (void)x; (void)p; (void)h; return RF_EUNSUPPORTED; }
+int rf_xchg_set_peer(rf_xchg* x, int p, rf_xchg* o) { (void)x; (void)p; (void)o; return RF_EUNSUPPORTED; }
+int rf_xchg_put(rf_xchg* x, const void* s, size_t b, void* st) { (void)x; (void)s; (void)b; (void)st; return RF_EUNSUPPORTED; }
+int rf_xchg_wait(rf_xchg* x, void* st, void** g) { (void)x; (void)st; (void)g; return RF_EUNSUPPORTED; }
+int rf_xchg_check(rf_xchg* x) { (void)x; return RF_EUNSUPPORTED; }
+const char* rf_xchg_last_error(void) { return g_err; }

@@ -63,7 +63,10 @@ struct RecFilterContents {
     vector<ScanDef> scans;
     std::map<string, int> tiles;    // split() hints
     rf_plan* plan = nullptr;
-    string plan_sig;                // the scans the plan was built for (its own, or a fused cascade's)
+    string plan_sig;                // what the plan was built for: scans (its own, or a fused cascade's), extents, border, tiles
+    rf_mgpu* mgpu = nullptr;        // RECFILTER_GPUS=n: the same filter cut over n GPUs (rf_mgpu_*)
+    string mgpu_sig;
+    bool mgpu_refused = false;      // the engine declined to shard this filter: said once, then one GPU
     // Tuple (multi-output) filters, lib/recfilter.cpp:68-74,197-203: every Tuple element is filtered
     // independently with the same scans -- one channel filter per element, kept in step by sync_channels()
     vector<std::shared_ptr<RecFilterContents>> channels;
@@ -72,6 +75,7 @@ struct RecFilterContents {
     ~RecFilterContents()
     {
         if (plan) rf_plan_destroy(plan);
+        if (mgpu) rf_mgpu_destroy(mgpu);
         if (dev_out) rf_free(dev_out);
         if (dev_tmp) rf_free(dev_tmp);
         if (dev_side) rf_free(dev_side);
@@ -329,13 +333,9 @@ vector<ScanDef> unit_scans(RecFilterContents& first, RecFilterContents& last)
     return scans;
 }
 
-void build_plan(RecFilterContents& c, const vector<ScanDef>& scans)
+// descriptor of the filter c with the scan list `scans`, and a signature of everything a plan depends on
+string fill_desc(RecFilterContents& c, const vector<ScanDef>& scans, rf_desc& d)
 {
-    std::ostringstream sig;
-    for (const ScanDef& sc : scans) { sig << sc.dim << (sc.causal ? '+' : '-'); for (float v : sc.coeff) sig << v << ','; sig << ';'; }
-    if (c.plan && c.plan_sig == sig.str()) return;
-    if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
-    rf_desc d;
     std::memset(&d, 0, sizeof(d));
     if (c.dims.size() > RF_MAX_DIMS) die("RecFilter: at most 4 dimensions are supported");
     if (scans.size() > RF_MAX_SCANS) die("RecFilter: too many scans");
@@ -358,8 +358,21 @@ void build_plan(RecFilterContents& c, const vector<ScanDef>& scans)
     }
     d.opt.fuse_dims = -1;
     d.opt.shard_dim = -1;
+    std::ostringstream sig;
+    sig << d.dtype << (c.clamped ? 'c' : 'z');
+    for (int i = 0; i < d.ndim; ++i) sig << d.extent[i] << '/' << d.opt.tile[i] << 'x';
+    for (const ScanDef& sc : scans) { sig << sc.dim << (sc.causal ? '+' : '-'); for (float v : sc.coeff) sig << v << ','; sig << ';'; }
+    return sig.str();
+}
+
+void build_plan(RecFilterContents& c, const vector<ScanDef>& scans)
+{
+    rf_desc d;
+    const string sig = fill_desc(c, scans, d);
+    if (c.plan && c.plan_sig == sig) return;
+    if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
     engine_check(rf_plan_create(&d, &c.plan), "rf_plan_create");
-    c.plan_sig = sig.str();
+    c.plan_sig = sig;
 }
 void build_plan(RecFilterContents& c) { build_plan(c, unit_scans(unit_first(c), c)); }
 
@@ -431,6 +444,41 @@ void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in)
     return c.dev_out;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// RECFILTER_GPUS=n: realize() / profile() cut the filter over n GPUs of this process (rf_mgpu_*: independent parts when
+// the outermost dimension carries no scans, strips with one order-r tail exchange over NVLink otherwise).  It applies
+// to a filter that is ONE plan on ONE input image of exactly its extents (every in-scope app: apps/gaussian,
+// apps/summed_table, apps/audio ...); anything else -- and anything the engine declines, e.g. an extent that
+// does not divide -- runs on one GPU as before, with a note on stderr.
+// ---------------------------------------------------------------------------------------------
+int requested_gpus()
+{
+    static const int n = getenv("RECFILTER_GPUS") ? std::max(1, atoi(getenv("RECFILTER_GPUS"))) : 1;
+    return n;
+}
+rf_mgpu* mgpu_for(RecFilterContents& c)
+{
+    if (requested_gpus() < 2 || c.mgpu_refused || !c.channels.empty()) return nullptr;
+    RecFilterContents& first = unit_first(c);
+    if (first.src_filter || !first.stencil.empty() || !first.src_image || !first.src_image->has_data()) return nullptr;
+    const BufferData& b = *first.src_image;
+    if (b.dims != (int)c.dims.size()) return nullptr;
+    for (int i = 0; i < b.dims; ++i) if (b.extent[i] != c.dims[i].num_pixels()) return nullptr;
+    rf_desc d;
+    const string sig = fill_desc(c, unit_scans(first, c), d);
+    if (c.mgpu && c.mgpu_sig == sig) return c.mgpu;
+    if (c.mgpu) { rf_mgpu_destroy(c.mgpu); c.mgpu = nullptr; }
+    const int rc = rf_mgpu_create(&d, requested_gpus(), &c.mgpu);
+    if (rc != RF_OK) {
+        cerr << "RecFilter " << c.name << ": RECFILTER_GPUS=" << requested_gpus() << " not used (" << rf_mgpu_last_error()
+             << "); running on one GPU" << endl;
+        c.mgpu = nullptr; c.mgpu_refused = true;
+        return nullptr;
+    }
+    c.mgpu_sig = sig;
+    return c.mgpu;
+}
 
 void* evaluate_device(RecFilterContents& c)
 {
@@ -836,11 +884,16 @@ Realization RecFilter::realize()
         }
         return Realization(bufs);
     }
-    void* dev = evaluate_device(c);
     vector<int> ext;
     for (const RecFilterDim& d : c.dims) ext.push_back(d.num_pixels());
     Buffer out(c.type, ext);
-    engine_check(rf_memcpy_d2h(out.host_ptr(), dev, out.size_in_bytes()), "rf_memcpy_d2h");
+    if (rf_mgpu* m = mgpu_for(c)) {
+        if (rf_mgpu_execute_host(m, unit_first(c).src_image->host_data(), out.host_ptr()) != RF_OK)
+            die(string("rf_mgpu_execute_host failed: ") + rf_mgpu_last_error());
+    } else {
+        void* dev = evaluate_device(c);
+        engine_check(rf_memcpy_d2h(out.host_ptr(), dev, out.size_in_bytes()), "rf_memcpy_d2h");
+    }
     if (const char* path = getenv("RECFILTER_DUMP_FILTER")) {
         // one JSON line per realize(): the filter chain as declared (used to label golden vectors)
         vector<RecFilterContents*> chain;
@@ -877,6 +930,14 @@ float RecFilter::profile(int iterations)
         for (auto& ch : c.channels) { RecFilter f; f.contents = ch; total += f.profile(iterations); }
         cerr << c.name << ": " << total << " ms per iteration for " << c.channels.size() << " Tuple elements" << endl;
         return total;
+    }
+    if (rf_mgpu* m = mgpu_for(c)) {
+        float per_iter = 0.0f;
+        if (rf_mgpu_profile(m, unit_first(c).src_image->host_data(), iterations, &per_iter) != RF_OK)
+            die(string("rf_mgpu_profile failed: ") + rf_mgpu_last_error());
+        cerr << c.name << ": " << per_iter << " ms per iteration over " << iterations << " iteration(s) on " << rf_mgpu_ngpus(m)
+             << " GPUs, " << (double(c.count()) / (per_iter * 1e-3) / 1e9) << " Gsamples/s" << endl;
+        return per_iter;
     }
     vector<std::pair<RecFilterContents*, RecFilterContents*>> units;
     collect_units(c, units);

@@ -202,3 +202,28 @@ def test_reference_bspline_apps_clamped_border(kind, prog, args, tmp_path):
     # apps/bspline: the reference's own checks of the CLAMPED border (lib/recfilter.cpp:330-336), feed-forward != 1
     rc, out = run(kind, prog, args, cwd=tmp_path)
     assert rc == 0 and max_error(out) is not None and max_error(out) <= MAX_PERCENT, out[-2000:]
+
+
+@pytest.mark.gpu
+def test_reference_apps_unchanged_on_two_gpus(tmp_path):
+    """RECFILTER_GPUS=2: RecFilter::realize / profile cut the filter over the GPUs of the process (rf_mgpu_*: strips
+    with one order-r tail exchange over NVLink).  The reference's apps, compiled unchanged, must still pass their
+    own checks; needs two devices (skipped on a one-GPU box)."""
+    import recfilter_b200 as rf
+    if rf.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, RECFILTER_GPUS="2")
+    for prog, args, checked in [("summed_table", ["-w", "1024", "-t", "32"], True),
+                                ("bicubic_filter", ["-w", "1024", "-t", "32"], True),
+                                ("gaussian_filter_3xy", ["-w", "2048", "-t", "32", "-iter", "3"], False),
+                                ("test_generic_xyz", [], True)]:
+        exe = os.path.join(ROOT, "oracle", "_ref", "gpu", prog)
+        if not os.path.exists(exe):
+            pytest.skip(f"{exe} not built")
+        p = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600, cwd=tmp_path, env=env)
+        out = p.stdout + p.stderr
+        assert p.returncode == 0, out[-2000:]
+        if checked:
+            assert max_error(out) is not None and max_error(out) <= MAX_PERCENT, out[-2000:]
+        if prog != "test_generic_xyz":                      # 20^3: the z extent does not divide into tiles; may run on one GPU
+            assert "on 2 GPUs" in out and "not used" not in out, out[-2000:]
