@@ -765,6 +765,133 @@ fchain_kernel(const __grid_constant__ FChainParams<CT, R> p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// carries of a short-memory dimension, no chain.  The serial inter-tile loop (lib/split.cpp:832-846,
+// ctail[t] = tail[t] + P * ctail[t-1]) multiplies the carry by the tile's transition matrix P = A^tile.  For a
+// filter whose impulse response is much shorter than a tile (the headline Gaussian: |pole| = 0.79, P ~ 6e-13 over
+// 128 samples) that product is far below the last bit of the tail it is added to, so the carry entering a tile is
+// the tail' of the tile before it -- every (line, tile) pair is independent and the carry stage becomes one
+// streaming launch per dimension.  The planner takes this path only when every entry of P (all tile variants,
+// difference basis, fp64) is below 1e-10 in magnitude; the result differs from the chained one by less than that.
+//   C_0[j] = T'_0[j -/+ 1]
+//   C_1[j] = T'_1[j -/+ 1] + M[0 -> 1] * C_0[j -/+ 1]            (same-dimension residual, lib/split.cpp:912-1004)
+// with T' = T + G_row * A[tile] in the x dimension (cross-dimension residual, as in fchain_kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr int FLOCAL_TPT = 8;     // tiles per thread (their loads are issued together: the kernel is pure latency otherwise)
+
+template <typename CT, int R>
+__global__ void __launch_bounds__(128)
+flocal_kernel(const __grid_constant__ FLocalParams<CT, R> p)
+{
+    constexpr int TPT = FLOCAL_TPT, HALO = 2, NT = TPT + 2 * HALO;
+    const int64_t l = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int j0 = blockIdx.y * TPT;
+    pdl_launch_dependents();
+    // x dimension: this line is row `row` of tile row bd (static tables: before the wait)
+    CT grow[FMAX_SCANS * R];
+    int64_t arow = 0;
+    const bool lv = l < p.nl;
+    if (p.A && lv) {
+        const int64_t o = l / p.Nd;
+        const int rem = (int)(l - o * p.Nd);
+        const int bd = rem / p.ts, row = rem - bd * p.ts;
+        const int vd = ftile_variant(bd, p.nbd);
+#pragma unroll
+        for (int n = 0; n < FMAX_SCANS * R; ++n)
+            grow[n] = n < p.Sd * R ? __ldg(p.G + (((int64_t)vd * p.Sd + n / R) * p.ts + row) * R + n % R) : (CT)0;
+        arow = (o * p.nbd + bd) * (int64_t)p.nb * p.S * R * p.sdk;
+    }
+    pdl_wait();
+    if (!lv) return;
+    const int64_t plane = (int64_t)p.nb * p.nl;
+    const int S = p.S;
+    // tail' of both scans at the tiles j0 - HALO .. j0 + TPT + HALO - 1 (zero outside the line): every load first
+    CT t[2][NT][R];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int tt = j0 - HALO + i;
+            const bool in = s < S && tt >= 0 && tt < p.nb;
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                t[s][i][k] = in ? ld_stream<CT>(p.T + ((int64_t)s * R + k) * plane + (int64_t)tt * p.nl + l) : (CT)0;
+        }
+    if (p.A) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const int tt = j0 - HALO + i;
+                if (s < S && tt >= 0 && tt < p.nb) {
+                    const CT* ap = p.A + arow + ((int64_t)tt * S + s) * R * p.sdk;
+#pragma unroll
+                    for (int kx = 0; kx < R; ++kx) {
+                        CT acc = t[s][i][kx];
+#pragma unroll
+                        for (int n = 0; n < FMAX_SCANS * R; ++n)
+                            if (n < p.Sd * R) acc = fmadd(grow[n], __ldg(ap + kx * p.sdk + n), acc);
+                        t[s][i][kx] = acc;
+                    }
+                }
+            }
+    }
+    // y = D^-1 (M' (D c)), M' of the tile variant `var`
+    auto residual = [&](int var, const CT (&c)[R], CT (&y)[R]) {
+        CT d[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { d[k] = c[k]; y[k] = (CT)0; }
+        fdiff_fwd<CT, R>(d);
+        const CT* m = p.M + (((int64_t)var * S + 0) * S + 1) * R * R;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+#pragma unroll
+            for (int kk = 0; kk < R; ++kk) y[k] = fmadd(__ldg(m + k * R + kk), d[kk], y[k]);
+        fdiff_inv<CT, R>(y);
+    };
+    // (register arrays need compile-time indices: the scan directions select between static neighbours)
+    const bool f0 = p.causal[0] != 0, f1 = p.causal[1] != 0;
+    const int d1 = f1 ? 1 : -1;
+#pragma unroll
+    for (int jj = 0; jj < TPT; ++jj) {
+        const int j = j0 + jj;
+        if (j >= p.nb) break;
+        const int i = jj + HALO;                                  // index of tile j in t[][]
+        // scan 0: the carry entering tile j is the tail' of the tile before it
+        CT c0[R], c0p[R];                                         // ... entering tile j, entering the tile before j in scan 1's order
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            c0[k] = f0 ? t[0][i - 1][k] : t[0][i + 1][k];
+            c0p[k] = f1 ? (f0 ? t[0][i - 2][k] : t[0][i][k]) : (f0 ? t[0][i][k] : t[0][i + 2][k]);
+            p.C[(int64_t)k * plane + (int64_t)j * p.nl + l] = c0[k];
+        }
+        if (p.tail_out && (p.causal[0] ? j == p.nb - 1 : j == 0)) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) p.tail_out[(int64_t)k * p.nl + l] = t[0][i][k];
+        }
+        if (S < 2) continue;
+        // scan 1: tail' of the tile before j (in its order) + the same-dimension residual of scan 0's carry there
+        const int jp = j - d1;
+        CT c1[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) c1[k] = f1 ? t[1][i - 1][k] : t[1][i + 1][k];
+        if (jp >= 0 && jp < p.nb) {
+            CT y[R];
+            residual(ftile_variant(jp, p.nb), c0p, y);
+#pragma unroll
+            for (int k = 0; k < R; ++k) c1[k] = c1[k] + y[k];
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) p.C[((int64_t)R + k) * plane + (int64_t)j * p.nl + l] = c1[k];
+        if (p.tail_out && (p.causal[1] ? j == p.nb - 1 : j == 0)) {
+            CT y[R];
+            residual(ftile_variant(j, p.nb), c0, y);
+#pragma unroll
+            for (int k = 0; k < R; ++k) p.tail_out[((int64_t)R + k) * p.nl + l] = t[1][i][k] + y[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // cross-dimension residual (/root/reference/lib/split.cpp:1215-1633), part 1: one warp per tile.
 // The completed d carries change the d-filtered tile by G_d * CY (rows x cols, rank R per d
 // scan); the x tails P1 took from the incomplete tile therefore miss (G_d * CY) * L_x^T:

@@ -135,6 +135,14 @@ static cudaError_t launch_fchain_T(const FChainParams<CT, R>& pin, cudaStream_t 
 }
 
 template <typename CT, int R>
+static cudaError_t launch_flocal_T(const FLocalParams<CT, R>& p, cudaStream_t st)
+{
+    if (p.nl <= 0 || p.nb <= 0) return cudaSuccess;
+    if (p.S < 1 || p.S > 2 || p.nb > 65535) return cudaErrorInvalidConfiguration;
+    return launch_pdl(flocal_kernel<CT, R>, dim3((unsigned)((p.nl + 127) / 128), (unsigned)((p.nb + FLOCAL_TPT - 1) / FLOCAL_TPT)), dim3(128), 0, st, p);
+}
+
+template <typename CT, int R>
 static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& pin, int ts, cudaStream_t st)
 {
     FCrossParams<CT, R> p = pin;
@@ -158,6 +166,10 @@ cudaError_t RFB_CAT(launch_fchain_f, RFB_R)(const FChainParams<float, RFB_R>& p,
 { return launch_fchain_T<float, RFB_R>(p, st); }
 cudaError_t RFB_CAT(launch_fchain_u, RFB_R)(const FChainParams<uint32_t, RFB_R>& p, cudaStream_t st)
 { return launch_fchain_T<uint32_t, RFB_R>(p, st); }
+cudaError_t RFB_CAT(launch_flocal_f, RFB_R)(const FLocalParams<float, RFB_R>& p, cudaStream_t st)
+{ return launch_flocal_T<float, RFB_R>(p, st); }
+cudaError_t RFB_CAT(launch_flocal_u, RFB_R)(const FLocalParams<uint32_t, RFB_R>& p, cudaStream_t st)
+{ return launch_flocal_T<uint32_t, RFB_R>(p, st); }
 cudaError_t RFB_CAT(launch_fcross_f, RFB_R)(const FCrossParams<float, RFB_R>& p, int ts, cudaStream_t st)
 { return launch_fcross_T<float, RFB_R>(p, ts, st); }
 cudaError_t RFB_CAT(launch_fcross_u, RFB_R)(const FCrossParams<uint32_t, RFB_R>& p, int ts, cudaStream_t st)

@@ -68,6 +68,19 @@ struct FChainParams {
     int64_t Nd; int nbd; int Sd; int ts; int sdk;
 };
 
+// carries of a SHORT-MEMORY dimension (see flocal_kernel in fused.cuh): at most two scans
+template <typename CT, int R>
+struct FLocalParams {
+    const CT* T; CT* C;           // [s][k][j][l], as the chain kernel
+    int64_t nl; int nb; int S;
+    int causal[2];
+    const CT* M;                  // [V][S][S][R][R]   (q -> s), difference basis
+    CT* tail_out;                 // [s][k][l] completed tail leaving the last tile or null
+    // x dimension only: cross-dimension residual applied while the tails are read (null: none), as in FChainParams
+    const CT* A; const CT* G;
+    int64_t Nd; int nbd; int Sd; int ts; int sdk;
+};
+
 template <typename CT, int R>
 struct FCrossParams {
     const CT* CY;                 // [sd][k][bd][ly]   completed d carries

@@ -1,0 +1,26 @@
+"""Small shapes of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from recfilter_b200 import Plan, Scan, gaussian_weights
+G3 = gaussian_weights(5.0, 3)
+rng = np.random.default_rng(1)
+def run(name, ext, dt, scans, border="zero", **kw):
+    a = (rng.random(ext[::-1], dtype=np.float32) if dt == "f32" else rng.integers(0, 255, size=ext[::-1], dtype=np.uint32))
+    p = Plan(ext, dt, [Scan(*s) for s in scans], border, **kw)
+    out = p.realize(a)
+    print(name, "ok", p.describe().splitlines()[1].strip()[:70], float(np.asarray(out, dtype=np.float64).sum()) != 0.0, flush=True)
+    p.close()
+c3 = [(0, True, G3), (0, False, G3), (1, True, G3), (1, False, G3)]
+sat = [(0, True, [1, 1]), (1, True, [1, 1])]
+run("two-sweep fused 256x384 clamp", (256, 384), "f32", c3, "clamp", engine="twopass")
+run("two-sweep fused 64-tile", (128, 192), "f32", c3, "clamp", engine="twopass")
+run("ragged two-sweep 200x136", (200, 136), "f32", c3, "clamp", engine="twopass")
+run("look-back 2-D u32 256x256", (256, 256), "u32", sat)
+run("look-back 2-D f32 order 3", (384, 256), "f32", [(0, False, G3), (1, True, G3)], "clamp")
+run("look-back signal r8", (32768, 3), "f32", [(0, True, [1.0] + [0.01] * 8)])
+run("look-back signal r3 anticausal", (16384 * 3, 2), "f32", [(0, False, G3)], "clamp")
+run("two-sweep signal r8", (32768, 2), "f32", [(0, True, [1.0] + [0.01] * 8)], engine="twopass")
+run("generic engine order 5", (96, 80), "f32", [(0, True, [1.0] + [0.1] * 5), (1, False, [1.0] + [0.1] * 5)], engine="generic")
+run("3-D volume", (128, 128, 64), "f32", [(0, True, [1, .5, .25]), (1, False, [1, .5, .125]), (2, True, [1, .5, .0625]), (2, False, [1, .5, .125])])
+print("SANITIZE SCRIPT DONE")

@@ -368,3 +368,33 @@ def test_ragged_single_dimension_and_volume(oracle):
     sc = [(0, True, W2[0]), (0, False, W2[1]), (1, True, W2[2]), (1, False, W2[3]), (2, True, W2[4]), (2, False, W2[5])]
     check_float(oracle, v, sc)
     check_float(oracle, v, sc, "clamp")
+
+
+# ---- short-memory dimensions: carries from the adjacent tile only (flocal_kernel), no chain ----
+def test_short_memory_carries_equal_chained_carries(oracle):
+    """sigma = 5 over 128-sample tiles: the tile transition matrix is ~6e-13, the planner drops the chain.  The
+    result must agree with the chained one (RFB_NO_LOCAL_CARRY=1) far below the fp32 tolerance, and with the oracle."""
+    import os
+    for shape, border in (((2048, 2560), "clamp"), ((2560, 2048), "zero")):       # >= 296 tiles of 128: the planner keeps 128-sample tiles
+        a = rand_image(shape, np.float32, 4711)
+        plan = Plan(shape[::-1], "f32", [Scan(*s) for s in C3], border, engine="twopass")
+        assert "short-memory carries" in plan.describe(), plan.describe()
+        fast = plan.realize(a)
+        plan.close()
+        os.environ["RFB_NO_LOCAL_CARRY"] = "1"
+        try:
+            plan = Plan(shape[::-1], "f32", [Scan(*s) for s in C3], border, engine="twopass")
+            assert "short-memory carries" not in plan.describe()
+            chained = plan.realize(a)
+            plan.close()
+        finally:
+            os.environ.pop("RFB_NO_LOCAL_CARRY", None)
+        assert rel_err(fast, chained) <= 8e-6, rel_err(fast, chained)      # two fp32 evaluations of the same carries, each ~3e-6 from the truth
+        truth = oracle.apply_filter(a.astype(np.float64), C3, border, threads=8)
+        assert rel_err(fast, truth) <= TOL
+    # a long-memory filter keeps the chain
+    wide = gaussian_weights(25.0, 3)
+    plan = Plan((512, 512), "f32", [Scan(0, True, wide), Scan(0, False, wide), Scan(1, True, wide), Scan(1, False, wide)], "clamp",
+                engine="twopass")
+    assert "short-memory carries" not in plan.describe()
+    plan.close()
