@@ -227,6 +227,10 @@ struct Variable {
     }
 };
 class Function {};
+// Internal::Cast::make(type, expr), as the reference's programs spell a cast (apps/DoG/diff_gauss.cpp:73, lib/iir_coeff.cpp:180)
+struct Cast {
+    static Expr make(Type t, Expr e) { return Halide::cast(t, e); }
+};
 } // namespace Internal
 
 class Tuple {

@@ -381,6 +381,18 @@ void build_plan(RecFilterContents& c) { build_plan(c, unit_scans(unit_first(c), 
 void* evaluate_device(RecFilterContents& c);
 
 // dense device copy of the [0, extent) box of a host image (which may be larger than the filter domain)
+// one element of an image of type `t`, as a double
+static double load_as_double(const unsigned char* p, const Type& t)
+{
+    if (t.is_float()) return t.bits == 32 ? (double)*reinterpret_cast<const float*>(p) : *reinterpret_cast<const double*>(p);
+    if (t.is_int()) {
+        switch (t.bits) { case 8: return *reinterpret_cast<const int8_t*>(p); case 16: return *reinterpret_cast<const int16_t*>(p);
+                          default: return *reinterpret_cast<const int32_t*>(p); }
+    }
+    switch (t.bits) { case 8: return *reinterpret_cast<const uint8_t*>(p); case 16: return *reinterpret_cast<const uint16_t*>(p);
+                      default: return *reinterpret_cast<const uint32_t*>(p); }
+}
+
 void* upload_image(RecFilterContents& c, const BufferData& b)
 {
     const size_t bytes = c.count() * (size_t)c.type.bytes();
@@ -388,11 +400,12 @@ void* upload_image(RecFilterContents& c, const BufferData& b)
     engine_check(rf_malloc(&dev, bytes), "rf_malloc");
     bool same = b.dims == (int)c.dims.size();
     for (int i = 0; same && i < b.dims; ++i) same = b.extent[i] == c.dims[i].num_pixels();
-    if (same) {
+    const bool convert = !(b.type == c.type);             // cast<float>(image16(x, y)): the filter type is the RHS type
+    if (same && !convert) {
         engine_check(rf_memcpy_h2d(dev, b.host_data(), bytes), "rf_memcpy_h2d");
     } else {
-        // the image is larger than the filter domain: pack the [0, extent) box
-        const int eb = c.type.bytes();
+        // the image is larger than the filter domain and / or of another type: pack (and convert) the [0, extent) box
+        const int eb = c.type.bytes(), sb = b.type.bytes();
         vector<unsigned char> packed(bytes);
         int ext[4] = { 1, 1, 1, 1 }, bext[4] = { 1, 1, 1, 1 };
         for (size_t i = 0; i < c.dims.size(); ++i) { ext[i] = c.dims[i].num_pixels(); bext[i] = b.extent[i]; }
@@ -401,7 +414,12 @@ void* upload_image(RecFilterContents& c, const BufferData& b)
             for (int z = 0; z < ext[2]; ++z)
                 for (int y = 0; y < ext[1]; ++y) {
                     const size_t src = (((size_t)w * bext[2] + z) * bext[1] + y) * (size_t)bext[0];
-                    std::memcpy(&packed[o * eb], b.host_data() + src * eb, (size_t)ext[0] * eb);
+                    if (!convert) {
+                        std::memcpy(&packed[o * eb], b.host_data() + src * eb, (size_t)ext[0] * eb);
+                    } else {                                // integer image -> float filter (the only conversion define() accepts)
+                        float* dstp = reinterpret_cast<float*>(&packed[o * eb]);
+                        for (int x = 0; x < ext[0]; ++x) dstp[x] = (float)load_as_double(b.host_data() + (src + x) * sb, b.type);
+                    }
                     o += (size_t)ext[0];
                 }
         engine_check(rf_memcpy_h2d(dev, packed.data(), bytes), "rf_memcpy_h2d");
@@ -662,6 +680,13 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     } else {
         c.src_image = image;
         c.type = image->type;                                       // type of the filter = type of the RHS (lib/recfilter.cpp:197)
+        // a type-converting definition, cast<float>(image16(x, y)) (apps/DoG/diff_gauss.cpp:66-73) or image8(x, y) * 0.5f:
+        // the RHS is Float(32) over an integer image -> a float filter, the image is converted on upload.  Any other
+        // mismatch is refused rather than run in the image's type with truncated coefficients.
+        if (e.defined() && !(e.type() == image->type)) {
+            if (e.type() == Float(32) && !image->type.is_float()) c.type = Float(32);
+            else die("RecFilter " + c.name + ": type-converting definitions other than integer image -> float are not supported");
+        }
     }
     // a single unit tap whose indices are the identity inside the domain is the input itself
     c.stencil.clear();

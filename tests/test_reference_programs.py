@@ -227,3 +227,10 @@ def test_reference_apps_unchanged_on_two_gpus(tmp_path):
             assert max_error(out) is not None and max_error(out) <= MAX_PERCENT, out[-2000:]
         if prog != "test_generic_xyz":                      # 20^3: the z extent does not divide into tiles; may run on one GPU
             assert "on 2 GPUs" in out and "not used" not in out, out[-2000:]
+
+
+@pytest.mark.parametrize("kind", ["pin", pytest.param("gpu", marks=pytest.mark.gpu)])
+def test_type_converting_definitions(kind, tmp_path):
+    # tests/cpp/cast_check.cpp: cast<float>(image16(x,y)) (apps/DoG/diff_gauss.cpp:66-73) and image16 * 0.5f run as float filters
+    rc, out = run(kind, "cast_check", [], cwd=tmp_path)
+    assert rc == 0 and out.count(": 0 mismatches") == 2, out[-2000:]
