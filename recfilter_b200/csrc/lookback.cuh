@@ -477,9 +477,9 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     mbar_wait(bar, 0);
 
     // scan the row from / to shared memory, 32 samples (one box) at a time; h: history in, tail out
-    auto scan_row = [&](CT (&h)[R], auto store) {
+    auto scan_row = [&](CT (&h)[R], auto store, const int first_chunk) {
 #pragma unroll 1
-        for (int cc = 0; cc < NBOX; ++cc) {
+        for (int cc = first_chunk; cc < NBOX; ++cc) {
             const int c = causal ? cc : NBOX - 1 - cc;
             CT v[32];
 #pragma unroll
@@ -511,7 +511,9 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     CT h[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) h[k] = (CT)0;
-    scan_row(h, std::false_type());                               // pass 0: the row's own tail
+    // pass 0: the row's own tail.  Short-memory filters: the tail does not see the first chunks of the row (their
+    // weight in it is below 1e-12, decided by the planner from the fp64 impulse response), so they are not scanned
+    scan_row(h, std::false_type(), p.pass0_first_chunk);
 
     // ---- inclusive scan over the rows of the warp (Kogge-Stone), difference basis ----
     CT T[R];
@@ -558,7 +560,13 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     CT X[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) X[k] = (CT)0;
-    if (pos != 0) {
+    if (p.depth1) {
+        // short memory across a whole tile (|Q| < 1e-12: any stable filter whose poles are not within ~1e-3 of the unit
+        // circle): the carry entering the tile is the aggregate of the tile before it, nothing further back counts
+        // -- one record to wait for, no inclusive vectors
+        if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
+        if (pos != 0) lb_wait_record<CT, R>(recs + (size_t)(t - 1) * LB_SIGNAL_REC_CHUNKS, X, p.epoch, p.err);
+    } else if (pos != 0) {
         if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
         for (uint32_t round = 0; ; ++round) {
             const uint32_t dist = round * (uint32_t)ROWS + (uint32_t)tid + 1u;
@@ -613,7 +621,7 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
             if (any_incl || round * (uint32_t)ROWS + (uint32_t)ROWS >= pos) break;
         }
     }
-    if (!last_of_signal && tid == 0) {
+    if (!p.depth1 && !last_of_signal && tid == 0) {
         lb_matvec_acc<CT, R>(E, p.Q, X);                                     // completed tail of the tile
         lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_inc);
     }
@@ -629,7 +637,7 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     }
     fdiff_inv<CT, R>(h);
 
-    scan_row(h, std::true_type());                                // pass 1: from the carry, scaled, stored
+    scan_row(h, std::true_type(), 0);                             // pass 1: from the carry, scaled, stored
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {

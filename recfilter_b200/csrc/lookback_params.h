@@ -63,6 +63,8 @@ struct LBSignalParams {
     void* rec;                    // [tile] records of LB_SIGNAL_REC_CHUNKS 16-byte chunks ((R + 2) / 3 used): aggregate, then inclusive
     uint32_t epoch;
     int prefetch;                 // > 0: L2 prefetch of the tile `prefetch` tickets ahead
+    int pass0_first_chunk;        // short-memory filters: the first chunks (32 samples each) of a row do not reach its tail
+    int depth1;                   // short memory across a whole tile: the carry is the previous tile's aggregate
     uint32_t* ticket;
     uint32_t* err;
 };

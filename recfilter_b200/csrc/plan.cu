@@ -1626,6 +1626,28 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
         sp.Plane = (const CT*)dPlane.p; sp.Qpow = (const CT*)dQpow.p;
         sp.rec = dRec.p;
         sp.ticket = (uint32_t*)this->dCtl.p; sp.err = (uint32_t*)this->dCtl.p + 1;
+        // ---- short-memory specialisations, decided from fp64 bounds (RFB_NO_SHORT_MEMORY=1: off) ----
+        sp.pass0_first_chunk = 0; sp.depth1 = 0;
+        if (std::is_same<CT, float>::value && !(getenv("RFB_NO_SHORT_MEMORY") && atoi(getenv("RFB_NO_SHORT_MEMORY")))) {
+            // (a) weight of sample i of a row (scan order) in the row's tail: L[k][i]; chunks whose weights are all below
+            //     1e-12 of the largest one are skipped by pass 0
+            std::vector<HT> cf = coeff_vec<HT>(scan, R, true);
+            double lmax = 0.0, cmax[4] = { 0, 0, 0, 0 };
+            for (int i = 0; i < ts; ++i) {
+                std::vector<HT> v(ts, (HT)0), hh(R, (HT)0);
+                v[i] = (HT)1;
+                sim_scan<HT>(v, ts, hh, cf, true, false, true);
+                for (int k = 0; k < R; ++k) { const double a = std::fabs((double)hh[k]); lmax = std::max(lmax, a); cmax[i / 32] = std::max(cmax[i / 32], a); }
+            }
+            while (sp.pass0_first_chunk < 3 && cmax[sp.pass0_first_chunk] < 1e-12 * lmax) ++sp.pass0_first_chunk;
+            // (b) transition of a whole tile
+            double qmax = 0.0;
+            for (const HT& q : Q) qmax = std::max(qmax, std::fabs((double)q));
+            std::vector<HT> Qd = Q;
+            FusedPass<CT, R>::conjugate_blocks(Qd);
+            for (const HT& q : Qd) qmax = std::max(qmax, std::fabs((double)q));
+            if (qmax < 1e-12) sp.depth1 = 1;
+        }
         sp.prefetch = 0;                                                    // optional L2 prefetch distance (measured: no gain)
         if (const char* e = getenv("RFB_LB_PREFETCH")) sp.prefetch = atoi(e);
         return RF_OK;
@@ -1643,8 +1665,10 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
         char b[512];
         snprintf(b, sizeof(b),
                  "  single-pass look-back signal pass: %lld signals x %lld rows of %d samples (thread per row, %d rows per CTA, "
-                 "%d CTAs per signal), 1 %s scan of order<=%d, 1 launch, 8 B/sample\n",
-                 (long long)nsig, (long long)M, ts, tile_rows, sp.tiles_per_signal, scan.causal ? "causal" : "anticausal", R);
+                 "%d CTAs per signal), 1 %s scan of order<=%d, 1 launch, 8 B/sample%s%s\n",
+                 (long long)nsig, (long long)M, ts, tile_rows, sp.tiles_per_signal, scan.causal ? "causal" : "anticausal", R,
+                 sp.pass0_first_chunk ? (", short memory: the tail pass skips " + std::to_string(32 * sp.pass0_first_chunk) + " samples per row").c_str() : "",
+                 sp.depth1 ? ", carries from the previous tile only" : "");
         return b;
     }
 };

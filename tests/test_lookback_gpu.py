@@ -218,3 +218,30 @@ def test_c4_audio_full_size(oracle):
     scale = float(dst2.abs().max())
     assert float((dst - dst2).abs().max()) / scale <= 2 * TOL
     plan.close(); two.close()
+
+
+def test_short_memory_specialisations_equal_the_general_path(oracle):
+    """Short-memory filters: the tail pass skips the chunks of a row that do not reach its tail, and the carry of a
+    tile is the aggregate of the tile before it (both decided from fp64 bounds < 1e-12).  Same result as the general
+    path (RFB_NO_SHORT_MEMORY=1) far below the tolerance; a prefix sum (pole 1) must keep the general path."""
+    a = rand_image((3, 1 << 18), np.float32, 99) - np.float32(0.5)
+    for coeff in (A8, B8, G3):
+        scans = [(0, True, coeff)]
+        plan = Plan((1 << 18, 3), "f32", [Scan(*s) for s in scans])
+        assert "carries from the previous tile only" in plan.describe(), plan.describe()
+        fast = plan.realize(a)
+        plan.close()
+        os.environ["RFB_NO_SHORT_MEMORY"] = "1"
+        try:
+            plan = Plan((1 << 18, 3), "f32", [Scan(*s) for s in scans])
+            assert "previous tile only" not in plan.describe() and "short memory" not in plan.describe()
+            general = plan.realize(a)
+            plan.close()
+        finally:
+            os.environ.pop("RFB_NO_SHORT_MEMORY", None)
+        assert rel_err(fast, general) <= 2e-7, rel_err(fast, general)
+        truth = oracle.apply_filter(a.astype(np.float64), scans, threads=8)
+        assert rel_err(fast, truth) <= TOL
+    plan = Plan((1 << 18, 3), "f32", [Scan(0, True, [1.0, 1.0])])
+    assert "previous tile only" not in plan.describe() and "short memory" not in plan.describe(), plan.describe()
+    plan.close()
