@@ -42,7 +42,7 @@ import numpy as np  # noqa: E402
 
 W = H = 8192
 SIGMA, ORDER = 5.0, 3
-BATCH = 4
+BATCH = 8
 METRIC = "Gsamples/s and % of HBM roofline for 2-D r=3 Gaussian 8192^2 fp32"
 WORKLOAD = "apps/gaussian: 3rd-order VYV Gaussian sigma=5, +x,-x,+y,-y, clamped border, 8192x8192 fp32"
 

@@ -215,6 +215,36 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// tile position class along a dimension
+__device__ __forceinline__ int ftile_variant(int j, int nb)
+{
+    if (nb == 1) return V_SINGLE;
+    if (j == 0) return V_FIRST;
+    if (j == nb - 1) return V_LAST;
+    return V_INTERIOR;
+}
+
+// y = D^-1 (M' (D c)): same-dimension residual of scan 0's carry in the tail of scan 1, M' = m[(var*S + 0)*S + 1]
+template <typename CT, int R>
+__device__ __forceinline__ void flocal_residual(const CT* m, const CT (&c)[R], CT (&y)[R])
+{
+    CT d[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) { d[k] = c[k]; y[k] = (CT)0; }
+#pragma unroll
+    for (int mm = 1; mm < R; ++mm)
+#pragma unroll
+        for (int k = R - 1; k >= mm; --k) d[k] = d[k - 1] - d[k];
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int kk = 0; kk < R; ++kk) y[k] = fmadd(__ldg(m + k * R + kk), d[kk], y[k]);
+#pragma unroll
+    for (int mm = R - 1; mm >= 1; --mm)
+#pragma unroll
+        for (int k = mm; k < R; ++k) y[k] = y[k - 1] - y[k];
+}
+
 // ---------------------------------------------------------------------------------------------
 // P1 / P2: the tile kernel.
 // Shared memory holds the tile as TS/32 TMA boxes of [TS rows][32 columns] (128 B rows) in the
@@ -281,6 +311,101 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     CT hn[R];                                                          // history of the next scan
 
     if constexpr (MODE == FMODE_P2) {
+      if (p.local) {
+        // ---- short-memory pass 2: the carries are derived here from the tails of the neighbouring tiles ----
+        // staging slots of R x TS words: [0, md + mx) the final carries (the layout the scan phases read), then one
+        // temporary per dimension
+        const int nfin = p.md + p.mx;
+        CT* abuf = cbuf + (nfin + 2) * R * TS;                            // [3][mx][R][sdk]: A of the three x neighbours
+        // row `tid` of the d response G (cross-dimension residual of the x tails): asked for first, used last
+        CT grow[FMAX_SCANS * R];
+        const bool crossx = p.A != nullptr && p.mx > 0 && p.md > 0;
+        if (crossx) {
+            const int vd = ftile_variant(bd, p.nbd);
+#pragma unroll
+            for (int n = 0; n < FMAX_SCANS * R; ++n)
+                grow[n] = n < p.md * R ? __ldg(p.G + (((int64_t)vd * p.md + n / R) * TS + tid) * R + n % R) : (CT)0;
+        }
+        auto stage = [&](int slot, const CT* base, int64_t idx0, int64_t kstride, bool ok) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                if (ok) cp_async4(cbuf + (slot * R + k) * TS + tid, base + idx0 + k * kstride);
+                else    cbuf[(slot * R + k) * TS + tid] = (CT)0;
+            }
+        };
+        const int dd0 = (p.md > 0 && !p.sd.causal[0]) ? -1 : 1, dd1 = (p.md > 1 && !p.sd.causal[1]) ? -1 : 1;
+        const int dx0 = (p.mx > 0 && !p.sx.causal[0]) ? -1 : 1, dx1 = (p.mx > 1 && !p.sx.causal[1]) ? -1 : 1;
+        if (p.md > 0) {
+            const int64_t ks = (int64_t)p.nbd * p.nly, ly = o * p.Nx + (int64_t)bx * TS + tid;
+            auto src = [&](int slot, int s, int t) {
+                stage(slot, p.TY, ((int64_t)s * R * p.nbd + t) * p.nly + ly, ks, col_valid && t >= 0 && t < p.nbd);
+            };
+            src(0, 0, bd - dd0);
+            if (p.md > 1) { src(1, 1, bd - dd1); src(nfin, 0, bd - dd1 - dd0); }
+        }
+        if (p.mx > 0) {
+            const int64_t ks = (int64_t)p.nbx * p.nlx, lx = o * p.Nd + (int64_t)bd * TS + tid;
+            auto src = [&](int slot, int s, int t) {
+                stage(slot, p.TX, ((int64_t)s * R * p.nbx + t) * p.nlx + lx, ks, row_valid && t >= 0 && t < p.nbx);
+            };
+            src(p.md + 0, 0, bx - dx0);
+            if (p.mx > 1) { src(p.md + 1, 1, bx - dx1); src(nfin + 1, 0, bx - dx1 - dx0); }
+            if (crossx) {
+                // A of the x neighbours bx - dx0, bx - dx1, bx - dx1 - dx0 (16-byte copies by the first threads)
+                const int per = p.mx * R * (p.sdk >> 2);                  // 16-byte chunks per tile
+                for (int i = tid; i < 3 * per; i += TS) {
+                    const int which = i / per, c = i - which * per;
+                    const int t = which == 0 ? bx - dx0 : (which == 1 ? bx - dx1 : bx - dx1 - dx0);
+                    if (t >= 0 && t < p.nbx && (which == 0 || p.mx > 1)) {
+                        const CT* g = p.A + (((o * p.nbd + bd) * (int64_t)p.nbx + t) * p.mx) * R * p.sdk + (int64_t)c * 4;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(abuf + (which * per + c) * 4)), "l"(g) : "memory");
+                    }
+                }
+            }
+        }
+        cp_async_wait_all();
+        if (crossx) __syncthreads();                                     // the A matrices were staged by other threads
+        if (p.md > 1 && col_valid) {
+            const int t1 = bd - dd1;
+            if (t1 >= 0 && t1 < p.nbd) {
+                CT c0p[R], y[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) c0p[k] = cbuf[(nfin * R + k) * TS + tid];
+                flocal_residual<CT, R>(p.Md + (((int64_t)ftile_variant(t1, p.nbd) * p.md + 0) * p.md + 1) * R * R, c0p, y);
+#pragma unroll
+                for (int k = 0; k < R; ++k) cbuf[(1 * R + k) * TS + tid] += y[k];
+            }
+        }
+        if (p.mx > 0 && row_valid) {
+            // T' = T + G_row * A[tile] for the three x sources (cross-dimension residual), then the combination along x
+            auto cross = [&](int slot, int which, int s, int t) {
+                if (!crossx || t < 0 || t >= p.nbx) return;
+                const CT* ap = abuf + (which * p.mx + s) * R * p.sdk;
+#pragma unroll
+                for (int kx = 0; kx < R; ++kx) {
+                    CT acc = cbuf[(slot * R + kx) * TS + tid];
+#pragma unroll
+                    for (int n = 0; n < FMAX_SCANS * R; ++n)
+                        if (n < p.md * R) acc = fmadd(grow[n], ap[kx * p.sdk + n], acc);
+                    cbuf[(slot * R + kx) * TS + tid] = acc;
+                }
+            };
+            cross(p.md + 0, 0, 0, bx - dx0);
+            if (p.mx > 1) {
+                cross(p.md + 1, 1, 1, bx - dx1);
+                cross(nfin + 1, 2, 0, bx - dx1 - dx0);
+                const int t1 = bx - dx1;
+                if (t1 >= 0 && t1 < p.nbx) {
+                    CT c0p[R], y[R];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) c0p[k] = cbuf[((nfin + 1) * R + k) * TS + tid];
+                    flocal_residual<CT, R>(p.Mx + (((int64_t)ftile_variant(t1, p.nbx) * p.mx + 0) * p.mx + 1) * R * R, c0p, y);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) cbuf[((p.md + 1) * R + k) * TS + tid] += y[k];
+                }
+            }
+        }
+      } else {
         // every carry this thread will need (column tid, then row tid) starts its way into shared
         // memory now, behind the tile: no load latency is left inside the scan phases
         for (int s = 0; s < p.md; ++s) {
@@ -300,6 +425,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             for (int k = 0; k < R; ++k) cp_async4(cbuf + ((p.md + s) * R + k) * TS + tid, p.CX + idx0 + k * (int64_t)p.nbx * p.nlx);
         }
         cp_async_wait_all();           // (the wait retires behind the mbarrier wait of the tile in practice)
+      }
     }
 
     if (p.md > 0) {
@@ -425,13 +551,6 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
 // global load of a scan is independent of the recurrence and issued up front, the tables live
 // in shared memory, segment tails are exchanged through shared memory.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ftile_variant(int j, int nb)
-{
-    if (nb == 1) return V_SINGLE;
-    if (j == 0) return V_FIRST;
-    if (j == nb - 1) return V_LAST;
-    return V_INTERIOR;
-}
 
 template <typename CT, int R>
 __device__ __forceinline__ void fmatvec_acc(CT (&y)[R], const CT* m, const CT (&x)[R])
@@ -919,6 +1038,41 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 
     // the d carries of this tile's columns, every d scan, in the difference basis (G is stored as G * D^-1)
     CT cy[FMAX_SCANS][R][CPL];
+    if (p.local) {
+        // short-memory d dimension: the carries are the tails of the tiles above / below (see FusedParams::local)
+#pragma unroll
+        for (int sd = 0; sd < FMAX_SCANS; ++sd)
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) cy[sd][k][c] = (CT)0;
+        const int dd0 = p.causal_d[0] ? 1 : -1, dd1 = p.causal_d[1] ? 1 : -1;
+        auto tail = [&](int s, int t, int c, CT (&x)[R]) {
+            const bool ok = t >= 0 && t < p.nbd && (int64_t)bx * TS + lane + c * 32 < p.Nx;
+#pragma unroll
+            for (int k = 0; k < R; ++k) x[k] = ok ? p.TY[((int64_t)s * R * p.nbd + t) * p.nly + k * kstride_y + ly0 + c * 32] : (CT)0;
+        };
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            CT x[R];
+            tail(0, bd - dd0, c, x);
+#pragma unroll
+            for (int k = 0; k < R; ++k) cy[0][k][c] = x[k];
+            if (p.Sd > 1) {
+                const int t1 = bd - dd1;
+                tail(1, t1, c, x);
+                if (t1 >= 0 && t1 < p.nbd) {
+                    CT c0p[R], y[R];
+                    tail(0, t1 - dd0, c, c0p);
+                    flocal_residual<CT, R>(p.Md + (((int64_t)ftile_variant(t1, p.nbd) * p.Sd + 0) * p.Sd + 1) * R * R, c0p, y);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) x[k] = x[k] + y[k];
+                }
+#pragma unroll
+                for (int k = 0; k < R; ++k) cy[1][k][c] = x[k];
+            }
+        }
+    } else {
 #pragma unroll
     for (int sd = 0; sd < FMAX_SCANS; ++sd)
 #pragma unroll
@@ -927,6 +1081,7 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
             for (int c = 0; c < CPL; ++c)
                 cy[sd][k][c] = (sd < p.Sd && (int64_t)bx * TS + lane + c * 32 < p.Nx)      // columns of a partial tile
                                    ? p.CY[((int64_t)sd * R * p.nbd + bd) * p.nly + k * kstride_y + ly0 + c * 32] : (CT)0;
+    }
 #pragma unroll
     for (int sd = 0; sd < FMAX_SCANS; ++sd)
 #pragma unroll

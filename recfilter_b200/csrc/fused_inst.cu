@@ -37,7 +37,7 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     const int64_t nblocks = (int64_t)p.nbx * p.nbd * (p.No_launch > 0 ? p.No_launch : p.No);
     if (nblocks <= 0) return cudaSuccess;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const size_t smem = fused_tile_smem_bytes(TS, mode == FMODE_P2 ? (p.mx + p.md) * R * TS : 0);
+    const size_t smem = fused_tile_smem_bytes(TS, mode == FMODE_P2 ? fused_p2_carry_words(p.mx, p.md, R, TS, p.local, p.sdk) : 0);
     static bool attr_set_dev[RFB_MAX_DEVICES] = {};
     int dev = 0;
     { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }

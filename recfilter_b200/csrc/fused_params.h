@@ -40,6 +40,14 @@ struct FusedParams {
     // row before it, sig_rows rows make one signal (only its first / last row is closed), md = 0, nbx = 1
     int signal;
     int64_t sig_rows;
+    // short-memory pass 2 (local != 0; at most two scans per dimension): the carries entering the tile are derived
+    // from the TAILS of the neighbouring tiles on the fly -- no carry kernels ran, CX / CY are not read:
+    //   C_0 = T'_0[tile before],  C_1 = T'_1[tile before] + M[0 -> 1] * C_0[there],  T' = T + G_row * A[tile] along x
+    int local;
+    const CT* Mx; const CT* Md;   // [V][S][S][R][R]  same-dimension residual, difference basis
+    const CT* A;                  // [tile][sx][kx][sdk]  cross-dimension residual (fcrossA_kernel) or null
+    const CT* G;                  // [V][Sd][ts][R]
+    int sdk;
     FusedScanTab<CT, R> sx, sd;
 };
 
@@ -88,6 +96,11 @@ struct FCrossParams {
     const CT* L;                  // [V][Sx][R][TS]
     int64_t Nx, Nd, No; int nbx, nbd; int Sx, Sd; int sdk; int64_t nly, nlx;
     int64_t w0, w1;               // tiles [w0, w1) are handled by this launch (w1 == 0: all of them)
+    // short-memory d dimension (local != 0): CY is not read; the d carries are derived from the d tails TY of the
+    // tiles above / below on the fly (see FusedParams::local)
+    int local;
+    const CT* TY; const CT* Md;
+    int causal_d[2];
 };
 
 // dynamic shared memory of one chain block (layout in fchain_kernel)
@@ -107,6 +120,12 @@ inline size_t fchain_smem_bytes(int S, int nseg, int R, int L, int nb, int sdk_i
 
 // dynamic shared memory of one tile CTA: the swizzled boxes, alignment slack, the mbarrier
 // (pass 2 adds the staged carries of the tile: nscans * R * ts words)
+// staged carries of a pass-2 CTA: one slot of R x ts words per scan; the short-memory variant adds one temporary per
+// dimension and the A matrices of three x neighbours
+inline int fused_p2_carry_words(int mx, int md, int R, int ts, int local, int sdk)
+{
+    return local ? (mx + md + 2) * R * ts + 3 * mx * R * sdk : (mx + md) * R * ts;
+}
 inline size_t fused_tile_smem_bytes(int ts, int carry_words = 0) { return (size_t)ts * ts * 4 + 1024 + 16 + (size_t)carry_words * 4; }
 
 // TMA descriptor of a dense [rows][Nx] matrix of 4-byte elements, box = 32 columns x ts rows, 128 B swizzle

@@ -838,6 +838,8 @@ struct FusedPass : PassBase {
     int nsegx = 1, nsegd = 1;
     int Lx = FCHAIN_L, Ld = FCHAIN_L;            // tiles per chain thread
     bool local_x = false, local_d = false;       // short-memory dimension: carries from the adjacent tile only (flocal_kernel)
+    bool local_p2 = false;                       // ... in every scanned dimension: pass 2 derives its carries itself, no carry kernels
+    bool local_now = false;                      // the carry stage of the call in flight took that path
     DevBuf TX, CX, TY, CY, dA;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
     DevBuf dExt, dTailOut, dW, dWact;       // dW: response of the strip's carries to what enters it (build_strip_response)
@@ -860,7 +862,7 @@ struct FusedPass : PassBase {
     int launches() const override
     {
         int n = 1;
-        if (needs_carries()) n += 1 + (d_needs() ? 1 : 0) + (cross_needed() ? 1 : 0) + (x_needs() ? 1 : 0);
+        if (needs_carries()) n += 1 + (cross_needed() ? 1 : 0) + (local_p2 ? 0 : (d_needs() ? 1 : 0) + (x_needs() ? 1 : 0));
         return n * nslices;
     }
 
@@ -1016,6 +1018,20 @@ struct FusedPass : PassBase {
             CUDA_TRY(cudaMemset(dA.p, 0, n));
         }
         fp.TX = (CT*)TX.p; fp.CX = (const CT*)CX.p; fp.TY = (CT*)TY.p; fp.CY = (const CT*)CY.p;
+        // short memory in every scanned dimension: pass 2 can derive the carries entering a tile from the tails of the
+        // neighbouring tiles (FusedParams::local), so that no carry kernel is launched at all -- P1, the cross residual
+        // A (from the tails), P2.  Needs full tiles, an unsharded pass, and the larger staging area must still allow
+        // three CTAs per SM.  OFF by default (RFB_LOCAL_P2=1 turns it on): measured on 8192^2, the carry stage shrinks
+        // from 30 to 19 us per image but pass 2 -- which is bound by the bytes its three CTAs per SM keep in flight --
+        // pays for every instruction in front of its scans: 94.6 -> 114 us for one image, 159.9 against 157.3 us per image
+        // in a stack of four.  Bit-for-bit checked against the chained carries (tests/test_fused_gpu.py).
+        {
+            const bool off = !(getenv("RFB_LOCAL_P2") && atoi(getenv("RFB_LOCAL_P2")) != 0);
+            const size_t smem = fused_tile_smem_bytes(ts, fused_p2_carry_words(fp.mx, fp.md, R, ts, 1, sdk()));
+            const int per_sm = ts == 128 ? 3 : 6;
+            local_p2 = !off && needs_carries() && !d_open() && (fp.mx == 0 || local_x || gx.nb == 1) && (fp.md == 0 || local_d || gd.nb == 1) &&
+                       fp.mx <= 2 && fp.md <= 2 && Nx % ts == 0 && Nd % ts == 0 && (smem + 1024) * per_sm <= 233472;
+        }
         return init_pipeline();
     }
 
@@ -1171,6 +1187,25 @@ struct FusedPass : PassBase {
     int run_carries(const void* ext_d, void* tail_out_d, cudaStream_t st, int stage) override
     {
         if (!needs_carries()) return RF_OK;
+        local_now = local_p2 && stage == 0 && !ext_d && !tail_out_d;
+        if (local_now) {
+            // no carry kernels: only the cross-dimension residual A, from the d tails
+            if (cross_needed()) {
+                FCrossParams<CT, R> cr;
+                std::memset(&cr, 0, sizeof(cr));
+                cr.CY = (const CT*)CY.p; cr.A = (CT*)dA.p; cr.L = (const TT*)dL.p;
+                cr.Nx = fp.Nx; cr.Nd = fp.Nd; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md;
+                cr.sdk = sdk();
+                cr.nly = fp.nly; cr.nlx = fp.nlx;
+                cr.local = 1; cr.TY = (const CT*)TY.p; cr.Md = (const TT*)dMd.p;
+                for (int s2 = 0; s2 < fp.md && s2 < 2; ++s2) cr.causal_d[s2] = sd[s2].causal;
+                if (sl_b > sl_a) { cr.w0 = sl_a * (int64_t)gx.nb * gd.nb; cr.w1 = sl_b * (int64_t)gx.nb * gd.nb; }
+                cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
+                CUDA_TRY((FLaunch<CT, R>::cross(cr, ts, st)));
+                if (timer) timer->end(st, ev);
+            }
+            return RF_OK;
+        }
         // strip sharding: stage 1 chains the strip with zero carries entering it, keeps those carries and emits the
         // outgoing tails; stage 2 does NOT chain again -- the carries are corrected by W * ext (carry_fix_kernel)
         static const bool rechain = getenv("RFB_SHARD_RECHAIN") && atoi(getenv("RFB_SHARD_RECHAIN")) != 0;   // old scheme, for comparison
@@ -1207,6 +1242,9 @@ struct FusedPass : PassBase {
     {
         cudaEvent_t ev = timer ? timer->begin(st, ST_FINAL) : nullptr;
         fp.reverse = needs_carries() ? 1 : 0;
+        fp.local = (local_p2 && local_now) ? 1 : 0;
+        fp.Mx = (const TT*)dMx.p; fp.Md = (const TT*)dMd.p; fp.sdk = sdk();
+        fp.A = cross_needed() ? (const CT*)dA.p : nullptr; fp.G = (const TT*)dG.p;
         CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P2, ts, st)));
         if (timer) timer->end(st, ev);
         return RF_OK;
@@ -1233,7 +1271,8 @@ struct FusedPass : PassBase {
                  "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), launches %d%s\n",
                  (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
                  launches(), (std::string(nslices > 1 ? " (stack pipelined in " + std::to_string(nslices) + " slices: carry stages on a side stream)" : "") +
-                              ((local_d || (local_x && !cross_needed())) ? std::string(" (short-memory carries, no chain, along") + (local_d ? " d" : "") + ((local_x && !cross_needed()) ? " x" : "") + ")" : "")).c_str());
+                              (local_p2 ? std::string(" (short memory: pass 2 derives its carries from the neighbouring tiles' tails, no carry kernels)") :
+                               (local_d || (local_x && !cross_needed())) ? std::string(" (short-memory carries, no chain, along") + (local_d ? " d" : "") + ((local_x && !cross_needed()) ? " x" : "") + ")" : std::string(""))).c_str());
         return b;
     }
 };

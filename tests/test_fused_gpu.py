@@ -372,29 +372,44 @@ def test_ragged_single_dimension_and_volume(oracle):
 
 # ---- short-memory dimensions: carries from the adjacent tile only (flocal_kernel), no chain ----
 def test_short_memory_carries_equal_chained_carries(oracle):
-    """sigma = 5 over 128-sample tiles: the tile transition matrix is ~6e-13, the planner drops the chain.  The
-    result must agree with the chained one (RFB_NO_LOCAL_CARRY=1) far below the fp32 tolerance, and with the oracle."""
+    """sigma = 5 over 128-sample tiles: the tile transition matrix is ~6e-13.  The planner then (a) lets pass 2 derive
+    its carries from the neighbouring tiles' tails -- no carry kernels at all (RFB_LOCAL_P2=1; measured slower, off by
+    default) --, or (b) replaces the d chain by one streaming launch (the default).  Both must agree with the chained result (RFB_NO_LOCAL_CARRY=1) to
+    fp32 rounding, and with the oracle within the tolerance."""
     import os
+
+    def realize(shape, border, env, expect, scans=C3):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            plan = Plan(shape[::-1], "f32", [Scan(*s) for s in scans], border, engine="twopass")
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        d = plan.describe()
+        assert (expect in d) if expect else ("short" not in d), d
+        out = plan.realize(a)
+        plan.close()
+        return out
+
     for shape, border in (((2048, 2560), "clamp"), ((2560, 2048), "zero")):       # >= 296 tiles of 128: the planner keeps 128-sample tiles
         a = rand_image(shape, np.float32, 4711)
-        plan = Plan(shape[::-1], "f32", [Scan(*s) for s in C3], border, engine="twopass")
-        assert "short-memory carries" in plan.describe(), plan.describe()
-        fast = plan.realize(a)
-        plan.close()
-        os.environ["RFB_NO_LOCAL_CARRY"] = "1"
-        try:
-            plan = Plan(shape[::-1], "f32", [Scan(*s) for s in C3], border, engine="twopass")
-            assert "short-memory carries" not in plan.describe()
-            chained = plan.realize(a)
-            plan.close()
-        finally:
-            os.environ.pop("RFB_NO_LOCAL_CARRY", None)
-        assert rel_err(fast, chained) <= 8e-6, rel_err(fast, chained)      # two fp32 evaluations of the same carries, each ~3e-6 from the truth
+        fast = realize(shape, border, {"RFB_LOCAL_P2": "1"}, "no carry kernels")
+        mid = realize(shape, border, {}, "short-memory carries, no chain, along d")
+        chained = realize(shape, border, {"RFB_NO_LOCAL_CARRY": "1"}, None)
         truth = oracle.apply_filter(a.astype(np.float64), C3, border, threads=8)
-        assert rel_err(fast, truth) <= TOL
+        for out in (fast, mid):
+            assert rel_err(out, chained) <= 8e-6, rel_err(out, chained)      # fp32 evaluations of the same carries, each ~3e-6 from the truth
+            assert rel_err(out, truth) <= TOL
+    # single-dimension and mixed-direction filters through the same path
+    a = rand_image((2048, 2560), np.float32, 4712)
+    for scans in ([(1, False, G3), (1, True, G2)], [(0, True, G3), (0, False, G3)], [(0, False, G2), (1, True, G3), (1, False, G3)]):
+        fast = realize((2048, 2560), "clamp", {"RFB_LOCAL_P2": "1"}, "no carry kernels", scans)
+        truth = oracle.apply_filter(a.astype(np.float64), scans, "clamp", threads=8)
+        assert rel_err(fast, truth) <= TOL, (scans, rel_err(fast, truth))
     # a long-memory filter keeps the chain
     wide = gaussian_weights(25.0, 3)
     plan = Plan((512, 512), "f32", [Scan(0, True, wide), Scan(0, False, wide), Scan(1, True, wide), Scan(1, False, wide)], "clamp",
                 engine="twopass")
-    assert "short-memory carries" not in plan.describe()
+    assert "short" not in plan.describe()
     plan.close()
