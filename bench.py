@@ -242,6 +242,19 @@ def other_configs(N, rank, barrier, peak, exchange):
 
     sat = [Scan(0, True, [1, 1]), Scan(1, True, [1, 1])]
     if N == 1:
+        # the headline filter on ONE image per call (the step of the headline number is a stack of images)
+        plan = Plan((W, H), "f32", [Scan(*s) for s in scans_c3()], "clamp")
+        src = [torch.rand(W * H, device="cuda") for _ in range(2)]
+        dst = torch.empty_like(src[0])
+        state = {"i": 0}
+
+        def one():
+            i = state["i"] = (state["i"] + 1) % 2
+            plan.execute(src[i], dst)
+        ms = _time_calls(one, 40, barrier, dist, 1)
+        entry("C3 Gaussian 8192^2, one image per call", W * H, ms, 1, plan.describe().splitlines()[1].strip()[:140], plan.num_launches)
+        plan.close()
+        del src, dst
         for name, ext, dt, tdt in (("C1 summed-area table 2048^2 u32", (2048, 2048), "u32", torch.int32),
                                    ("C2 box-filter integral image 4096^2 f32", (4096, 4096), "f32", torch.float32)):
             plan = Plan(ext, dt, sat)

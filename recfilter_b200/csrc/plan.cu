@@ -2009,8 +2009,10 @@ static int lookback_tile_size(const rf_plan* plan, const std::vector<HostScan>& 
 {
     if (!lookback_allowed(plan) || plan->R > 4) return 0;
     if (sx.size() > 1 || sd.size() > 1 || (sx.empty() && sd.empty())) return 0;
+    double gain = 1.0;
     for (const auto* v : { &sx, &sd })
-        for (const HostScan& h : *v) if (!unit_ff_ok(plan, h)) return 0;
+        for (const HostScan& h : *v) { if (!unit_ff_ok(plan, h)) return 0; gain *= std::fabs((double)h.coeff[0]); }
+    if (plan->is_float && !(gain > 1e-24 && gain < 1e24)) return 0;      // unit feed-forward form: see fused_tile_size
     const char* force = getenv("RFB_LB_TS");
     for (int ts : { 128, 64 }) {
         if (force && atoi(force) != ts) continue;
@@ -2083,6 +2085,15 @@ static int fused_tile_size(const rf_plan* plan, const std::vector<HostScan>& sx,
                 if (h.coeff[0] == 0.f || !std::isfinite((float)inv)) return 0;
             } else if (cvt_coeff<uint32_t>(h.coeff[0]) != 1u) return 0;
         }
+    // the fused kernels run every scan with unit feed-forward and apply the product of the feed-forward coefficients
+    // once at the store: the intermediates grow by prod |1 / b0| (two fused wide Gaussians reach 1e36).  Outside a safe
+    // range the pass takes the generic engine, which keeps every scan in its own scale.
+    if (plan->is_float) {
+        double gain = 1.0;
+        for (const auto* v : { &sx, &sd })
+            for (const HostScan& h : *v) gain *= std::fabs((double)h.coeff[0]);
+        if (!(gain > 1e-24 && gain < 1e24)) return 0;
+    }
     const char* force = getenv("RFB_FUSED_TS");          // development knob: force a tile size
     static const bool ragged_ok = !(getenv("RFB_NO_RAGGED") && atoi(getenv("RFB_NO_RAGGED")) != 0);
     const bool sharded = opt.open_lo || opt.open_hi;

@@ -265,17 +265,20 @@ void linearize(const RecFilterContents& c, const Expr& e, const IndexEnv& env, d
                 }
                 stride *= (size_t)t.image->extent[i];
             }
-            static std::map<std::pair<BufferData*, size_t>, std::shared_ptr<BufferData>> views;   // one view per plane
+            // one view per plane, so that two taps of the same plane are "the same image"; the table holds weak
+            // references (a view lives as long as a filter reads it, and keeps its parent image alive that long)
+            static std::map<std::pair<BufferData*, size_t>, std::weak_ptr<BufferData>> views;
+            for (auto it = views.begin(); it != views.end(); ) it = it->second.expired() ? views.erase(it) : std::next(it);
             auto key = std::make_pair(t.image.get(), off);
-            auto it = views.find(key);
-            if (it == views.end()) {
-                auto v = std::make_shared<BufferData>();
+            std::shared_ptr<BufferData> v = views.count(key) ? views[key].lock() : nullptr;
+            if (!v) {
+                v = std::make_shared<BufferData>();
                 v->type = t.image->type; v->dims = (int)c.dims.size();
                 for (size_t i = 0; i < c.dims.size(); ++i) v->extent[i] = t.image->extent[i];
                 v->parent = t.image; v->parent_offset = off * (size_t)t.image->type.bytes();
-                it = views.emplace(key, v).first;
+                views[key] = v;
             }
-            t.image = it->second;
+            t.image = v;
             nidx = c.dims.size();
         }
         for (size_t i = 0; i < nidx; ++i) t.idx.push_back(eval_index(c, n.args[i], env));
@@ -451,7 +454,11 @@ void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in)
             if (!c.dev_tmp) engine_check(rf_malloc(&c.dev_tmp, bytes), "rf_malloc");
             dst = c.dev_tmp;
         }
-        if (f.side_image && !f.dev_side) f.dev_side = upload_image(f, *f.side_image);   // stays resident
+        if (f.side_image) {
+            // uploaded for every evaluation, like the primary image: the caller may have changed it between realize() calls
+            if (f.dev_side) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(f.dev_side), "rf_free"); f.dev_side = nullptr; }
+            f.dev_side = upload_image(f, *f.side_image);
+        }
         engine_check(rf_stencil_execute((int)c.dims.size(), ext, engine_dtype(c.type), (int)f.stencil.size(), f.stencil.data(),
                                         f.stencil_scale, in, f.dev_side, dst, nullptr), "rf_stencil_execute");
         if (scans.empty()) return c.dev_out;

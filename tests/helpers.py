@@ -55,3 +55,11 @@ def rand_image(shape, dtype, seed):
         info = np.iinfo(dtype)
         return rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
     return rng.random(size=shape, dtype=np.float32).astype(dtype)
+
+
+def ref_metric_percent(out, ref):
+    """The reference's own error metric, lib/recfilter.h:818-825: max over samples of 100 * |ref - out| / (ref + 1e-9)
+    (no abs on ref: meant for positive images) -- a PER-SAMPLE relative error in percent."""
+    out = np.asarray(out, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float((100.0 * np.abs(ref - out) / (ref + 1e-9)).max())

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from recfilter_b200 import Plan, Scan, RecFilterError, gaussian_weights
-from helpers import rand_image, rel_err
+from helpers import rand_image, rel_err, ref_metric_percent
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +62,10 @@ def test_c3_gaussian(oracle, shape, border):
 def test_c3_full_size_8192(oracle):
     a = rand_image((8192, 8192), np.float32, 2)
     out = check_float(oracle, a, C3, "clamp")
+    # the reference's own per-sample metric (lib/recfilter.h:818-825) beside the scale-relative one: the image is
+    # positive (uniform [0, 1) blurred: every sample is ~0.5), so the two nearly coincide; 2e-3 % = 2e-5 per sample
+    truth = oracle.apply_filter(a.astype(np.float64), C3, "clamp", threads=8)
+    assert ref_metric_percent(out, truth) <= 2e-3, ref_metric_percent(out, truth)
     # unit DC gain + clamped border: a constant image is a fixed point, at full size too
     c = run(np.full((8192, 8192), 0.625, np.float32), C3, "clamp")
     np.testing.assert_allclose(c, 0.625, rtol=3e-4)
@@ -413,3 +417,19 @@ def test_short_memory_carries_equal_chained_carries(oracle):
                 engine="twopass")
     assert "short" not in plan.describe()
     plan.close()
+
+
+def test_tiny_feed_forward_products_leave_the_unit_feed_forward_kernels(oracle):
+    """Two cascaded wide Gaussians per dimension: prod |b0| ~ 1e-37, i.e. intermediates of ~1e37 in the unit
+    feed-forward form of the fused kernels.  The planner must hand such a pass to the generic engine (every scan in
+    its own scale): finite output, within tolerance of the oracle."""
+    w = gaussian_weights(60.0, 3)
+    scans = [(0, True, w), (0, False, w), (0, True, w), (0, False, w), (1, True, w), (1, False, w), (1, True, w), (1, False, w)]
+    a = rand_image((512, 640), np.float32, 77)
+    plan = Plan((640, 512), "f32", [Scan(*s) for s in scans], "clamp")
+    assert "fused pass" not in plan.describe(), plan.describe()
+    out = plan.realize(a)
+    plan.close()
+    truth = oracle.apply_filter(a.astype(np.float64), scans, "clamp", threads=8)
+    assert np.isfinite(out).all()
+    assert rel_err(out, truth) <= 1e-4, rel_err(out, truth)       # sigma 60, order 3, eight scans: the cancellation-prone corner
