@@ -10,6 +10,8 @@ every compute call raises.
 """
 from .capi import (  # noqa: F401
     Plan,
+    MultiGpuPlan,
+    Exchange,
     Scan,
     RecFilterError,
     lib,
@@ -26,7 +28,7 @@ from .filters import (  # noqa: F401
 )
 
 __all__ = [
-    "Plan", "Scan", "RecFilterError", "lib", "lib_path", "device_count", "DTYPES",
+    "Plan", "MultiGpuPlan", "Exchange", "Scan", "RecFilterError", "lib", "lib_path", "device_count", "DTYPES",
     "exported_symbols", "gaussian_weights", "integral_image_coeff",
     "overlap_feedback_coeff", "gaussian_box_filter",
 ]

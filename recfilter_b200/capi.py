@@ -106,6 +106,14 @@ def lib():
     L.rf_plan_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), i32]
     L.rf_clock_begin.argtypes = [vp, C.POINTER(vp)]
     L.rf_clock_end.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.rf_mgpu_create.argtypes = [C.POINTER(_Desc), i32, C.POINTER(vp)]
+    L.rf_mgpu_destroy.argtypes = [vp]
+    L.rf_mgpu_destroy.restype = None
+    L.rf_mgpu_ngpus.argtypes = [vp]
+    L.rf_mgpu_describe.argtypes = [vp, C.c_char_p, sz]
+    L.rf_mgpu_execute_host.argtypes = [vp, vp, vp]
+    L.rf_mgpu_profile.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
+    L.rf_mgpu_last_error.restype = C.c_char_p
     L.rf_xchg_create.argtypes = [sz, i32, i32, C.POINTER(vp)]
     L.rf_xchg_destroy.argtypes = [vp]
     L.rf_xchg_destroy.restype = None
@@ -168,6 +176,12 @@ class Plan:
                  shard_dim: int = -1, open_lo: bool = False, open_hi: bool = False, engine: str = "auto"):
         self._h = C.c_void_p()
         L = lib()
+        d = self._describe(extents, dtype, scans, border, tile, honor_tile, fuse_dims, shard_dim, open_lo, open_hi, engine)
+        self.size = int(np.prod(self.extents)) if self.extents else 0
+        _check(L.rf_plan_create(C.byref(d), C.byref(self._h)), "rf_plan_create")
+
+    def _describe(self, extents, dtype, scans, border, tile, honor_tile, fuse_dims, shard_dim, open_lo, open_hi, engine):
+        """Fill an rf_desc (shared with MultiGpuPlan)."""
         self.extents = tuple(int(e) for e in extents)
         self.dtype_name = _dtype_name(dtype)
         self.np_dtype = np.dtype(DTYPES[self.dtype_name][1])
@@ -209,8 +223,7 @@ class Plan:
         d.opt.engine = ENGINES[engine]
         d.opt.open_lo = 1 if open_lo else 0
         d.opt.open_hi = 1 if open_hi else 0
-        self.size = int(np.prod(self.extents)) if self.extents else 0
-        _check(L.rf_plan_create(C.byref(d), C.byref(self._h)), "rf_plan_create")
+        return d
 
     # -- life cycle -------------------------------------------------------------------------
     def close(self):
@@ -348,6 +361,48 @@ class Plan:
         _check(lib().rf_plan_stage2(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
                                     C.c_void_p(gp), int(nshards), int(rank), C.c_void_p(st)),
                "rf_plan_stage2")
+
+
+class MultiGpuPlan(Plan):
+    """One filter over `ngpus` GPUs of this process (rf_mgpu_*): the outermost dimension is cut into independent parts
+    (no scans along it) or strips (one order-r tail exchange over NVLink per call).  Host arrays in, host arrays out."""
+
+    def __init__(self, extents, dtype, scans, border: str = "zero", *, ngpus: int):
+        self._h = C.c_void_p()              # (no single-GPU plan)
+        self._m = C.c_void_p()
+        d = self._describe(extents, dtype, scans, border, None, False, -1, -1, False, False, "auto")
+        self.size = int(np.prod(self.extents)) if self.extents else 0
+        rc = lib().rf_mgpu_create(C.byref(d), int(ngpus), C.byref(self._m))
+        if rc != 0:
+            raise RecFilterError(f"rf_mgpu_create failed ({rc}): {lib().rf_mgpu_last_error().decode()}")
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(8192)
+        lib().rf_mgpu_describe(self._m, buf, len(buf))
+        return buf.value.decode()
+
+    def realize(self, array: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(array, dtype=self.np_dtype)
+        if a.size != self.size:
+            raise RecFilterError(f"array has {a.size} samples, plan expects {self.size}")
+        out = np.empty_like(a)
+        rc = lib().rf_mgpu_execute_host(self._m, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RecFilterError(f"rf_mgpu_execute_host failed ({rc}): {lib().rf_mgpu_last_error().decode()}")
+        return out
+
+    def profile_host(self, array: np.ndarray, iters: int) -> float:
+        a = np.ascontiguousarray(array, dtype=self.np_dtype)
+        ms = C.c_float()
+        rc = lib().rf_mgpu_profile(self._m, a.ctypes.data_as(C.c_void_p), int(iters), C.byref(ms))
+        if rc != 0:
+            raise RecFilterError(f"rf_mgpu_profile failed ({rc}): {lib().rf_mgpu_last_error().decode()}")
+        return float(ms.value)
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m.value:
+            lib().rf_mgpu_destroy(self._m)
+            self._m = C.c_void_p()
 
 
 class Exchange:
