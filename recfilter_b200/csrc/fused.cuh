@@ -245,6 +245,27 @@ __device__ __forceinline__ void flocal_residual(const CT* m, const CT (&c)[R], C
         for (int k = mm; k < R; ++k) y[k] = y[k - 1] - y[k];
 }
 
+// the same with M' in kernel-constant memory (no global load in front of the FMAs)
+template <typename CT, int R>
+__device__ __forceinline__ void flocal_residual_c(const CT (&m)[R * R], const CT (&c)[R], CT (&y)[R])
+{
+    CT d[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) { d[k] = c[k]; y[k] = (CT)0; }
+#pragma unroll
+    for (int mm = 1; mm < R; ++mm)
+#pragma unroll
+        for (int k = R - 1; k >= mm; --k) d[k] = d[k - 1] - d[k];
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int kk = 0; kk < R; ++kk) y[k] = fmadd(m[k * R + kk], d[kk], y[k]);
+#pragma unroll
+    for (int mm = R - 1; mm >= 1; --mm)
+#pragma unroll
+        for (int k = mm; k < R; ++k) y[k] = y[k - 1] - y[k];
+}
+
 // ---------------------------------------------------------------------------------------------
 // P1 / P2: the tile kernel.
 // Shared memory holds the tile as TS/32 TMA boxes of [TS rows][32 columns] (128 B rows) in the
@@ -371,7 +392,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
                 CT c0p[R], y[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) c0p[k] = cbuf[(nfin * R + k) * TS + tid];
-                flocal_residual<CT, R>(p.Md + (((int64_t)ftile_variant(t1, p.nbd) * p.md + 0) * p.md + 1) * R * R, c0p, y);
+                flocal_residual_c<CT, R>(p.Mld[ftile_variant(t1, p.nbd)], c0p, y);
 #pragma unroll
                 for (int k = 0; k < R; ++k) cbuf[(1 * R + k) * TS + tid] += y[k];
             }
@@ -399,7 +420,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
                     CT c0p[R], y[R];
 #pragma unroll
                     for (int k = 0; k < R; ++k) c0p[k] = cbuf[((nfin + 1) * R + k) * TS + tid];
-                    flocal_residual<CT, R>(p.Mx + (((int64_t)ftile_variant(t1, p.nbx) * p.mx + 0) * p.mx + 1) * R * R, c0p, y);
+                    flocal_residual_c<CT, R>(p.Mlx[ftile_variant(t1, p.nbx)], c0p, y);
 #pragma unroll
                     for (int k = 0; k < R; ++k) cbuf[((p.md + 1) * R + k) * TS + tid] += y[k];
                 }
@@ -1018,7 +1039,7 @@ flocal_kernel(const __grid_constant__ FLocalParams<CT, R> p)
 // Part 2 (TX[sx][kx][row] += sum_sd sum_k G[sd][row][k] * A[..]) is applied by the x chain while
 // it loads its tails, so the x tails are never rewritten in memory.
 // ---------------------------------------------------------------------------------------------
-template <typename CT, int R, int TS>
+template <typename CT, int R, int TS, bool TAILS>
 __global__ void __launch_bounds__(128)
 fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 {
@@ -1095,6 +1116,20 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
         }
 
     CT* Aout = p.A + w * ((int64_t)p.Sx * R * p.sdk);
+    // tails mode (short-memory pass 2, FusedParams::local == 2): the x tails of this tile get their cross-dimension
+    // residual G_row * A added in place -- pass 2 then reads corrected tails and needs neither A nor G.  This warp owns the
+    // tile: its 128 rows are 4 per lane; gv = the G rows of those rows (at most two d scans in this mode)
+    constexpr int NL = TAILS ? 2 * R : 1;
+    CT gv[CPL][NL];
+    constexpr bool fix_tails = TAILS;               // (p.local == 2)
+    if constexpr (TAILS) {
+        const int vd = ftile_variant(bd, p.nbd);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int n = 0; n < NL; ++n)
+                gv[c][n] = n < p.Sd * R ? __ldg(p.G + (((int64_t)vd * p.Sd + n / R) * TS + lane + c * 32) * R + n % R) : (CT)0;
+    }
     for (int q = 0; q < p.Sx; ++q) {
         CT lv[R][CPL];
 #pragma unroll
@@ -1105,6 +1140,9 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 #pragma unroll
         for (int kx = 0; kx < R; ++kx) {
             CT mine = (CT)0;                                 // lane n keeps entry n = sd * R + k
+            CT av[NL];                                       // every lane: the whole row A[q][kx][.] (butterfly sums)
+#pragma unroll
+            for (int n = 0; n < NL; ++n) av[n] = (CT)0;
 #pragma unroll
             for (int sd = 0; sd < FMAX_SCANS; ++sd) {
                 if (sd < p.Sd) {
@@ -1116,10 +1154,25 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, off);
                         if (lane == sd * R + k) mine = x;
+                        if (TAILS && sd < 2) av[(sd * R + k) % NL] = x;
                     }
                 }
             }
-            if (lane < p.sdk) Aout[((int64_t)q * R + kx) * p.sdk + lane] = mine;
+            if constexpr (!fix_tails) {
+                if (lane < p.sdk) Aout[((int64_t)q * R + kx) * p.sdk + lane] = mine;
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int row = lane + c * 32;
+                    if ((int64_t)bd * TS + row < p.Nd) {
+                        CT* tx = p.TXw + (((int64_t)q * R + kx) * p.nbx + bx) * p.nlx + o * p.Nd + (int64_t)bd * TS + row;
+                        CT acc = *tx;
+#pragma unroll
+                        for (int n = 0; n < NL; ++n) acc = fmadd(gv[c][n], av[n], acc);
+                        *tx = acc;
+                    }
+                }
+            }
         }
     }
 }

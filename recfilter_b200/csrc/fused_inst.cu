@@ -150,8 +150,13 @@ static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& pin, int ts, cudaS
     const int64_t ntiles = p.w1 - p.w0;
     if (ntiles <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((ntiles + 3) / 4);
-    if (ts == 128) return launch_pdl(fcrossA_kernel<CT, R, 128>, dim3(grid), dim3(128), 0, st, p);
-    if (ts == 64)  return launch_pdl(fcrossA_kernel<CT, R, 64>, dim3(grid), dim3(128), 0, st, p);
+    if (p.local == 2) {                                      // tails mode: the x tails are corrected in place
+        if (ts == 128) return launch_pdl(fcrossA_kernel<CT, R, 128, true>, dim3(grid), dim3(128), 0, st, p);
+        if (ts == 64)  return launch_pdl(fcrossA_kernel<CT, R, 64, true>, dim3(grid), dim3(128), 0, st, p);
+        return cudaErrorInvalidValue;
+    }
+    if (ts == 128) return launch_pdl(fcrossA_kernel<CT, R, 128, false>, dim3(grid), dim3(128), 0, st, p);
+    if (ts == 64)  return launch_pdl(fcrossA_kernel<CT, R, 64, false>, dim3(grid), dim3(128), 0, st, p);
     return cudaErrorInvalidValue;
 }
 

@@ -45,6 +45,7 @@ struct FusedParams {
     //   C_0 = T'_0[tile before],  C_1 = T'_1[tile before] + M[0 -> 1] * C_0[there],  T' = T + G_row * A[tile] along x
     int local;
     const CT* Mx; const CT* Md;   // [V][S][S][R][R]  same-dimension residual, difference basis
+    CT Mlx[V_COUNT][R * R], Mld[V_COUNT][R * R];   // M[0 -> 1] per tile variant, as kernel constants (no load latency in the prologue)
     const CT* A;                  // [tile][sx][kx][sdk]  cross-dimension residual (fcrossA_kernel) or null
     const CT* G;                  // [V][Sd][ts][R]
     int sdk;
@@ -98,9 +99,10 @@ struct FCrossParams {
     int64_t w0, w1;               // tiles [w0, w1) are handled by this launch (w1 == 0: all of them)
     // short-memory d dimension (local != 0): CY is not read; the d carries are derived from the d tails TY of the
     // tiles above / below on the fly (see FusedParams::local)
-    int local;
+    int local;                    // 1: A is stored (pass 2 applies G_row * A itself); 2: A is applied to the x tails TXw in place
     const CT* TY; const CT* Md;
     int causal_d[2];
+    CT* TXw; const CT* G;
 };
 
 // dynamic shared memory of one chain block (layout in fchain_kernel)

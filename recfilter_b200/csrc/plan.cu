@@ -840,6 +840,7 @@ struct FusedPass : PassBase {
     bool local_x = false, local_d = false;       // short-memory dimension: carries from the adjacent tile only (flocal_kernel)
     bool local_p2 = false;                       // ... in every scanned dimension: pass 2 derives its carries itself, no carry kernels
     bool local_now = false;                      // the carry stage of the call in flight took that path
+    int local_mode = 1;                          // RFB_LOCAL_P2: 1 = pass 2 applies the cross residual, 2 = the cross kernel corrects the x tails
     DevBuf TX, CX, TY, CY, dA;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
     DevBuf dExt, dTailOut, dW, dWact;       // dW: response of the strip's carries to what enters it (build_strip_response)
@@ -1018,15 +1019,24 @@ struct FusedPass : PassBase {
             CUDA_TRY(cudaMemset(dA.p, 0, n));
         }
         fp.TX = (CT*)TX.p; fp.CX = (const CT*)CX.p; fp.TY = (CT*)TY.p; fp.CY = (const CT*)CY.p;
+        // M[0 -> 1] per tile variant as kernel constants (short-memory pass 2)
+        for (int var = 0; var < V_COUNT; ++var)
+            for (int i = 0; i < R * R; ++i) {
+                fp.Mlx[var][i] = fp.mx > 1 ? (CT)tx_tab.M[((((size_t)var * fp.mx + 0) * fp.mx + 1) * R * R) + i] : (CT)0;
+                fp.Mld[var][i] = fp.md > 1 ? (CT)td_tab.M[((((size_t)var * fp.md + 0) * fp.md + 1) * R * R) + i] : (CT)0;
+            }
         // short memory in every scanned dimension: pass 2 can derive the carries entering a tile from the tails of the
         // neighbouring tiles (FusedParams::local), so that no carry kernel is launched at all -- P1, the cross residual
         // A (from the tails), P2.  Needs full tiles, an unsharded pass, and the larger staging area must still allow
         // three CTAs per SM.  OFF by default (RFB_LOCAL_P2=1 turns it on): measured on 8192^2, the carry stage shrinks
         // from 30 to 19 us per image but pass 2 -- which is bound by the bytes its three CTAs per SM keep in flight --
-        // pays for every instruction in front of its scans: 94.6 -> 114 us for one image, 159.9 against 157.3 us per image
-        // in a stack of four.  Bit-for-bit checked against the chained carries (tests/test_fused_gpu.py).
+        // pays for every instruction in front of its scans: 94.6 -> 112 us for one image (RFB_LOCAL_P2=1: pass 2 also applies
+        // the cross residual G_row * A), or 101 us with a 31 us cross kernel that corrects the x tails in place
+        // (RFB_LOCAL_P2=2); 156.5 / 158.3 against 157 us per image in a stack of eight.  Checked against the chained carries
+        // (tests/test_fused_gpu.py).
         {
             const bool off = !(getenv("RFB_LOCAL_P2") && atoi(getenv("RFB_LOCAL_P2")) != 0);
+            local_mode = (getenv("RFB_LOCAL_P2") && atoi(getenv("RFB_LOCAL_P2")) == 2) ? 2 : 1;
             const size_t smem = fused_tile_smem_bytes(ts, fused_p2_carry_words(fp.mx, fp.md, R, ts, 1, sdk()));
             const int per_sm = ts == 128 ? 3 : 6;
             local_p2 = !off && needs_carries() && !d_open() && (fp.mx == 0 || local_x || gx.nb == 1) && (fp.md == 0 || local_d || gd.nb == 1) &&
@@ -1197,7 +1207,9 @@ struct FusedPass : PassBase {
                 cr.Nx = fp.Nx; cr.Nd = fp.Nd; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md;
                 cr.sdk = sdk();
                 cr.nly = fp.nly; cr.nlx = fp.nlx;
-                cr.local = 1; cr.TY = (const CT*)TY.p; cr.Md = (const TT*)dMd.p;
+                // RFB_LOCAL_P2=1: A stored, pass 2 applies it; =2: this kernel corrects the x tails in place
+                cr.local = local_mode; cr.TY = (const CT*)TY.p; cr.Md = (const TT*)dMd.p;
+                cr.TXw = (CT*)TX.p; cr.G = (const TT*)dG.p;
                 for (int s2 = 0; s2 < fp.md && s2 < 2; ++s2) cr.causal_d[s2] = sd[s2].causal;
                 if (sl_b > sl_a) { cr.w0 = sl_a * (int64_t)gx.nb * gd.nb; cr.w1 = sl_b * (int64_t)gx.nb * gd.nb; }
                 cudaEvent_t ev = timer ? timer->begin(st, ST_CROSS) : nullptr;
@@ -1244,7 +1256,7 @@ struct FusedPass : PassBase {
         fp.reverse = needs_carries() ? 1 : 0;
         fp.local = (local_p2 && local_now) ? 1 : 0;
         fp.Mx = (const TT*)dMx.p; fp.Md = (const TT*)dMd.p; fp.sdk = sdk();
-        fp.A = cross_needed() ? (const CT*)dA.p : nullptr; fp.G = (const TT*)dG.p;
+        fp.A = (cross_needed() && local_mode == 1) ? (const CT*)dA.p : nullptr; fp.G = (const TT*)dG.p;
         CUDA_TRY((FLaunch<CT, R>::tile(fp, in, out, FMODE_P2, ts, st)));
         if (timer) timer->end(st, ev);
         return RF_OK;

@@ -399,10 +399,11 @@ def test_short_memory_carries_equal_chained_carries(oracle):
     for shape, border in (((2048, 2560), "clamp"), ((2560, 2048), "zero")):       # >= 296 tiles of 128: the planner keeps 128-sample tiles
         a = rand_image(shape, np.float32, 4711)
         fast = realize(shape, border, {"RFB_LOCAL_P2": "1"}, "no carry kernels")
+        fast2 = realize(shape, border, {"RFB_LOCAL_P2": "2"}, "no carry kernels")     # the cross kernel corrects the x tails in place
         mid = realize(shape, border, {}, "short-memory carries, no chain, along d")
         chained = realize(shape, border, {"RFB_NO_LOCAL_CARRY": "1"}, None)
         truth = oracle.apply_filter(a.astype(np.float64), C3, border, threads=8)
-        for out in (fast, mid):
+        for out in (fast, fast2, mid):
             assert rel_err(out, chained) <= 8e-6, rel_err(out, chained)      # fp32 evaluations of the same carries, each ~3e-6 from the truth
             assert rel_err(out, truth) <= TOL
     # single-dimension and mixed-direction filters through the same path
