@@ -10,7 +10,8 @@
  * (12 B/sample for 4-byte types).  Here a tile is read once and written once (8 B/sample): every CTA
  *
  *   1. takes a ticket (tiles are handed out in scan order, so every tile a CTA will ever wait for is
- *      already running or finished: no deadlock whatever the block scheduler does),
+ *      already running or finished: no deadlock whatever the block scheduler does; the ticket also carries the
+ *      number of the launch, see lb_take_ticket),
  *   2. loads its tile with TMA and scans it with zero history -> the tile's own tail ("aggregate"),
  *      published with a status word,
  *   3. looks back over its predecessors: a predecessor that already knows its completed tail
@@ -116,6 +117,24 @@ __device__ __forceinline__ uint32_t lb_wait_record(const uint4* rec, CT (&y)[R],
         }
         if (spins > 4) __nanosleep(32);
     }
+}
+
+/*
+ * Tickets come from a 64-bit counter in device memory that is never reset.  Every launch uses a ticket space of
+ * P = 2^shift >= tiles tickets: ticket >> shift is the number of the launch (the epoch of the record tags), ticket & (P-1)
+ * the tile; the CTA that draws the last tile skips the rest of the space.  One atomic gives both numbers without a
+ * division, and nothing about a launch is baked into its parameters, so a captured CUDA graph can be replayed (every
+ * replay is a new epoch).  The tickets of one launch are contiguous: a dependent launch only starts once every CTA of the
+ * launch before has taken its ticket (tickets are taken before griddepcontrol.launch_dependents).
+ */
+__device__ __forceinline__ void lb_take_ticket(unsigned long long* ctr, const uint32_t tiles, volatile uint32_t* sflag)
+{
+    const int shift = 32 - __clz(tiles - 1u);                      // P = 2^shift >= tiles (tiles >= 1; tiles == 1: shift 0)
+    const unsigned long long raw = atomicAdd(ctr, 1ull);
+    const uint32_t t = (uint32_t)(raw & ((1ull << shift) - 1ull));
+    if (t == tiles - 1u && (1ull << shift) != (unsigned long long)tiles) atomicAdd(ctr, (1ull << shift) - (unsigned long long)tiles);
+    sflag[0] = t;
+    sflag[2] = (uint32_t)((raw >> shift) % 0x3fffffffull) + 1u;    // never 0: cleared records carry tag 0
 }
 
 template <typename CT, int R, int N>
@@ -278,15 +297,16 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
     extern __shared__ __align__(16) unsigned char lbsmem_raw[];
     unsigned char* tile = lbsmem_raw + ((1024u - (smem_u32(lbsmem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tile + NBOX * BOX_BYTES);
-    volatile uint32_t* sflag = reinterpret_cast<volatile uint32_t*>(bar + 1);     // [0] ticket
+    volatile uint32_t* sflag = reinterpret_cast<volatile uint32_t*>(bar + 1);     // [0] ticket, [2] epoch of this launch
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        sflag[0] = atomicInc(p.ticket, gridDim.x - 1);      // the last ticket resets the counter
+        lb_take_ticket(p.ticket, gridDim.x, sflag);
         mbar_init(bar, 1);
     }
     __syncthreads();
     const uint32_t t = sflag[0];
+    const uint32_t epoch = sflag[2];
     pdl_launch_dependents();
     // scan-order coordinates and the tile they denote in memory
     int bxs, bds; int64_t o;
@@ -350,7 +370,7 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
     if (p.d.nscan) {
         // ---- column phase: thread tid owns column tid; predecessors are the tiles above (scan order) ----
         load_col();
-        lb_phase<CT, R, TS>(v, p.d, bds, p.nbd, sidx, (uint32_t)p.nbx, p.epoch, p.clamp != 0, p.err, tid, load_col, peek);
+        lb_phase<CT, R, TS>(v, p.d, bds, p.nbd, sidx, (uint32_t)p.nbx, epoch, p.clamp != 0, p.err, tid, load_col, peek);
         const CT g = p.x.nscan ? (CT)1 : p.gain;
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
@@ -365,7 +385,7 @@ lb_tile_kernel(const __grid_constant__ LBTileParams<CT, R> p, const __grid_const
             lb_load_record<R>(reinterpret_cast<const uint4*>(p.x.rec) + ((size_t)(sidx - 1u) * TS + tid) * NCH, peek);
         if (p.d.nscan) __syncthreads();
         load_row();
-        lb_phase<CT, R, TS>(v, p.x, bxs, p.nbx, sidx, 1u, p.epoch, p.clamp != 0, p.err, tid, load_row, peek);
+        lb_phase<CT, R, TS>(v, p.x, bxs, p.nbx, sidx, 1u, epoch, p.clamp != 0, p.err, tid, load_row, peek);
 #pragma unroll
         for (int c4 = 0; c4 < TS / 4; ++c4) {
             uint4 q;
@@ -440,11 +460,12 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) {
-        sflag[0] = atomicInc(p.ticket, gridDim.x - 1);
+        lb_take_ticket(p.ticket, gridDim.x, sflag);
         mbar_init(bar, 1);
     }
     __syncthreads();
     const uint32_t t = sflag[0];                                  // tile index in scan order
+    const uint32_t epoch = sflag[2];
     pdl_launch_dependents();
     const bool causal = p.causal != 0;
     const uint32_t pos = t % (uint32_t)p.tiles_per_signal;        // tile of its signal, scan order
@@ -454,8 +475,8 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
     // thread order = scan order: thread tid scans row `row`, after the row of thread tid - 1
     const int row = causal ? tid : ROWS - 1 - tid;
     const bool closed = pos == 0 && tid == 0;                     // the scan starts at the signal's border here
-    const uint32_t tag_agg = (p.epoch << 2) | LB_AGGREGATE, tag_inc = (p.epoch << 2) | LB_INCLUSIVE;
     uint4* const recs = reinterpret_cast<uint4*>(p.rec);
+    const uint32_t tag_agg = (epoch << 2) | LB_AGGREGATE, tag_inc = (epoch << 2) | LB_INCLUSIVE;
 
     pdl_wait();
     if (tid == 0) {
@@ -565,7 +586,7 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
         // circle): the carry entering the tile is the aggregate of the tile before it, nothing further back counts
         // -- one record to wait for, no inclusive vectors
         if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
-        if (pos != 0) lb_wait_record<CT, R>(recs + (size_t)(t - 1) * LB_SIGNAL_REC_CHUNKS, X, p.epoch, p.err);
+        if (pos != 0) lb_wait_record<CT, R>(recs + (size_t)(t - 1) * LB_SIGNAL_REC_CHUNKS, X, epoch, p.err);
     } else if (pos != 0) {
         if (!last_of_signal && tid == 0) lb_publish<CT, R>(recs + (size_t)t * LB_SIGNAL_REC_CHUNKS, E, tag_agg);
         for (uint32_t round = 0; ; ++round) {
@@ -575,7 +596,7 @@ lb_signal_kernel(const __grid_constant__ LBSignalParams<CT, R> p, const __grid_c
             CT y[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) y[k] = (CT)0;
-            if (active) state = lb_wait_record<CT, R>(recs + (size_t)(t - dist) * LB_SIGNAL_REC_CHUNKS, y, p.epoch, p.err);
+            if (active) state = lb_wait_record<CT, R>(recs + (size_t)(t - dist) * LB_SIGNAL_REC_CHUNKS, y, epoch, p.err);
             const uint32_t incl = __ballot_sync(0xffffffffu, active && state == LB_INCLUSIVE);
             const int firsti = incl ? __ffs(incl) - 1 : 32;                  // nearest complete predecessor of the window
             CT c[R];

@@ -36,10 +36,9 @@ struct LBTileParams {
     int nbx, nbd;
     int clamp;
     CT  gain;                     // product of the feed-forward coefficients, applied at the store
-    uint32_t epoch;
     int prefetch;                 // > 0: L2 prefetch of the tile `prefetch` tickets ahead
     int rows_first;               // 1: tiles are handed out row-major instead of along anti-diagonals
-    uint32_t* ticket;             // tile counter (atomicInc, wraps to 0 with the last tile)
+    unsigned long long* ticket;   // ticket counter, never reset: ticket / tiles = launch number (epoch of the tags), % tiles = tile
     uint32_t* err;                // set to 1 if a CTA ran into LB_SPIN_LIMIT
     LBDim<CT, R> x, d;
 };
@@ -61,11 +60,10 @@ struct LBSignalParams {
     const CT* Plane;              // [R*R][32]: P^lane
     const CT* Qpow;               // [R*R][32]: Q^k
     void* rec;                    // [tile] records of LB_SIGNAL_REC_CHUNKS 16-byte chunks ((R + 2) / 3 used): aggregate, then inclusive
-    uint32_t epoch;
     int prefetch;                 // > 0: L2 prefetch of the tile `prefetch` tickets ahead
     int pass0_first_chunk;        // short-memory filters: the first chunks (32 samples each) of a row do not reach its tail
     int depth1;                   // short memory across a whole tile: the carry is the previous tile's aggregate
-    uint32_t* ticket;
+    unsigned long long* ticket;   // see LBTileParams
     uint32_t* err;
 };
 

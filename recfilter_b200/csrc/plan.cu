@@ -1472,8 +1472,7 @@ struct SignalPass : PassBase {
 template <typename CT, int R>
 struct LookbackBase : PassBase {
     using HT = typename std::conditional<std::is_same<CT, float>::value, double, uint32_t>::type;
-    DevBuf dCtl;                                   // [0] ticket counter, [1] error flag
-    uint32_t epoch = 0;
+    DevBuf dCtl;                                   // words [0,1] 64-bit ticket counter (never reset), [2] error flag
     bool needs_carries() const override { return false; }
     bool d_open() const override { return false; }
     const void* ext_buffer() const override { return nullptr; }
@@ -1484,11 +1483,11 @@ struct LookbackBase : PassBase {
     int launches() const override { return 1; }
     int run_tails(const void*, void*, cudaStream_t) override { return RF_OK; }
     int run_carries(const void*, void*, cudaStream_t, int) override { return RF_OK; }
-    const uint32_t* error_flag() const override { return dCtl.p ? (const uint32_t*)dCtl.p + 1 : nullptr; }
+    const uint32_t* error_flag() const override { return dCtl.p ? (const uint32_t*)dCtl.p + 2 : nullptr; }
     int init_ctl()
     {
-        CUDA_TRY(dCtl.alloc(2 * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemset(dCtl.p, 0, 2 * sizeof(uint32_t)));
+        CUDA_TRY(dCtl.alloc(4 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemset(dCtl.p, 0, 4 * sizeof(uint32_t)));
         return RF_OK;
     }
     // transition of one tile of `ts` samples (unit feed-forward form), raw basis
@@ -1583,7 +1582,7 @@ struct LookbackPass : LookbackBase<CT, R> {
         if ((rc = init_dim(lp.x, sx, lp.nbx, ntiles, clamp, 0, gain, gain_u))) return rc;
         if ((rc = init_dim(lp.d, sd, lp.nbd, ntiles, clamp, 1, gain, gain_u))) return rc;
         lp.gain = std::is_same<CT, float>::value ? (CT)gain : (CT)gain_u;
-        lp.ticket = (uint32_t*)this->dCtl.p; lp.err = (uint32_t*)this->dCtl.p + 1;
+        lp.ticket = (unsigned long long*)this->dCtl.p; lp.err = (uint32_t*)this->dCtl.p + 2;
         // tiles of an image are handed out along anti-diagonals of the scan-order grid (the tiles a tile waits for are
         // then a whole diagonal older; measured on the 8192^2 table: 134 vs 143 us); RFB_LB_ORDER=rows: row-major
         lp.rows_first = (getenv("RFB_LB_ORDER") && !strcmp(getenv("RFB_LB_ORDER"), "rows")) ? 1 : 0;
@@ -1595,7 +1594,6 @@ struct LookbackPass : LookbackBase<CT, R> {
     int run_final(const void* in, void* out, cudaStream_t st) override
     {
         cudaEvent_t ev = this->timer ? this->timer->begin(st, ST_FINAL) : nullptr;
-        lp.epoch = (++this->epoch % 0x3fffffffu) + 1u;
         CUDA_TRY((LBLaunch<CT, R>::tile(lp, in, out, ts, st)));
         if (this->timer) this->timer->end(st, ev);
         return RF_OK;
@@ -1676,7 +1674,7 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
         CUDA_TRY(cudaMemset(dRec.p, 0, (size_t)ntiles * LB_SIGNAL_REC_CHUNKS * 16));
         sp.Plane = (const CT*)dPlane.p; sp.Qpow = (const CT*)dQpow.p;
         sp.rec = dRec.p;
-        sp.ticket = (uint32_t*)this->dCtl.p; sp.err = (uint32_t*)this->dCtl.p + 1;
+        sp.ticket = (unsigned long long*)this->dCtl.p; sp.err = (uint32_t*)this->dCtl.p + 2;
         // ---- short-memory specialisations, decided from fp64 bounds (RFB_NO_SHORT_MEMORY=1: off) ----
         sp.pass0_first_chunk = 0; sp.depth1 = 0;
         if (std::is_same<CT, float>::value && !(getenv("RFB_NO_SHORT_MEMORY") && atoi(getenv("RFB_NO_SHORT_MEMORY")))) {
@@ -1706,7 +1704,6 @@ struct SignalLookbackPass : LookbackBase<CT, R> {
     int run_final(const void* in, void* out, cudaStream_t st) override
     {
         cudaEvent_t ev = this->timer ? this->timer->begin(st, ST_FINAL) : nullptr;
-        sp.epoch = (++this->epoch % 0x3fffffffu) + 1u;
         CUDA_TRY((LBLaunch<CT, R>::signal(sp, in, out, st)));
         if (this->timer) this->timer->end(st, ev);
         return RF_OK;

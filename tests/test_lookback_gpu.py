@@ -245,3 +245,32 @@ def test_short_memory_specialisations_equal_the_general_path(oracle):
     plan = Plan((1 << 18, 3), "f32", [Scan(0, True, [1.0, 1.0])])
     assert "previous tile only" not in plan.describe() and "short memory" not in plan.describe(), plan.describe()
     plan.close()
+
+
+def test_lookback_plans_replay_in_a_cuda_graph(oracle):
+    """Nothing about a launch is baked into the kernel parameters (the epoch of the record tags lives in device
+    memory): a captured graph of a look-back plan must give the right answer for NEW inputs on every replay."""
+    import torch
+    sat = Plan((1024, 512), "u32", [Scan(*s) for s in SAT])
+    sig = Plan((1 << 18, 4), "f32", [Scan(0, True, B8)])
+    assert "single-pass" in sat.describe() and "look-back signal pass" in sig.describe()
+    a = torch.zeros((512, 1024), device="cuda", dtype=torch.int32); ao = torch.empty_like(a)
+    b = torch.zeros((4, 1 << 18), device="cuda", dtype=torch.float32); bo = torch.empty_like(b)
+    sat.execute(a, ao); sig.execute(b, bo)                    # lazy initialisations outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        sat.execute(a, ao)
+        sig.execute(b, bo)
+    rng = np.random.default_rng(12)
+    for rep in range(4):
+        an = rng.integers(0, 1 << 31, size=(512, 1024), dtype=np.int64).astype(np.uint32)
+        bn = rng.random((4, 1 << 18), dtype=np.float32) - np.float32(0.5)
+        a.copy_(torch.from_numpy(an.view(np.int32))); b.copy_(torch.from_numpy(bn))
+        g.replay()
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(ao.cpu().numpy().view(np.uint32), oracle.apply_filter(an, SAT, threads=8))
+        truth = oracle.apply_filter(bn.astype(np.float64), [(0, True, B8)], threads=8)
+        assert rel_err(bo.cpu().numpy(), truth) <= TOL
+    sat.check(); sig.check()
+    sat.close(); sig.close()
