@@ -53,6 +53,30 @@ def scans_c3():
     return [(0, True, w3), (0, False, w3), (1, True, w3), (1, False, w3)]
 
 
+def bench_config(N: int, batch: int, strong: bool, exchange: str, graph: bool, overlap: int = 1) -> dict:
+    """The workload description of a run -- the same dict for the GPU arm and for `--impl reference` (the CPU arm reports
+    the configuration it stands beside; what it actually samples is said in its `cpu_baseline.sample`)."""
+    weak = N > 1 and not strong
+    B = batch * (N if weak else 1)
+    if N == 1:
+        sharding = "none"
+    else:
+        # ShardedFilter's rule: peer-to-peer windows on request; NCCL all-gather, two column-chunked all-to-alls from 4 ranks
+        # on when the all-gather would deliver 8 MB or more per rank (2 d scans x order 3 x 8192 columns x B strips x 4 B)
+        tail_bytes = 2 * ORDER * W * B * 4
+        chunked = exchange == "alltoall" or (exchange == "auto" and N >= 4 and tail_bytes * N >= (8 << 20))
+        how = ("peer-to-peer exchange windows over NVLink (rf_xchg_put / rf_xchg_wait)" if exchange == "p2p" else
+               "two column-chunked NCCL all-to-alls" if chunked else "one NCCL all-gather")
+        sharding = (f"every image cut into {N} row strips, one per GPU; the order-3 strip tails travel once per step ({how}); "
+                    f"{batch} images' worth of samples per GPU per step")
+    groups = overlap if (B > 1 and overlap > 1 and B % overlap == 0) else 1
+    return {"workload": WORKLOAD, "images_per_step": B, "sharding": sharding,
+            "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
+            "tile": "128x128 register tiles (fused engine)",
+            "launch": "one CUDA graph per step (captured once, replayed)" if (graph and B > 1 and exchange != "p2p") else "eager launches",
+            "streams": f"{groups} sub-stacks of {B // groups} images on their own CUDA streams" if B > 1 else "1"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -174,11 +198,8 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the GPU arm's N = 1 configuration; the CPU sample of it is one image per step
-        "config": {"workload": WORKLOAD, "images_per_step": BATCH, "sharding": "none",
-                   "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % BATCH,
-                   "tile": "128x128 register tiles (fused engine)", "streams": "1",
-                   "sample": "bounded CPU sample: one 8192x8192 image per step"},
+        # the GPU arm's configuration at this N; the CPU sample of it is one image per step (cpu_baseline.sample)
+        "config": bench_config(args.gpus, args.batch, args.strong, args.exchange, bool(args.graph), args.overlap),
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
                          "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
                          "sample": "one full 8192x8192 image per step, oracle/oracle.c serial recurrence loops, "
@@ -592,15 +613,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": N, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (N > 1 and not weak) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_step": B,
-                       "sharding": "none" if N == 1 else
-                                   f"every image cut into {N} row strips, one per GPU; the order-3 strip tails travel once per step "
-                                   f"({'peer-to-peer exchange windows over NVLink (rf_xchg_put / rf_xchg_wait)' if flt.p2p else 'two column-chunked NCCL all-to-alls' if flt.chunked else 'one NCCL all-gather'}); "
-                                   f"{args.batch} images' worth of samples per GPU per step",
-                       "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
-                       "tile": "128x128 register tiles (fused engine)",
-                       "launch": "one CUDA graph per step (captured once, replayed)" if flt.use_graph else "eager launches",
-                       "streams": f"{flt.groups} sub-stacks of {flt.sub} images on their own CUDA streams" if flt.stacked else "1"},
+            "config": bench_config(N, args.batch, args.strong, args.exchange, bool(args.graph), args.overlap),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "batch_sharded": batch_sharded,
             "strip_sharded_strong": strong, "other_configs": others,
             "gpu_launches": int(args.steps * B * launches_per_image), "clocks": clocks,

@@ -1280,7 +1280,7 @@ struct FusedPass : PassBase {
         char b[512];
         snprintf(b, sizeof(b),
                  "  fused pass view [%lld][%lld][%lld]: %dx%d register tiles, d scans %d (%d tiles) then x scans %d "
-                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), launches %d%s\n",
+                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), two sweeps: 12 B/sample, launches %d%s\n",
                  (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
                  launches(), (std::string(nslices > 1 ? " (stack pipelined in " + std::to_string(nslices) + " slices: carry stages on a side stream)" : "") +
                               (local_p2 ? std::string(" (short memory: pass 2 derives its carries from the neighbouring tiles' tails, no carry kernels)") :
@@ -1837,6 +1837,7 @@ using namespace rfb;
 
 struct rf_plan {
     rf_desc desc;
+    int device = 0;          // the device that was current at rf_plan_create: workspace, tables and launches belong to it
     int R = 1;
     bool is_float = true;
     size_t elem_bytes = 4;
@@ -2217,6 +2218,7 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
     std::unique_ptr<rf_plan> plan(new (std::nothrow) rf_plan());
     if (!plan) return fail(RF_ENOMEM, "out of host memory");
     plan->desc = *desc;
+    CUDA_TRY(cudaGetDevice(&plan->device));
     plan->R = round_order(maxr);
     plan->is_float = desc->dtype == RF_F32;
     plan->elem_bytes = eb;
@@ -2345,6 +2347,16 @@ int rf_plan_describe(const rf_plan* plan, char* buf, size_t n)
     return RF_OK;
 }
 
+// a plan may only run on the device it was created on
+static int check_device(const rf_plan* plan)
+{
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != plan->device)
+        return fail(RF_EINVAL, "the plan was created on device %d but device %d is current (rf_set_device before the call)", plan->device, dev);
+    return RF_OK;
+}
+
 static int copy_through(rf_plan* plan, const void* in_dev, void* out_dev, cudaStream_t st)
 {
     if (in_dev != out_dev && plan->total > 0)
@@ -2357,6 +2369,7 @@ int rf_plan_execute(rf_plan* plan, const void* in_dev, void* out_dev, void* stre
     if (!plan) return fail(RF_EINVAL, "null plan");
     if (plan->total == 0) return RF_OK;
     if (!in_dev || !out_dev) return fail(RF_EINVAL, "null buffer");
+    if (int drc = check_device(plan)) return drc;
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->passes.empty()) return copy_through(plan, in_dev, out_dev, st);
     const void* src = in_dev;
@@ -2487,6 +2500,7 @@ int rf_plan_stage1(rf_plan* plan, const void* in_dev, void* out_dev, void* tails
 {
     if (!plan) return fail(RF_EINVAL, "null plan");
     if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
+    if (int drc = check_device(plan)) return drc;
     cudaStream_t st = (cudaStream_t)stream;
     const void* src = in_dev;
     for (int i = 0; i <= plan->shard_pass; ++i) {
@@ -2507,6 +2521,7 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev, const void*
     if (!plan) return fail(RF_EINVAL, "null plan");
     if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
     if (nshards < 1 || shard_rank < 0 || shard_rank >= nshards) return fail(RF_EINVAL, "bad shard rank");
+    if (int drc = check_device(plan)) return drc;
     cudaStream_t st = (cudaStream_t)stream;
     const void* src = plan->shard_pass == 0 ? in_dev : out_dev;
     for (int i = plan->shard_pass; i < (int)plan->passes.size(); ++i) {
@@ -2546,6 +2561,7 @@ int rf_plan_stage2_ext(rf_plan* plan, const void* in_dev, void* out_dev, const v
     if (!plan) return fail(RF_EINVAL, "null plan");
     if (plan->shard_pass < 0) return fail(RF_EINVAL, "plan is not sharded");
     if (!ext_dev) return fail(RF_EINVAL, "null carries");
+    if (int drc = check_device(plan)) return drc;
     cudaStream_t st = (cudaStream_t)stream;
     const void* src = plan->shard_pass == 0 ? in_dev : out_dev;
     for (int i = plan->shard_pass; i < (int)plan->passes.size(); ++i) {

@@ -54,3 +54,22 @@ def test_two_gpus_equal_one_gpu(oracle, name, ext, dtype, scans, border):
     if dtype == "f32":
         truth = oracle.apply_filter(a.astype(np.float64), scans, border, threads=8)
         assert rel_err(out, truth) <= 1e-5
+
+
+def test_plan_is_bound_to_its_device():
+    """rf_plan_execute on another device than the plan's fails loudly (the kernel attributes, the workspace and the
+    tables belong to the device that was current at rf_plan_create)."""
+    need(2)
+    import torch
+    from recfilter_b200 import RecFilterError
+    rf.lib().rf_set_device(0)
+    plan = Plan((256, 256), "f32", [Scan(0, True, G3), Scan(1, False, G3)], "clamp")
+    a = torch.rand(256 * 256, device="cuda:0")
+    plan.execute(a)
+    rf.lib().rf_set_device(1)
+    try:
+        with pytest.raises(RecFilterError, match="created on device 0"):
+            plan.execute_ptr(a.data_ptr(), a.data_ptr())
+    finally:
+        rf.lib().rf_set_device(0)
+    plan.close()
