@@ -93,7 +93,12 @@ typedef struct rf_options {
     int32_t open_hi;            /*   cut, carries come from the neighbour shard */
     int32_t shard_dim;          /* dimension that is sharded across devices, -1: none */
     int32_t engine;             /* rf_engine: which tile engine a pass may use (0: planner decides) */
-    int32_t reserved[7];
+    int32_t epilogue;           /* 1: out = epi_out * filtered + epi_in * input, fused into the filter's last store -- the
+                                   pointwise stage the reference merges with RecFilter::compute_at (unsharp mask,
+                                   apps/usm/unsharp_mask_optimized.cpp:61-66).  RF_EUNSUPPORTED unless the filter is one
+                                   fused float pass with scans along dimension 0; in-place execution stays legal */
+    float   epi_in, epi_out;
+    int32_t reserved[4];
 } rf_options;
 
 /* filter descriptor */

@@ -39,6 +39,8 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
     const char* so = getenv("ORACLE_SUM_ORDER");                 /* "tests": see oracle.c */
     oracle_set_sum_order(so && strcmp(so, "tests") == 0);
     if (!desc || !out) { snprintf(g_err, sizeof g_err, "null argument"); return RF_EINVAL; }
+    /* the checker keeps the pointwise stage separate (the host then runs it through rf_stencil_execute) */
+    if (desc->opt.epilogue) { snprintf(g_err, sizeof g_err, "oracle backend: no fused epilogue"); return RF_EUNSUPPORTED; }
     rf_plan* p = (rf_plan*)calloc(1, sizeof(rf_plan));
     if (!p) return RF_ENOMEM;
     p->d = *desc;

@@ -42,7 +42,8 @@ class _Scan(C.Structure):
 class _Options(C.Structure):
     _fields_ = [("tile", C.c_int32 * RF_MAX_DIMS), ("honor_tile", C.c_int32), ("fuse_dims", C.c_int32),
                 ("open_lo", C.c_int32), ("open_hi", C.c_int32), ("shard_dim", C.c_int32),
-                ("engine", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("engine", C.c_int32), ("epilogue", C.c_int32), ("epi_in", C.c_float), ("epi_out", C.c_float),
+                ("reserved", C.c_int32 * 4)]
 
 
 class _Desc(C.Structure):
@@ -173,10 +174,15 @@ class Plan:
 
     def __init__(self, extents: Sequence[int], dtype, scans: Iterable[Scan], border: str = "zero", *,
                  tile: Sequence[int] | int | None = None, honor_tile: bool = False, fuse_dims: int = -1,
-                 shard_dim: int = -1, open_lo: bool = False, open_hi: bool = False, engine: str = "auto"):
+                 shard_dim: int = -1, open_lo: bool = False, open_hi: bool = False, engine: str = "auto",
+                 epilogue: tuple[float, float] | None = None):
+        """``epilogue=(a_in, a_out)``: the result is ``a_out * filtered + a_in * input`` (the unsharp mask of
+        apps/usm/unsharp_mask_optimized.cpp:61-66), fused into the filter's last store."""
         self._h = C.c_void_p()
         L = lib()
         d = self._describe(extents, dtype, scans, border, tile, honor_tile, fuse_dims, shard_dim, open_lo, open_hi, engine)
+        if epilogue is not None:
+            d.opt.epilogue, d.opt.epi_in, d.opt.epi_out = 1, float(epilogue[0]), float(epilogue[1])
         self.size = int(np.prod(self.extents)) if self.extents else 0
         _check(L.rf_plan_create(C.byref(d), C.byref(self._h)), "rf_plan_create")
 

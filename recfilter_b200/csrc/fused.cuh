@@ -519,6 +519,17 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             v[c4 * 4 + 2] = *reinterpret_cast<const CT*>(&q.z);
             v[c4 * 4 + 3] = *reinterpret_cast<const CT*>(&q.w);
         }
+        if (MODE == FMODE_P2 && p.epilogue) {
+            // every row is in registers, the tile buffer is free: the INPUT tile comes in again (TMA, an L2 hit) behind
+            // the row scans, for the pointwise epilogue at the store
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(bar, NBOX * BOX_BYTES);
+#pragma unroll
+                for (int bb = 0; bb < NBOX; ++bb) tma_load_2d(tile + bb * BOX_BYTES, &tm_in, x0 + bb * 32, y0, bar);
+            }
+        }
         for (int s = 0; s < p.mx; ++s) {
             const bool causal = p.sx.causal[s] != 0;
             const bool closed = x_closed(causal);
@@ -537,14 +548,30 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             }
         }
         if constexpr (MODE == FMODE_P2) {
+            if (p.epilogue) {
+                // out = epi_out * filtered + epi_in * input, the input row read back from the re-loaded tile
+                mbar_wait(bar, 1);
+                const CT go = p.gain * p.epi_out;
+#pragma unroll
+                for (int c4 = 0; c4 < TS / 4; ++c4) {
+                    uint4 q;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                                 : "r"(rbase + (c4 >> 3) * BOX_BYTES + ((((c4 & 7) << 4)) ^ rx)));
+                    v[c4 * 4 + 0] = fmadd(v[c4 * 4 + 0], go, *reinterpret_cast<const CT*>(&q.x) * p.epi_in);
+                    v[c4 * 4 + 1] = fmadd(v[c4 * 4 + 1], go, *reinterpret_cast<const CT*>(&q.y) * p.epi_in);
+                    v[c4 * 4 + 2] = fmadd(v[c4 * 4 + 2], go, *reinterpret_cast<const CT*>(&q.z) * p.epi_in);
+                    v[c4 * 4 + 3] = fmadd(v[c4 * 4 + 3], go, *reinterpret_cast<const CT*>(&q.w) * p.epi_in);
+                }
+            }
+            const CT gs = p.epilogue ? (CT)1 : p.gain;
             // scale, rows back to shared memory (each thread only touches its own row)
 #pragma unroll
             for (int c4 = 0; c4 < TS / 4; ++c4) {
                 uint4 q;
-                *reinterpret_cast<CT*>(&q.x) = v[c4 * 4 + 0] * p.gain;
-                *reinterpret_cast<CT*>(&q.y) = v[c4 * 4 + 1] * p.gain;
-                *reinterpret_cast<CT*>(&q.z) = v[c4 * 4 + 2] * p.gain;
-                *reinterpret_cast<CT*>(&q.w) = v[c4 * 4 + 3] * p.gain;
+                *reinterpret_cast<CT*>(&q.x) = v[c4 * 4 + 0] * gs;
+                *reinterpret_cast<CT*>(&q.y) = v[c4 * 4 + 1] * gs;
+                *reinterpret_cast<CT*>(&q.z) = v[c4 * 4 + 2] * gs;
+                *reinterpret_cast<CT*>(&q.w) = v[c4 * 4 + 3] * gs;
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
                              :: "r"(rbase + (c4 >> 3) * BOX_BYTES + ((((c4 & 7) << 4)) ^ rx)),
                                 "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");

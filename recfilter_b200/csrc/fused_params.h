@@ -40,6 +40,11 @@ struct FusedParams {
     // row before it, sig_rows rows make one signal (only its first / last row is closed), md = 0, nbx = 1
     int signal;
     int64_t sig_rows;
+    // pointwise epilogue fused into the store of pass 2 (epilogue != 0; needs x scans): out = epi_out * filtered + epi_in * input
+    // -- the unsharp mask (1+w)*image - w*blur of apps/usm/unsharp_mask_optimized.cpp:61-66, which the reference merges
+    // with RecFilter::compute_at(USM, ...).  The input tile is fetched again (TMA, an L2 hit) behind the row scans.
+    int epilogue;
+    CT  epi_in, epi_out;
     // short-memory pass 2 (local != 0; at most two scans per dimension): the carries entering the tile are derived
     // from the TAILS of the neighbouring tiles on the fly -- no carry kernels ran, CX / CY are not read:
     //   C_0 = T'_0[tile before],  C_1 = T'_1[tile before] + M[0 -> 1] * C_0[there],  T' = T + G_row * A[tile] along x

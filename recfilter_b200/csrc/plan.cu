@@ -584,6 +584,8 @@ struct PassBase {
     virtual const void* ext_buffer() const = 0;
     // device word a kernel of the pass sets when it gave up waiting (look-back kernels), or null
     virtual const uint32_t* error_flag() const { return nullptr; }
+    // pointwise epilogue out = a_out * filtered + a_in * input fused into the store of the last kernel (rf_options.epilogue)
+    virtual bool set_epilogue(float, float) { return false; }
     // the whole pass on one stream; a pass may overlap its own stages internally (FusedPass: stack slices)
     virtual int run_all(const void* in, void* out, cudaStream_t st)
     {
@@ -1262,6 +1264,12 @@ struct FusedPass : PassBase {
         return RF_OK;
     }
 
+    bool set_epilogue(float a_in, float a_out) override
+    {
+        if (!std::is_same<CT, float>::value || fp.mx == 0 || d_open() || local_p2) return false;
+        fp.epilogue = 1; fp.epi_in = (CT)a_in; fp.epi_out = (CT)a_out;
+        return true;
+    }
     size_t shard_tail_elems() const override { return d_open() ? (size_t)fp.md * R * fp.nly : 0; }
     int shard_resolve(const void* gathered, int nshards, int rank, cudaStream_t st) override
     {
@@ -1280,9 +1288,10 @@ struct FusedPass : PassBase {
         char b[512];
         snprintf(b, sizeof(b),
                  "  fused pass view [%lld][%lld][%lld]: %dx%d register tiles, d scans %d (%d tiles) then x scans %d "
-                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), two sweeps: 12 B/sample, launches %d%s\n",
+                 "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), two sweeps: 12 B/sample, launches %d%s%s\n",
                  (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
-                 launches(), (std::string(nslices > 1 ? " (stack pipelined in " + std::to_string(nslices) + " slices: carry stages on a side stream)" : "") +
+                 launches(), fp.epilogue ? " (pointwise epilogue a*in + b*filtered fused into the store)" : "",
+                 (std::string(nslices > 1 ? " (stack pipelined in " + std::to_string(nslices) + " slices: carry stages on a side stream)" : "") +
                               (local_p2 ? std::string(" (short memory: pass 2 derives its carries from the neighbouring tiles' tails, no carry kernels)") :
                                (local_d || (local_x && !cross_needed())) ? std::string(" (short-memory carries, no chain, along") + (local_d ? " d" : "") + ((local_x && !cross_needed()) ? " x" : "") + ")" : std::string(""))).c_str());
         return b;
@@ -2001,6 +2010,7 @@ static bool lookback_allowed(const rf_plan* plan)
     const rf_options& opt = plan->desc.opt;
     if (opt.engine == RF_ENGINE_GENERIC || opt.engine == RF_ENGINE_TWOPASS || opt.honor_tile) return false;
     if (opt.open_lo || opt.open_hi) return false;
+    if (opt.epilogue) return false;               // the fused epilogue lives in the two-sweep kernels' pass 2
     if (const char* e = getenv("RFB_NO_LOOKBACK")) if (atoi(e)) return false;
     return true;
 }
@@ -2049,7 +2059,7 @@ static bool signal_eligible(const rf_plan* plan, const std::vector<HostScan>& sx
                             int64_t Nx, int64_t rows)
 {
     const rf_options& opt = plan->desc.opt;
-    if (opt.engine == RF_ENGINE_GENERIC || opt.honor_tile) return false;
+    if (opt.engine == RF_ENGINE_GENERIC || opt.honor_tile || opt.epilogue) return false;
     if (!sd.empty() || sx.size() != 1 || plan->R > 8) return false;
     if (const char* e = getenv("RFB_NO_SIGNAL")) if (atoi(e)) return false;
     const HostScan& h = sx[0];
@@ -2309,6 +2319,11 @@ int rf_plan_create(const rf_desc* desc, rf_plan** out)
             return fail(RF_EINVAL, "shard_dim %d has no scans: shard it as independent batches instead", shard_dim);
     }
 
+    if (opt.epilogue && total > 0) {
+        // apps/usm/unsharp_mask_optimized.cpp:61-66 merged into the filter: only where the whole filter is ONE two-sweep pass
+        if (plan->passes.size() != 1 || eb != 4 || plan->shard_pass >= 0 || !plan->passes[0]->set_epilogue(opt.epi_in, opt.epi_out))
+            return fail(RF_EUNSUPPORTED, "the fused epilogue needs a float filter that is one fused two-sweep pass with scans along dimension 0");
+    }
     if (eb < 4 && total > 0 && !plan->passes.empty()) {
         if (plan->shard_pass >= 0) return fail(RF_EUNSUPPORTED, "sharded plans need a 32-bit element type");
         CUDA_TRY(plan->stage.alloc((size_t)total * 4));

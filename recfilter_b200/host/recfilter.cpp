@@ -67,6 +67,7 @@ struct RecFilterContents {
     rf_mgpu* mgpu = nullptr;        // RECFILTER_GPUS=n: the same filter cut over n GPUs (rf_mgpu_*)
     string mgpu_sig;
     bool mgpu_refused = false;      // the engine declined to shard this filter: said once, then one GPU
+    bool epi_refused = false;       // the engine declined to fuse this pointwise definition into its filter's last store
     // Tuple (multi-output) filters, lib/recfilter.cpp:68-74,197-203: every Tuple element is filtered
     // independently with the same scans -- one channel filter per element, kept in step by sync_channels()
     vector<std::shared_ptr<RecFilterContents>> channels;
@@ -440,7 +441,7 @@ void* input_device(RecFilterContents& c, bool& owned)
 
 // run the unit first..c on the device buffer `in` (the input of `first`): the stencil of first's definition
 // (if any), then every scan of the run in one plan
-void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in)
+void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in, bool refresh_side = true)
 {
     const size_t bytes = c.count() * (size_t)c.type.bytes();
     const vector<ScanDef> scans = unit_scans(first, c);
@@ -454,8 +455,9 @@ void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in)
             if (!c.dev_tmp) engine_check(rf_malloc(&c.dev_tmp, bytes), "rf_malloc");
             dst = c.dev_tmp;
         }
-        if (f.side_image) {
+        if (f.side_image && (refresh_side || !f.dev_side)) {
             // uploaded for every evaluation, like the primary image: the caller may have changed it between realize() calls
+            // (profile() keeps it resident over its timed iterations, like the primary image)
             if (f.dev_side) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(f.dev_side), "rf_free"); f.dev_side = nullptr; }
             f.dev_side = upload_image(f, *f.side_image);
         }
@@ -505,9 +507,70 @@ rf_mgpu* mgpu_for(RecFilterContents& c)
     return c.mgpu;
 }
 
+// ---------------------------------------------------------------------------------------------
+// epilogue fusion.  A definition without scans that is  a * image(x, y) + b * F(x, y)  -- F a filter (or fused run of
+// filters) whose input is that same image, unchanged -- is the unsharp mask of apps/usm/unsharp_mask_optimized.cpp:
+// 61-66, where the reference merges the blur's last stage into USM with RecFilter::compute_at.  Here the combination
+// is applied by the store of the filter's last kernel (rf_options.epilogue): the blurred image never travels to HBM
+// and back.  Anything the engine declines (RF_EUNSUPPORTED) runs as the separate stencil kernel, as before.
+// RECFILTER_NO_EPILOGUE_FUSION=1 turns the fusion off.
+// ---------------------------------------------------------------------------------------------
+struct EpilogueMatch {
+    RecFilterContents *first = nullptr, *last = nullptr;      // the filter run whose store takes the epilogue
+    float a_in = 0.0f, a_out = 0.0f;
+};
+bool epilogue_match(RecFilterContents& c, EpilogueMatch& m)
+{
+    static const bool off = getenv("RECFILTER_NO_EPILOGUE_FUSION") && atoi(getenv("RECFILTER_NO_EPILOGUE_FUSION")) != 0;
+    if (off || c.epi_refused || !c.scans.empty() || !c.src_filter || !c.side_image || c.stencil.size() != 2) return false;
+    if (!(c.type == Float(32)) || !c.side_image->has_data()) return false;
+    const rf_tap *tf = nullptr, *ti = nullptr;
+    for (const rf_tap& t : c.stencil) {
+        for (int d = 0; d < RF_MAX_DIMS; ++d) if (t.offset[d] != 0) return false;
+        (t.source ? ti : tf) = &t;
+    }
+    if (!tf || !ti) return false;
+    RecFilterContents& last = *c.src_filter;
+    if (!last.defined || !last.channels.empty() || last.scans.empty() || !(last.type == c.type) || last.dims.size() != c.dims.size()) return false;
+    RecFilterContents& first = unit_first(last);
+    if (first.src_filter || !first.stencil.empty() || first.src_image != c.side_image) return false;
+    const BufferData& b = *c.side_image;
+    if (!(b.type == c.type) || b.dims != (int)c.dims.size()) return false;
+    for (size_t i = 0; i < c.dims.size(); ++i)
+        if (b.extent[i] != c.dims[i].num_pixels() || last.dims[i].num_pixels() != c.dims[i].num_pixels()) return false;
+    m.first = &first; m.last = &last;
+    m.a_in = c.stencil_scale * ti->weight; m.a_out = c.stencil_scale * tf->weight;
+    return true;
+}
+// the matched run with the epilogue on `in` (the image on the device); null when the engine declines the fusion
+void* run_epilogue_unit(RecFilterContents& c, const EpilogueMatch& m, const void* in)
+{
+    rf_desc d;
+    std::ostringstream sig;
+    sig << fill_desc(*m.last, unit_scans(*m.first, *m.last), d) << "|epilogue " << m.a_in << ' ' << m.a_out;
+    d.opt.epilogue = 1; d.opt.epi_in = m.a_in; d.opt.epi_out = m.a_out;
+    if (!(c.plan && c.plan_sig == sig.str())) {
+        if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
+        const int rc = rf_plan_create(&d, &c.plan);
+        if (rc == RF_EUNSUPPORTED) { c.plan = nullptr; c.epi_refused = true; return nullptr; }
+        engine_check(rc, "rf_plan_create");
+        c.plan_sig = sig.str();
+    }
+    if (!c.dev_out) engine_check(rf_malloc(&c.dev_out, c.count() * (size_t)c.type.bytes()), "rf_malloc");
+    engine_check(rf_plan_execute(c.plan, in, c.dev_out, nullptr), "rf_plan_execute");
+    return c.dev_out;
+}
+
 void* evaluate_device(RecFilterContents& c)
 {
     if (!c.defined) die("RecFilter " + c.name + " is used before it is defined");
+    EpilogueMatch epi;
+    if (epilogue_match(c, epi)) {
+        void* img = upload_image(c, *c.side_image);
+        void* out = run_epilogue_unit(c, epi, img);
+        engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(img), "rf_free");
+        if (out) return out;
+    }
     RecFilterContents& first = unit_first(c);
     bool owned = false;
     void* in = input_device(first, owned);
@@ -972,14 +1035,29 @@ float RecFilter::profile(int iterations)
         return per_iter;
     }
     vector<std::pair<RecFilterContents*, RecFilterContents*>> units;
-    collect_units(c, units);
     bool owned = false;
-    void* root_in = input_device(*units[0].first, owned);             // the image stays resident: kernels only are timed
+    void* root_in = nullptr;
+    EpilogueMatch epi;
+    bool fused_epilogue = epilogue_match(c, epi);
+    if (fused_epilogue) {                                             // a * image + b * filter(image): one plan, epilogue in its store
+        root_in = upload_image(c, *c.side_image); owned = true;
+        if (!run_epilogue_unit(c, epi, root_in)) {
+            fused_epilogue = false;
+            engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(root_in), "rf_free");
+        }
+    }
+    if (!fused_epilogue) {
+        collect_units(c, units);
+        root_in = input_device(*units[0].first, owned);               // the image stays resident: kernels only are timed
+    }
+    bool warm = false;
     auto run_chain = [&]() {
+        if (fused_epilogue) { run_epilogue_unit(c, epi, root_in); return; }
         const void* in = root_in;
-        for (auto& u : units) in = run_unit(*u.first, *u.second, in);
+        for (auto& u : units) in = run_unit(*u.first, *u.second, in, !warm);
     };
     run_chain();                                                      // warm-up (lib/recfilter.cpp:995-997)
+    warm = true;
     void* clock = nullptr;
     engine_check(rf_clock_begin(nullptr, &clock), "rf_clock_begin");
     for (int i = 0; i < iterations; ++i) run_chain();

@@ -438,3 +438,34 @@ def test_tiny_feed_forward_products_leave_the_unit_feed_forward_kernels(oracle):
     # itself is ~1e-3 from the fp64 truth here; the engine must not be much worse than it
     e_gpu, e_cpu = rel_err(out, truth), rel_err(ref32, truth)
     assert e_gpu <= 8 * e_cpu + 1e-5, (e_gpu, e_cpu)
+
+
+@pytest.mark.parametrize("shape,border", [((512, 512), "clamp"), ((384, 640), "zero"), ((300, 420), "clamp"), ((3, 256, 256), "clamp")])
+def test_pointwise_epilogue_fused_into_the_store(oracle, shape, border):
+    """rf_options.epilogue: out = a_out * filtered + a_in * input (the unsharp mask the reference merges into the
+    blur's last stage, apps/usm/unsharp_mask_optimized.cpp:61-66) equals filter-then-combine, also in place."""
+    a = rand_image(shape, np.float32, seed=71)
+    w = 1.0
+    plain = run(a, C3, border)
+    want = (1.0 + w) * a.astype(np.float64) - w * plain.astype(np.float64)
+    plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in C3], border, epilogue=(1.0 + w, -w))
+    assert "pointwise epilogue" in plan.describe()
+    got = plan.realize(a)
+    assert rel_err(got, want) <= 4e-7
+    # against the oracle's filter (fp64 truth), judged like every other fused case
+    truth = oracle.apply_filter(a.astype(np.float64), C3, border, threads=8)
+    assert rel_err(got, (1.0 + w) * a - w * truth) <= TOL
+    import torch
+    t = torch.from_numpy(a).cuda()
+    plan.execute(t.view(-1), t.view(-1)); torch.cuda.synchronize()          # in place: a tile is read again before it is stored
+    assert np.array_equal(t.cpu().numpy(), got)
+    plan.close()
+
+
+def test_pointwise_epilogue_is_refused_where_no_kernel_carries_it():
+    with pytest.raises(RecFilterError):           # no scan along dimension 0
+        Plan((256, 256), np.float32, [Scan(1, True, G3)], "zero", epilogue=(2.0, -1.0))
+    with pytest.raises(RecFilterError):           # integer filter
+        Plan((256, 256), np.uint32, [Scan(0, True, [1.0, 1.0])], "zero", epilogue=(2.0, -1.0))
+    with pytest.raises(RecFilterError):           # order above the fused kernels'
+        Plan((256, 256), np.float32, [Scan(0, True, [1.0] + [0.1] * 8)], "zero", epilogue=(2.0, -1.0))
