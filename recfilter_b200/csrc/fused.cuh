@@ -275,10 +275,42 @@ __device__ __forceinline__ void flocal_residual_c(const CT (&m)[R * R], const CT
 // ---------------------------------------------------------------------------------------------
 // RAGGED: the pass has partial tiles (extents that are not multiples of TS); the instantiation without them is
 // the exact full-tile kernel (the partial-tile code costs the common path ~15 % when it is compiled in)
-template <typename CT, int R, int TS, int MODE, bool RAGGED>
-__global__ void __launch_bounds__(TS, (TS == 128 ? 3 : 6))
-fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_constant__ CUtensorMap tm_in,
-                  const __grid_constant__ CUtensorMap tm_out)
+// The body is shared by fused_tile_kernel (one launch per sweep: `b` is the block's tile, PDL on) and by
+// fused_stream_kernel (STREAM: one launch does both sweeps, a CTA's work item comes from a ticket; `sy` tells a pass-2
+// item which counters to wait for once its tile is on its way)
+struct FStreamWait {
+    const unsigned* cnt_p1;     // [rows] pass-1 tiles finished per tile row
+    const unsigned* cnt_a;      // [rows] cross-residual blocks finished per tile row
+    unsigned* err;
+    int rows, row;              // tile rows of the whole stack, the row of this item
+    unsigned need_p1, need_a;
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr unsigned FSTREAM_SPIN_LIMIT = 1u << 22;
+// one thread: wait until tile rows [row - 2, row + 2] have finished pass 1 (and, need_a > 0, row's cross residuals exist)
+__device__ __forceinline__ void fstream_wait(const FStreamWait& sy)
+{
+    unsigned spins = 0;
+    bool ok = true;
+    auto until = [&](const unsigned* c, unsigned need) {
+        while (ok && ld_acquire_u32(c) < need) {
+            __nanosleep(100);
+            if (++spins > FSTREAM_SPIN_LIMIT) { ok = false; atomicExch(sy.err, 1u); }    // never hang: flag, go on
+        }
+    };
+    for (int r = sy.row - 2; r <= sy.row + 2; ++r)
+        if (r >= 0 && r < sy.rows) until(sy.cnt_p1 + r, sy.need_p1);
+    if (sy.need_a) until(sy.cnt_a + sy.row, sy.need_a);
+}
+
+template <typename CT, int R, int TS, int MODE, bool RAGGED, bool STREAM>
+__device__ __forceinline__ void fused_tile_body(const FusedParams<CT, R>& p, const CUtensorMap& tm_in, const CUtensorMap& tm_out,
+                                                int64_t b, const FStreamWait& sy)
 {
     constexpr int NBOX = TS / 32;
     constexpr int BOX_BYTES = TS * 128;
@@ -289,7 +321,6 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     CT* cbuf = reinterpret_cast<CT*>(tile + NBOX * BOX_BYTES + 16);      // P2: carries [d scans | x scans][R][TS]
 
     const int tid = threadIdx.x;
-    int64_t b = p.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
     const int bx = (int)(b % p.nbx); b /= p.nbx;
     const int bd = (int)(b % p.nbd);
     const int64_t o = b / p.nbd + p.o0;
@@ -301,7 +332,7 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     const int lend = (RAGGED && !p.signal) ? (int)min((int64_t)TS, p.Nd - (int64_t)bd * TS) : TS;
     const bool col_valid = !RAGGED || tid < lenx, row_valid = !RAGGED || tid < lend;
 
-    pdl_launch_dependents();
+    if (!STREAM) pdl_launch_dependents();
     // does an x scan start at a closed border in the row of this thread?  (signal mode: a row continues the
     // previous row of the same signal, so only the first / last row of a signal is closed)
     const int64_t sig_row = p.signal ? ((int64_t)y0 + tid) % p.sig_rows : 0;
@@ -311,14 +342,14 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
     };
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    pdl_wait();                                   // the input (and, for P2, the carries) may come from the previous kernel
+    if (!STREAM) pdl_wait();                      // the input (and, for P2, the carries) may come from the previous kernel
     if (tid == 0) {
         mbar_expect_tx(bar, NBOX * BOX_BYTES);
 #pragma unroll
         for (int bb = 0; bb < NBOX; ++bb) tma_load_2d(tile + bb * BOX_BYTES, &tm_in, x0 + bb * 32, y0, bar);
         // the tile of the CTA that takes over this CTA's slot (`prefetch` blocks further on) starts its way into L2
         const int64_t nxt = (int64_t)blockIdx.x + p.prefetch;
-        if (p.prefetch > 0 && nxt < (int64_t)gridDim.x) {
+        if (!STREAM && p.prefetch > 0 && nxt < (int64_t)gridDim.x) {
             int64_t b2 = p.reverse ? (int64_t)gridDim.x - 1 - nxt : nxt;
             const int bx2 = (int)(b2 % p.nbx); b2 /= p.nbx;
             const int bd2 = (int)(b2 % p.nbd);
@@ -328,6 +359,11 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
         }
     }
 
+    if (STREAM && MODE == FMODE_P2) {
+        // the tile is on its way; the tails / cross residuals this item reads come from items with earlier tickets
+        if (tid == 0) fstream_wait(sy);
+        __syncthreads();
+    }
     CT v[TS];
     CT hn[R];                                                          // history of the next scan
 
@@ -588,6 +624,15 @@ fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_con
             tma_store_commit_and_wait_read();
         }
     }
+}
+
+template <typename CT, int R, int TS, int MODE, bool RAGGED>
+__global__ void __launch_bounds__(TS, (TS == 128 ? 3 : 6))
+fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_constant__ CUtensorMap tm_in,
+                  const __grid_constant__ CUtensorMap tm_out)
+{
+    const int64_t b = p.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
+    fused_tile_body<CT, R, TS, MODE, RAGGED, false>(p, tm_in, tm_out, b, FStreamWait{});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1067,15 +1112,10 @@ flocal_kernel(const __grid_constant__ FLocalParams<CT, R> p)
 // it loads its tails, so the x tails are never rewritten in memory.
 // ---------------------------------------------------------------------------------------------
 template <typename CT, int R, int TS, bool TAILS>
-__global__ void __launch_bounds__(128)
-fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
+__device__ __forceinline__ void fcrossA_body(const FCrossParams<CT, R>& p, const int64_t w)
 {
     constexpr int CPL = TS / 32;                 // columns per lane
     const int lane = threadIdx.x & 31;
-    const int64_t w = p.w0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    pdl_launch_dependents();
-    pdl_wait();
-    if (w >= p.w1) return;
     int64_t b = w;
     const int bx = (int)(b % p.nbx); b /= p.nbx;
     const int bd = (int)(b % p.nbd);
@@ -1201,6 +1241,82 @@ fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
                 }
             }
         }
+    }
+}
+
+template <typename CT, int R, int TS, bool TAILS>
+__global__ void __launch_bounds__(128)
+fcrossA_kernel(const __grid_constant__ FCrossParams<CT, R> p)
+{
+    const int64_t w = p.w0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
+    if (w >= p.w1) return;
+    fcrossA_body<CT, R, TS, TAILS>(p, w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Both sweeps in ONE launch, for filters with short memory in every scanned dimension (FusedParams::local: the
+// carries entering a tile follow from the tails of its neighbours, there is no chain).  The two-sweep scheme reads the
+// image twice from HBM because pass 2 of ANY tile has to wait for pass 1 of EVERY tile; here pass 2 of tile row r only
+// waits for pass 1 of rows r-2 .. r+2, so it can follow pass 1 at a distance of a few tile rows and find its input
+// still in L2: 8 bytes of HBM traffic per sample instead of 12.
+//   Work items are handed out by a ticket counter in dependency order -- step s: pass 1 of tile row s, the cross
+// residuals A of row s - lag_a (one item = 4 tiles, fcrossA_body), pass 2 of row s - lag_p -- so everything an item
+// waits for has an earlier ticket and is resident or finished: no deadlock, whatever order the hardware starts CTAs in.
+// Finished items count up per-row counters (release); a waiting item polls them (acquire, one thread, bounded).
+// The counters and the ticket are zeroed before each launch (a memset node in front of the kernel).
+//   OFF by default (RFB_STREAM=1).  Measured (profiles/r02_stream_*): the unrolled scans are 41 KB (pass 1) and 64 KB
+// (pass 2) of code.  In a one-sweep launch the three resident CTAs of an SM start together, take the same time and so run
+// through that code in step, sharing the instruction fetch (hit rate 90-95 %); here an SM holds a mix of items at
+// unrelated phases and the instruction cache thrashes (hit rate 71 %, `no_instruction` 2.0 stalls per issue against
+// 0.3-0.5) -- also with ONE body for both passes told apart at run time (74 %), and with the SMs split into a pass-1
+// and a pass-2 class (81 %).  8192^2 therefore takes 250 us per image instead of 156 although pass 2 can find its
+// input in L2; stacks that fit L2 anyway tie with the two sweeps (4096^2: 79.2 against 78.9 us).
+// ---------------------------------------------------------------------------------------------
+template <typename CT, int R, int TS>
+__global__ void __launch_bounds__(TS, 3)
+fused_stream_kernel(const __grid_constant__ FStreamParams<CT, R> sp, const __grid_constant__ CUtensorMap tm_in,
+                    const __grid_constant__ CUtensorMap tm_out)
+{
+    // the ticket is broadcast through the spare word beside the tile's mbarrier (no static shared memory: three CTAs
+    // per SM leave ~1 KB)
+    extern __shared__ __align__(16) unsigned char fsmem_raw[];
+    unsigned char* tile0 = fsmem_raw + ((1024u - (smem_u32(fsmem_raw) & 1023u)) & 1023u);
+    volatile unsigned* s_ticket = reinterpret_cast<volatile unsigned*>(tile0 + (TS / 32) * TS * 128 + 8);
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(sp.ticket, 1u);
+    __syncthreads();
+    const unsigned t = *s_ticket;
+    const int s = (int)(t / (unsigned)sp.step), q = (int)(t % (unsigned)sp.step);
+    const int nbx = sp.t.nbx;
+    auto done = [&](unsigned* counter) {
+        __syncthreads();                                   // every thread's tails / residuals are written ...
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(counter, 1u); }      // ... and visible before the count
+    };
+    FStreamWait sy;
+    sy.cnt_p1 = sp.cnt_p1; sy.cnt_a = sp.cnt_a; sy.err = sp.err; sy.rows = sp.rows;
+    sy.need_p1 = (unsigned)nbx; sy.need_a = 0; sy.row = 0;
+    if (q >= nbx && q < nbx + sp.na) {
+        const int row = s - sp.lag_a;
+        if (row < 0 || row >= sp.rows) return;
+        sy.row = row;
+        if (threadIdx.x == 0) fstream_wait(sy);
+        __syncthreads();
+        const int tx = (q - nbx) * (TS / 32) + (threadIdx.x >> 5);              // one warp per tile
+        if (tx < nbx) fcrossA_body<CT, R, TS, false>(sp.c, (int64_t)row * nbx + tx);
+        done(sp.cnt_a + row);
+        return;
+    }
+    if (q < nbx) {
+        const int row = s;
+        if (row >= sp.rows) return;
+        fused_tile_body<CT, R, TS, FMODE_P1, false, true>(sp.t, tm_in, tm_in, (int64_t)row * nbx + q, sy);
+        done(sp.cnt_p1 + row);
+    } else {
+        const int row = s - sp.lag_p;
+        if (row < 0 || row >= sp.rows) return;
+        sy.row = row; sy.need_a = (unsigned)sp.na;
+        fused_tile_body<CT, R, TS, FMODE_P2, false, true>(sp.t, tm_in, tm_out, (int64_t)row * nbx + (q - nbx - sp.na), sy);
     }
 }
 

@@ -160,6 +160,34 @@ static cudaError_t launch_fcross_T(const FCrossParams<CT, R>& pin, int ts, cudaS
     return cudaErrorInvalidValue;
 }
 
+template <typename CT, int R>
+static cudaError_t launch_fused_stream_T(const FStreamParams<CT, R>& sp, const void* in, void* out, cudaStream_t st)
+{
+    constexpr int TS = 128;
+    const FusedParams<CT, R>& p = sp.t;
+    const int64_t nblocks = (int64_t)(sp.rows + sp.lag_p) * sp.step;
+    if (nblocks <= 0) return cudaSuccess;
+    if (nblocks > 0x7fffffffLL || p.Nx % TS || p.Nd % TS) return cudaErrorInvalidConfiguration;
+    const size_t smem = fused_tile_smem_bytes(TS, fused_p2_carry_words(p.mx, p.md, R, TS, 1, p.sdk));
+    static size_t attr_bytes_dev[RFB_MAX_DEVICES] = {};
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    const bool cacheable = dev >= 0 && dev < RFB_MAX_DEVICES;
+    if (!cacheable || smem > attr_bytes_dev[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fused_stream_kernel<CT, R, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (cacheable) attr_bytes_dev[dev] = smem;
+    }
+    const bool is_float = std::is_same<CT, float>::value;
+    CUtensorMap tm_in, tm_out;
+    cudaError_t e = make_tile_map(&tm_in, in, p.Nx, p.No * p.Nd, TS, is_float);
+    if (e != cudaSuccess) return e;
+    e = make_tile_map(&tm_out, out, p.Nx, p.No * p.Nd, TS, is_float);
+    if (e != cudaSuccess) return e;
+    fused_stream_kernel<CT, R, TS><<<dim3((unsigned)nblocks), dim3(TS), smem, st>>>(sp, tm_in, tm_out);
+    return cudaGetLastError();
+}
+
 #define RFB_CAT_(a, b) a##b
 #define RFB_CAT(a, b) RFB_CAT_(a, b)
 
@@ -167,6 +195,10 @@ cudaError_t RFB_CAT(launch_fused_tile_f, RFB_R)(const FusedParams<float, RFB_R>&
 { return launch_fused_tile_T<float, RFB_R>(p, in, out, mode, ts, st); }
 cudaError_t RFB_CAT(launch_fused_tile_u, RFB_R)(const FusedParams<uint32_t, RFB_R>& p, const void* in, void* out, int mode, int ts, cudaStream_t st)
 { return launch_fused_tile_T<uint32_t, RFB_R>(p, in, out, mode, ts, st); }
+#if RFB_R <= 4
+cudaError_t RFB_CAT(launch_fused_stream_f, RFB_R)(const FStreamParams<float, RFB_R>& p, const void* in, void* out, cudaStream_t st)
+{ return launch_fused_stream_T<float, RFB_R>(p, in, out, st); }
+#endif
 cudaError_t RFB_CAT(launch_fchain_f, RFB_R)(const FChainParams<float, RFB_R>& p, cudaStream_t st)
 { return launch_fchain_T<float, RFB_R>(p, st); }
 cudaError_t RFB_CAT(launch_fchain_u, RFB_R)(const FChainParams<uint32_t, RFB_R>& p, cudaStream_t st)

@@ -125,6 +125,21 @@ inline size_t fchain_smem_bytes(int S, int nseg, int R, int L, int nb, int sdk_i
             (size_t)S * nseg * R * R + (size_t)nseg * R * 32 + work) * 4;
 }
 
+// both sweeps in one launch (fused_stream_kernel, fused.cuh)
+template <typename CT, int R>
+struct FStreamParams {
+    FusedParams<CT, R> t;           // the tile items: pass 1 and the short-memory pass 2 (local = 1)
+    FCrossParams<CT, R> c;          // the cross-residual items (local = 1)
+    unsigned* ticket;               // device words, zeroed before every launch: [ticket][pad][cnt_p1 rows][cnt_a rows]
+    unsigned* cnt_p1;               // pass-1 tiles finished per tile row
+    unsigned* cnt_a;                // A items finished per tile row
+    unsigned* err;                  // set (never cleared by the kernel) when an item gave up waiting
+    int rows;                       // tile rows of the whole stack: No * nbd
+    int na;                         // A items per tile row: ceil(nbx / 4)
+    int step;                       // tickets per step: nbx + na + nbx
+    int lag_a, lag_p;               // tile rows the cross residuals / pass 2 run behind pass 1
+};
+
 // dynamic shared memory of one tile CTA: the swizzled boxes, alignment slack, the mbarrier
 // (pass 2 adds the staged carries of the tile: nscans * R * ts words)
 // staged carries of a pass-2 CTA: one slot of R x ts words per scan; the short-memory variant adds one temporary per

@@ -43,6 +43,7 @@ RFB_FOR_EACH_R(DECLARE_LAUNCHERS)
 #define DECLARE_FLAUNCHERS(RR)                                                                      \
     cudaError_t launch_fused_tile_f##RR(const FusedParams<float, RR>&, const void*, void*, int, int, cudaStream_t);    \
     cudaError_t launch_fused_tile_u##RR(const FusedParams<uint32_t, RR>&, const void*, void*, int, int, cudaStream_t); \
+    cudaError_t launch_fused_stream_f##RR(const FStreamParams<float, RR>&, const void*, void*, cudaStream_t);          \
     cudaError_t launch_fchain_f##RR(const FChainParams<float, RR>&, cudaStream_t);                  \
     cudaError_t launch_fchain_u##RR(const FChainParams<uint32_t, RR>&, cudaStream_t);               \
     cudaError_t launch_fcross_f##RR(const FCrossParams<float, RR>&, int, cudaStream_t);             \
@@ -50,6 +51,11 @@ RFB_FOR_EACH_R(DECLARE_LAUNCHERS)
     cudaError_t launch_flocal_f##RR(const FLocalParams<float, RR>&, cudaStream_t);                  \
     cudaError_t launch_flocal_u##RR(const FLocalParams<uint32_t, RR>&, cudaStream_t);
 RFB_FOR_EACH_FR(DECLARE_FLAUNCHERS)
+
+static inline cudaError_t launch_fused_stream(const FStreamParams<float, 1>& p, const void* i, void* o, cudaStream_t s) { return launch_fused_stream_f1(p, i, o, s); }
+static inline cudaError_t launch_fused_stream(const FStreamParams<float, 2>& p, const void* i, void* o, cudaStream_t s) { return launch_fused_stream_f2(p, i, o, s); }
+static inline cudaError_t launch_fused_stream(const FStreamParams<float, 3>& p, const void* i, void* o, cudaStream_t s) { return launch_fused_stream_f3(p, i, o, s); }
+static inline cudaError_t launch_fused_stream(const FStreamParams<float, 4>& p, const void* i, void* o, cudaStream_t s) { return launch_fused_stream_f4(p, i, o, s); }
 
 template <typename CT, int R> struct FLaunch;
 #define DEFINE_FLAUNCH_TRAITS(RR)                                                                   \
@@ -846,6 +852,10 @@ struct FusedPass : PassBase {
     DevBuf TX, CX, TY, CY, dA;
     DevBuf dPx, dMx, dPsegx, dL, dPd, dMd, dPsegd, dG;
     DevBuf dExt, dTailOut, dW, dWact;       // dW: response of the strip's carries to what enters it (build_strip_response)
+    // both sweeps in one launch (fused_stream_kernel): short memory in both dimensions, full 128-sample tiles, unsharded
+    bool stream_ok = false;
+    int lag_a = 3, lag_p = 6;
+    DevBuf dSync, dStreamErr;               // ticket + per-row counters (zeroed before every launch); the give-up flag
     DimTables<HT> tx_tab, td_tab;
     std::unique_ptr<ShardResolver<CT, R>> resolver;
     int sdk() const { return ((fp.md * R + 3) / 4) * 4; }     // entries of one A row, padded for 128-bit loads
@@ -864,6 +874,7 @@ struct FusedPass : PassBase {
     }
     int launches() const override
     {
+        if (stream_ok && nslices < 2) return 1;
         int n = 1;
         if (needs_carries()) n += 1 + (cross_needed() ? 1 : 0) + (local_p2 ? 0 : (d_needs() ? 1 : 0) + (x_needs() ? 1 : 0));
         return n * nslices;
@@ -1043,6 +1054,33 @@ struct FusedPass : PassBase {
             const int per_sm = ts == 128 ? 3 : 6;
             local_p2 = !off && needs_carries() && !d_open() && (fp.mx == 0 || local_x || gx.nb == 1) && (fp.md == 0 || local_d || gd.nb == 1) &&
                        fp.mx <= 2 && fp.md <= 2 && Nx % ts == 0 && Nd % ts == 0 && (smem + 1024) * per_sm <= 233472;
+            // the same conditions allow both sweeps in ONE launch (fused_stream_kernel: pass 2 follows pass 1 a few tile
+            // rows behind and reads its input from L2: 8 B/sample of HBM traffic instead of 12).  OFF by default
+            // (RFB_STREAM=1 turns it on): measured, an SM that holds a mix of pass-1 and pass-2 items loses more to
+            // instruction-cache misses than the filter gains in traffic -- 8192^2: 250 us against 156 per image; stacks
+            // that fit L2 tie (4096^2: 79.2 against 78.9 us), see fused.cuh.  Checked against the two sweeps in
+            // tests/test_fused_gpu.py.
+            const bool want = getenv("RFB_STREAM") && atoi(getenv("RFB_STREAM")) != 0;
+            const int64_t rows = No * gd.nb;
+            stream_ok = want && std::is_same<CT, float>::value && ts == 128 && cross_needed() && !d_open() && local_x && local_d &&
+                        fp.mx <= 2 && fp.md <= 2 && Nx % ts == 0 && Nd % ts == 0 && (smem + 1024) * 3 <= 233472 &&
+                        rows < (1 << 24) && (rows + 64) * (2 * (int64_t)gx.nb + (gx.nb + 3) / 4) < 0x7fffffffLL;
+            if (stream_ok) {
+                CUDA_TRY(dSync.alloc((size_t)(2 + 2 * rows) * sizeof(unsigned)));
+                CUDA_TRY(dStreamErr.alloc(sizeof(unsigned)));
+                CUDA_TRY(cudaMemset(dStreamErr.p, 0, sizeof(unsigned)));
+                // the cross residuals of a row wait for pass 1 of two rows further on, pass 2 for the residuals: keep
+                // about a wave of resident CTAs (3 per SM) between producer and consumer so that waiting is rare,
+                // and no more (every tile row pass 2 lags behind has to stay in L2, beside what pass 2 writes)
+                int sms = 148, dev = 0;
+                if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const int step = 2 * gx.nb + (gx.nb + 3) / 4;
+                const int gap = (3 * sms + step - 1) / step;
+                lag_a = 2 + gap; lag_p = lag_a + gap;
+                if (const char* e = getenv("RFB_STREAM_LAG_A")) lag_a = std::max(2, atoi(e));
+                if (const char* e = getenv("RFB_STREAM_LAG_P")) lag_p = atoi(e);
+                lag_p = std::max(lag_p, lag_a);
+            }
         }
         return init_pipeline();
     }
@@ -1103,8 +1141,44 @@ struct FusedPass : PassBase {
         }
         return RF_OK;
     }
+    const uint32_t* error_flag() const override { return stream_ok ? (const uint32_t*)dStreamErr.p : nullptr; }
+
+    // both sweeps in one launch
+    int run_stream(const void* in, void* out, cudaStream_t st)
+    {
+        if constexpr (std::is_same<CT, float>::value && R <= 4) {
+            FStreamParams<CT, R> sp;
+            std::memset(&sp, 0, sizeof(sp));
+            sp.t = fp;
+            sp.t.reverse = 0; sp.t.local = 1; sp.t.prefetch = 0; sp.t.o0 = 0; sp.t.No_launch = 0;
+            sp.t.Mx = (const TT*)dMx.p; sp.t.Md = (const TT*)dMd.p; sp.t.sdk = sdk();
+            sp.t.A = (const CT*)dA.p; sp.t.G = (const TT*)dG.p;
+            FCrossParams<CT, R>& cr = sp.c;
+            cr.CY = (const CT*)CY.p; cr.A = (CT*)dA.p; cr.L = (const TT*)dL.p;
+            cr.Nx = fp.Nx; cr.Nd = fp.Nd; cr.No = fp.No; cr.nbx = gx.nb; cr.nbd = gd.nb; cr.Sx = fp.mx; cr.Sd = fp.md;
+            cr.sdk = sdk(); cr.nly = fp.nly; cr.nlx = fp.nlx;
+            cr.local = 1; cr.TY = (const CT*)TY.p; cr.Md = (const TT*)dMd.p; cr.TXw = (CT*)TX.p; cr.G = (const TT*)dG.p;
+            for (int s2 = 0; s2 < fp.md && s2 < 2; ++s2) cr.causal_d[s2] = sd[s2].causal;
+            cr.w0 = 0; cr.w1 = (int64_t)gx.nb * gd.nb * fp.No;
+            const int64_t rows = fp.No * gd.nb;
+            unsigned* w = (unsigned*)dSync.p;
+            sp.ticket = w; sp.cnt_p1 = w + 2; sp.cnt_a = w + 2 + rows; sp.err = (unsigned*)dStreamErr.p;
+            sp.rows = (int)rows; sp.na = (gx.nb + 3) / 4; sp.step = 2 * gx.nb + sp.na;
+            sp.lag_a = lag_a; sp.lag_p = lag_p;
+            cudaEvent_t ev = timer ? timer->begin(st, ST_FINAL) : nullptr;
+            CUDA_TRY(cudaMemsetAsync(dSync.p, 0, dSync.bytes, st));
+            CUDA_TRY(launch_fused_stream(sp, in, out, st));
+            if (timer) timer->end(st, ev);
+            return RF_OK;
+        } else {
+            (void)in; (void)out; (void)st;
+            return fail(RF_EINTERNAL, "fused_stream_kernel is a float kernel");
+        }
+    }
+
     int run_all(const void* in, void* out, cudaStream_t st) override
     {
+        if (stream_ok && nslices < 2) return run_stream(in, out, st);
         if (nslices < 2) return PassBase::run_all(in, out, st);
         auto bounds = [&](int i, int64_t& a, int64_t& b) { a = fp.No * i / nslices; b = fp.No * (i + 1) / nslices; };
         int rc = RF_OK;
@@ -1290,7 +1364,8 @@ struct FusedPass : PassBase {
                  "  fused pass view [%lld][%lld][%lld]: %dx%d register tiles, d scans %d (%d tiles) then x scans %d "
                  "(%d tiles), order<=%d, unit feed-forward (gain applied at the store), two sweeps: 12 B/sample, launches %d%s%s\n",
                  (long long)fp.No, (long long)fp.Nd, (long long)fp.Nx, ts, ts, fp.md, fp.nbd, fp.mx, fp.nbx, R,
-                 launches(), fp.epilogue ? " (pointwise epilogue a*in + b*filtered fused into the store)" : "",
+                 launches(), fp.epilogue ? " (pointwise epilogue a*in + b*filtered fused into the store)" :
+                 (stream_ok && nslices < 2) ? " -- whole-filter calls: both sweeps in ONE launch (short memory: pass 2 follows pass 1 a few tile rows behind and reads its input from L2, 8 B/sample of HBM traffic)" : "",
                  (std::string(nslices > 1 ? " (stack pipelined in " + std::to_string(nslices) + " slices: carry stages on a side stream)" : "") +
                               (local_p2 ? std::string(" (short memory: pass 2 derives its carries from the neighbouring tiles' tails, no carry kernels)") :
                                (local_d || (local_x && !cross_needed())) ? std::string(" (short-memory carries, no chain, along") + (local_d ? " d" : "") + ((local_x && !cross_needed()) ? " x" : "") + ")" : std::string(""))).c_str());

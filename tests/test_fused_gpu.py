@@ -469,3 +469,30 @@ def test_pointwise_epilogue_is_refused_where_no_kernel_carries_it():
         Plan((256, 256), np.uint32, [Scan(0, True, [1.0, 1.0])], "zero", epilogue=(2.0, -1.0))
     with pytest.raises(RecFilterError):           # order above the fused kernels'
         Plan((256, 256), np.float32, [Scan(0, True, [1.0] + [0.1] * 8)], "zero", epilogue=(2.0, -1.0))
+
+
+def test_both_sweeps_in_one_launch_equal_the_two_sweeps(oracle, monkeypatch):
+    """RFB_STREAM=1: fused_stream_kernel (pass 1, cross residuals and the short-memory pass 2 as ticketed work items of
+    one launch) against the default two-sweep kernels and the oracle; stacked, in place, with the fused epilogue."""
+    import torch
+    a = rand_image((4, 1024, 1280), np.float32, seed=83)          # 320 tiles of 128 x 128
+    two = run(a, C3, "clamp")
+    monkeypatch.setenv("RFB_STREAM", "1")
+    plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in C3], "clamp", engine="twopass")
+    assert "ONE launch" in plan.describe() and plan.num_launches == 1
+    one = plan.realize(a)
+    assert rel_err(one, two) <= 8e-6
+    truth = oracle.apply_filter(a.astype(np.float64), C3, "clamp", threads=8)
+    assert rel_err(one, truth) <= TOL
+    t = torch.from_numpy(a).cuda()
+    for _ in range(3):                                   # the counters are re-armed before every launch
+        t.copy_(torch.from_numpy(a))
+        plan.execute(t.view(-1), t.view(-1))
+    torch.cuda.synchronize(); plan.check()
+    assert np.array_equal(t.cpu().numpy(), one)
+    plan.close()
+    plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in C3], "clamp", epilogue=(2.0, -1.0))
+    assert "ONE launch" not in plan.describe() or plan.num_launches == 1
+    got = plan.realize(a)
+    assert rel_err(got, 2.0 * a - truth) <= TOL
+    plan.close()
