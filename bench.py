@@ -275,6 +275,16 @@ def other_configs(N, rank, barrier, peak, exchange):
         ms = _time_calls(one, 40, barrier, dist, 1)
         entry("C3 Gaussian 8192^2, one image per call", W * H, ms, 1, plan.describe().splitlines()[1].strip()[:140], plan.num_launches)
         plan.close()
+        # apps/usm: unsharp mask (1+w)*image - w*blur, the pointwise stage fused into pass 2's store (rf_options.epilogue)
+        plan = Plan((W, H), "f32", [Scan(*s) for s in scans_c3()], "clamp", epilogue=(2.0, -1.0))
+
+        def usm():
+            i = state["i"] = (state["i"] + 1) % 2
+            plan.execute(src[i], dst)
+        ms = _time_calls(usm, 40, barrier, dist, 1)
+        entry("apps/usm unsharp mask 8192^2 (Gaussian + fused pointwise epilogue)", W * H, ms, 1,
+              plan.describe().splitlines()[1].strip()[-110:], plan.num_launches)
+        plan.close()
         del src, dst
         for name, ext, dt, tdt in (("C1 summed-area table 2048^2 u32", (2048, 2048), "u32", torch.int32),
                                    ("C2 box-filter integral image 4096^2 f32", (4096, 4096), "f32", torch.float32)):
