@@ -108,7 +108,27 @@ __device__ __forceinline__ void scan_dispatch(CT (&v)[TILE], CT (&h)[R], const C
                                               const bool full)
 {
     if constexpr (R > 8) {
-        scan_rolled<CT, R>(v, h, c, len, clampb, causal);
+        // full tiles: the unrolled register scan (history shifts become register renaming); with the rolled loops the
+        // history lives in local memory and every sample costs ~3R local accesses (measured: 16.7 M samples of order
+        // 9..15 took 0.9 ms in K1 alone, order 17..29 2.0 ms)
+        if (full) {
+            if (causal) scan_regs<CT, R, true,  true>(v, h, c, len, clampb);
+            else        scan_regs<CT, R, false, true>(v, h, c, len, clampb);
+        } else {
+            // local copies: the arrays handed to the rolled (noinline) scan live in local memory, the caller's stay in registers
+            CT w[TILE], hh[R], cc[R + 1];
+#pragma unroll
+            for (int i = 0; i < TILE; ++i) w[i] = v[i];
+#pragma unroll
+            for (int k = 0; k < R; ++k) hh[k] = h[k];
+#pragma unroll
+            for (int k = 0; k <= R; ++k) cc[k] = c[k];
+            scan_rolled<CT, R>(w, hh, cc, len, clampb, causal);
+#pragma unroll
+            for (int i = 0; i < TILE; ++i) v[i] = w[i];
+#pragma unroll
+            for (int k = 0; k < R; ++k) h[k] = hh[k];
+        }
     } else {
         if (full) {
             if (causal) scan_regs<CT, R, true,  true>(v, h, c, len, clampb);
@@ -482,13 +502,161 @@ chain_fix_kernel(const __grid_constant__ ChainParams<CT, R> p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: cross-dimension residual.  The completed x carries change the x-filtered tile by
-//   F = sum_q CXq (rows x R) * Gq^T (R x cols); the d tails computed by K1 on the
-//   incomplete tile therefore miss  L_s * F  (/root/reference/lib/split.cpp:1215-1633).
-//   A[s][q] = L_s (R x rows) * CXq (rows x R)   -- reduction over the rows of the tile
-//   TY[s][.][col] += sum_q A[s][q] * Gq[col][.]
-// One CTA of TILE threads per tile.
+// K2 for high orders (R >= 16): the same three steps with one WARP per (segment, line) -- lane k owns component k of
+// the history, a matrix-vector product is R shuffles + R FMAs per lane with the matrix row read conflict-free from a
+// transposed copy in shared memory (interior tiles; the border variants, a handful of tiles, read global memory).
+// One thread per line, as above, keeps R-element arrays that it indexes in rolled loops, i.e. in local memory: a
+// 16.7 M-sample order-9..15 signal spent 25 ms of its 26.7 ms in the chain, order 17..29 90 of 93 ms
+// (scripts/high_order_time.py).
 // ---------------------------------------------------------------------------------------------
+template <typename TT, int R>
+__device__ __forceinline__ TT wmatvec(const TT* __restrict__ m, const bool transposed, const TT x, const int kl)
+{
+    TT a[4] = { (TT)0, (TT)0, (TT)0, (TT)0 };       // four partial sums: the FMA chain is R/4 deep
+#pragma unroll
+    for (int kk = 0; kk < R; kk += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const TT xe = __shfl_sync(0xffffffffu, x, kk + e);
+            a[e] = madd(transposed ? m[(kk + e) * R + kl] : m[kl * R + kk + e], xe, a[e]);
+        }
+    }
+    return (a[0] + a[1]) + (a[2] + a[3]);
+}
+// stage `count` R x R matrices, transposed, into shared memory (the whole block takes part)
+template <typename TT, int R>
+__device__ __forceinline__ void wstage(TT* dst, const TT* __restrict__ src, int count)
+{
+    for (int i = threadIdx.x; i < count * R * R; i += blockDim.x) {
+        const int mtx = i / (R * R), e = i - mtx * R * R, k = e / R, kk = e - k * R;
+        dst[mtx * R * R + kk * R + k] = src[(int64_t)mtx * R * R + e];
+    }
+    __syncthreads();
+}
+constexpr int WCHAIN_MAXQ = 2;      // same-dimension residual matrices kept in shared memory (earlier scans q < 2)
+constexpr int WCHAIN_BATCH = 8;     // chain steps whose (recurrence-independent) loads are issued together
+
+template <typename CT, int R>
+__global__ void __launch_bounds__(128)
+chain_local_wkernel(const __grid_constant__ ChainParams<CT, R> p)
+{
+    typedef typename TabType<CT>::type TT;
+    __shared__ TT sm[(1 + WCHAIN_MAXQ) * R * R];
+    const int s = p.s;
+    // interior variant: P[s], then M[q -> s] for q < min(s, WCHAIN_MAXQ)
+    wstage<TT, R>(sm, p.P + ((int64_t)V_INTERIOR * p.S + s) * R * R, 1);
+    for (int q = 0; q < s && q < WCHAIN_MAXQ; ++q)
+        wstage<TT, R>(sm + (1 + q) * R * R, p.M + (((int64_t)V_INTERIOR * p.S + q) * p.S + s) * R * R, 1);
+    const int lane = threadIdx.x & 31, kl = lane < R ? lane : 0;
+    const bool act = lane < R;
+    const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gid >= p.nl * p.nseg) return;
+    const int64_t l = gid % p.nl;
+    const int g = (int)(gid / p.nl);          // segment index in SCAN order
+    TT tau = (g == 0 && p.ext && act) ? (TT)p.ext[(int64_t)kl * p.nl + l] : (TT)0;
+    const int j_begin = g * p.seg;
+    const int j_end = min(p.nb, j_begin + p.seg);
+    auto tile_of = [&](int jj) { return p.causal ? jj : p.nb - 1 - jj; };
+    auto index = [&](int sc, int j) { return ((int64_t)sc * R + kl) * p.plane + (int64_t)j * p.tile_stride + l * p.line_stride; };
+    // the tails do not depend on the recurrence: WB steps' worth are asked for at once, ahead of the serial part
+    // (one step ahead left ~500 cycles of L2 latency exposed in every step)
+    for (int jb = j_begin; jb < j_end; jb += WCHAIN_BATCH) {
+        TT tb[WCHAIN_BATCH];
+#pragma unroll
+        for (int e = 0; e < WCHAIN_BATCH; ++e) tb[e] = (jb + e < j_end) ? (TT)p.T[index(s, tile_of(jb + e))] : (TT)0;
+#pragma unroll
+        for (int e = 0; e < WCHAIN_BATCH; ++e) {
+            const int jj = jb + e;
+            if (jj < j_end) {
+                const int j = tile_of(jj);
+                const int var = tile_variant(j, p.nb);
+                TT t = tb[e];
+                if (act) p.C[index(s, j)] = (CT)tau;
+                for (int q = 0; q < s; ++q) {
+                    const TT cq = (TT)p.C[index(q, j)];
+                    const bool fast = var == V_INTERIOR && q < WCHAIN_MAXQ;
+                    t = t + wmatvec<TT, R>(fast ? sm + (1 + q) * R * R : p.M + (((int64_t)var * p.S + q) * p.S + s) * R * R, fast, cq, kl);
+                }
+                const bool fast = var == V_INTERIOR;
+                t = t + wmatvec<TT, R>(fast ? sm : p.P + ((int64_t)var * p.S + s) * R * R, fast, tau, kl);
+                tau = t;
+            }
+        }
+    }
+    if (!act) return;
+    if (p.nseg > 1) p.SEGT[((int64_t)kl * p.nseg + g) * p.nl + l] = tau;
+    else if (p.tail_out) p.tail_out[(int64_t)kl * p.nl + l] = (CT)tau;
+}
+
+template <typename CT, int R>
+__global__ void __launch_bounds__(128)
+chain_top_wkernel(const __grid_constant__ ChainParams<CT, R> p)
+{
+    typedef typename TabType<CT>::type TT;
+    __shared__ TT sm[2 * R * R];
+    wstage<TT, R>(sm, p.Pseg, 2);
+    const int lane = threadIdx.x & 31, kl = lane < R ? lane : 0;
+    const bool act = lane < R;
+    const int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (l >= p.nl) return;
+    TT sigma = (TT)0;                             // segment 0 already started from ext
+    for (int gb = 0; gb < p.nseg; gb += WCHAIN_BATCH) {
+        TT tb[WCHAIN_BATCH];
+#pragma unroll
+        for (int e = 0; e < WCHAIN_BATCH; ++e) tb[e] = (gb + e < p.nseg) ? p.SEGT[((int64_t)kl * p.nseg + gb + e) * p.nl + l] : (TT)0;
+#pragma unroll
+        for (int e = 0; e < WCHAIN_BATCH; ++e) {
+            const int g = gb + e;
+            if (g < p.nseg) {
+                if (act) p.SEGC[((int64_t)kl * p.nseg + g) * p.nl + l] = sigma;
+                sigma = tb[e] + wmatvec<TT, R>(sm + (g == p.nseg - 1 ? R * R : 0), true, sigma, kl);
+            }
+        }
+    }
+    if (p.tail_out && act) p.tail_out[(int64_t)kl * p.nl + l] = (CT)sigma;
+}
+
+template <typename CT, int R>
+__global__ void __launch_bounds__(128)
+chain_fix_wkernel(const __grid_constant__ ChainParams<CT, R> p)
+{
+    typedef typename TabType<CT>::type TT;
+    __shared__ TT sm[R * R];
+    const int s = p.s;
+    wstage<TT, R>(sm, p.P + ((int64_t)V_INTERIOR * p.S + s) * R * R, 1);
+    const int lane = threadIdx.x & 31, kl = lane < R ? lane : 0;
+    const bool act = lane < R;
+    const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gid >= p.nl * (p.nseg - 1)) return;
+    const int64_t l = gid % p.nl;
+    const int g = (int)(gid / p.nl) + 1;
+    TT u = p.SEGC[((int64_t)kl * p.nseg + g) * p.nl + l];
+    const int j_begin = g * p.seg;
+    const int j_end = min(p.nb, j_begin + p.seg);
+    for (int jb = j_begin; jb < j_end; jb += WCHAIN_BATCH) {
+        TT cb[WCHAIN_BATCH];
+        int64_t ib[WCHAIN_BATCH];
+#pragma unroll
+        for (int e = 0; e < WCHAIN_BATCH; ++e) {
+            const int jj = min(jb + e, j_end - 1);
+            const int j = p.causal ? jj : p.nb - 1 - jj;
+            ib[e] = ((int64_t)s * R + kl) * p.plane + (int64_t)j * p.tile_stride + l * p.line_stride;
+            cb[e] = (TT)p.C[ib[e]];
+        }
+#pragma unroll
+        for (int e = 0; e < WCHAIN_BATCH; ++e) {
+            const int jj = jb + e;
+            if (jj < j_end) {
+                const int j = p.causal ? jj : p.nb - 1 - jj;
+                const int var = tile_variant(j, p.nb);
+                if (act) p.C[ib[e]] = (CT)(cb[e] + u);
+                const bool fast = var == V_INTERIOR;
+                u = wmatvec<TT, R>(fast ? sm : p.P + ((int64_t)var * p.S + s) * R * R, fast, u, kl);
+            }
+        }
+    }
+}
+
 template <typename CT, int R>
 __global__ void __launch_bounds__(TILE)
 cross_kernel(const __grid_constant__ CrossParams<CT, R> p)

@@ -3,6 +3,7 @@
  * filter order (compile with -DRFB_R=<1|2|3|4|8|16|32>); one object per order so the
  * orders build in parallel.
  */
+#include <cstdlib>
 #include "kernels.cuh"
 
 #ifndef RFB_R
@@ -31,6 +32,19 @@ static cudaError_t launch_chain_T(const ChainParams<CT, R>& p, cudaStream_t st)
 {
     const int64_t n1 = p.nl * p.nseg;
     if (n1 <= 0) return cudaSuccess;
+    if constexpr (R >= 16) {
+        // high orders: one warp per (segment, line), see kernels.cuh (RFB_NO_WARP_CHAIN=1: the thread-per-line kernels)
+        static const bool off = getenv("RFB_NO_WARP_CHAIN") && atoi(getenv("RFB_NO_WARP_CHAIN")) != 0;
+        if (!off) {
+            chain_local_wkernel<CT, R><<<(unsigned)((n1 + 3) / 4), 128, 0, st>>>(p);
+            if (p.nseg > 1) {
+                chain_top_wkernel<CT, R><<<(unsigned)((p.nl + 3) / 4), 128, 0, st>>>(p);
+                const int64_t n3 = p.nl * (p.nseg - 1);
+                chain_fix_wkernel<CT, R><<<(unsigned)((n3 + 3) / 4), 128, 0, st>>>(p);
+            }
+            return cudaGetLastError();
+        }
+    }
     chain_local_kernel<CT, R><<<(unsigned)((n1 + 127) / 128), 128, 0, st>>>(p);
     if (p.nseg > 1) {
         chain_top_kernel<CT, R><<<(unsigned)((p.nl + 127) / 128), 128, 0, st>>>(p);
