@@ -23,4 +23,17 @@ run("look-back signal r3 anticausal", (16384 * 3, 2), "f32", [(0, False, G3)], "
 run("two-sweep signal r8", (32768, 2), "f32", [(0, True, [1.0] + [0.01] * 8)], engine="twopass")
 run("generic engine order 5", (96, 80), "f32", [(0, True, [1.0] + [0.1] * 5), (1, False, [1.0] + [0.1] * 5)], engine="generic")
 run("3-D volume", (128, 128, 64), "f32", [(0, True, [1, .5, .25]), (1, False, [1, .5, .125]), (2, True, [1, .5, .0625]), (2, False, [1, .5, .125])])
+run("fused pointwise epilogue (usm)", (256, 384), "f32", c3, "clamp", epilogue=(2.0, -1.0))
+run("fused pointwise epilogue, 128 tiles", (1280, 1024, 4), "f32", c3, "clamp", engine="twopass", epilogue=(2.0, -1.0))
+run("order 12, one long line (warp chain, 3 levels)", (65536 + 64,), "f32", [(0, True, [1.0] + [0.01] * 12)])
+run("order 20, lines x 40000 (warp chain)", (40000, 3), "f32", [(0, True, [1.0] + [0.01] * 20), (0, False, [1.0] + [0.01] * 20)], "clamp")
+os.environ["RFB_STREAM"] = "1"
+run("both sweeps in one launch (RFB_STREAM=1)", (1280, 1024, 4), "f32", c3, "clamp", engine="twopass")
+del os.environ["RFB_STREAM"]
+from recfilter_b200.capi import stencil
+import torch
+img = torch.rand((300, 520), device="cuda")
+box = stencil(img, [(1.0, (3, 3)), (-1.0, (3, -4)), (1.0, (-4, -4)), (-1.0, (-4, 3))], post_scale=1.0 / 49.0)
+torch.cuda.synchronize()
+print("stencil ok", float(box.sum()) != 0.0, flush=True)
 print("SANITIZE SCRIPT DONE")
