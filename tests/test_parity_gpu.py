@@ -191,6 +191,24 @@ def test_orders(oracle, order):
     check_float(oracle, a, [(0, True, coeff), (1, False, coeff)], "clamp")
 
 
+@pytest.mark.parametrize("order", [9, 12, 16, 20, 29])
+def test_high_orders_on_long_lines_take_the_warp_chain(oracle, order):
+    """Orders above 8 on lines of more than 512 tiles (apps/audio/audio_filter_high_order.cpp sweeps 1..29): the
+    generic engine's segmented chain, one warp per (segment, line), with the same-dimension residual between a causal
+    and an anticausal scan; float against the fp64 oracle, integers bit exact."""
+    coeff = [1.0] + [0.9 / order / (1 + 0.1 * k) for k in range(order)]
+    a = (rand_image((1, 70001), np.float32, 300 + order) * 2 - 1).astype(np.float32)
+    check_float(oracle, a, [(0, True, coeff)])
+    b = (rand_image((3, 40000), np.float32, 320 + order) * 2 - 1).astype(np.float32)
+    check_float(oracle, b, [(0, True, coeff), (0, False, coeff)], "clamp")
+    ci = [1] + [(-1) ** k * (1 + k % 3) for k in range(order)]                 # integer ring: any coefficients are exact
+    c = rand_image((2, 50000), np.uint32, 340 + order)
+    check_int(oracle, c, [(0, True, ci), (0, False, ci)])
+    # lines along the strided dimension (image mode): 600 tiles of 64 rows
+    d = (rand_image((38400, 5), np.float32, 360 + order) * 2 - 1).astype(np.float32)
+    check_float(oracle, d, [(1, True, coeff), (1, False, coeff)])
+
+
 def test_mixed_orders_in_one_dim(oracle):
     a = rand_image((130, 140), np.float32, 80)
     sc = [(0, True, [1, .5]), (0, False, [1, .3, .2, .1]), (1, True, [.5, .2, .2]), (1, True, [1, .4])]
