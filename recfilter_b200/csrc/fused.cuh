@@ -308,7 +308,7 @@ __device__ __forceinline__ void fstream_wait(const FStreamWait& sy)
     if (sy.need_a) until(sy.cnt_a + sy.row, sy.need_a);
 }
 
-template <typename CT, int R, int TS, int MODE, bool RAGGED, bool STREAM>
+template <typename CT, int R, int TS, int MODE, bool RAGGED, bool STREAM, bool EPI = false>
 __device__ __forceinline__ void fused_tile_body(const FusedParams<CT, R>& p, const CUtensorMap& tm_in, const CUtensorMap& tm_out,
                                                 int64_t b, const FStreamWait& sy)
 {
@@ -555,7 +555,7 @@ __device__ __forceinline__ void fused_tile_body(const FusedParams<CT, R>& p, con
             v[c4 * 4 + 2] = *reinterpret_cast<const CT*>(&q.z);
             v[c4 * 4 + 3] = *reinterpret_cast<const CT*>(&q.w);
         }
-        if (MODE == FMODE_P2 && p.epilogue) {
+        if (MODE == FMODE_P2 && EPI) {
             // every row is in registers, the tile buffer is free: the INPUT tile comes in again (TMA, an L2 hit) behind
             // the row scans, for the pointwise epilogue at the store
             fence_async_smem();
@@ -584,7 +584,7 @@ __device__ __forceinline__ void fused_tile_body(const FusedParams<CT, R>& p, con
             }
         }
         if constexpr (MODE == FMODE_P2) {
-            if (p.epilogue) {
+            if (EPI) {
                 // out = epi_out * filtered + epi_in * input, the input row read back from the re-loaded tile
                 mbar_wait(bar, 1);
                 const CT go = p.gain * p.epi_out;
@@ -599,7 +599,7 @@ __device__ __forceinline__ void fused_tile_body(const FusedParams<CT, R>& p, con
                     v[c4 * 4 + 3] = fmadd(v[c4 * 4 + 3], go, *reinterpret_cast<const CT*>(&q.w) * p.epi_in);
                 }
             }
-            const CT gs = p.epilogue ? (CT)1 : p.gain;
+            const CT gs = EPI ? (CT)1 : p.gain;
             // scale, rows back to shared memory (each thread only touches its own row)
 #pragma unroll
             for (int c4 = 0; c4 < TS / 4; ++c4) {
@@ -626,13 +626,15 @@ __device__ __forceinline__ void fused_tile_body(const FusedParams<CT, R>& p, con
     }
 }
 
-template <typename CT, int R, int TS, int MODE, bool RAGGED>
+// EPI: pass 2 with the pointwise epilogue (FusedParams::epilogue) -- its own instantiation, so that the plain pass 2 does
+// not carry the branch (measured: 2 us per 8192^2 image when the epilogue was a run-time flag of the one kernel)
+template <typename CT, int R, int TS, int MODE, bool RAGGED, bool EPI = false>
 __global__ void __launch_bounds__(TS, (TS == 128 ? 3 : 6))
 fused_tile_kernel(const __grid_constant__ FusedParams<CT, R> p, const __grid_constant__ CUtensorMap tm_in,
                   const __grid_constant__ CUtensorMap tm_out)
 {
     const int64_t b = p.reverse ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x;
-    fused_tile_body<CT, R, TS, MODE, RAGGED, false>(p, tm_in, tm_out, b, FStreamWait{});
+    fused_tile_body<CT, R, TS, MODE, RAGGED, false, EPI>(p, tm_in, tm_out, b, FStreamWait{});
 }
 
 // ---------------------------------------------------------------------------------------------

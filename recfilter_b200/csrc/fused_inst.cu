@@ -66,6 +66,18 @@ static cudaError_t launch_fused_tile_TS(const FusedParams<CT, R>& p, const void*
     } else {
         e = make_tile_map(&tm_out, out, p.Nx, p.No * p.Nd, TS, is_float);
         if (e != cudaSuccess) return e;
+        if constexpr (std::is_same<CT, float>::value && R <= 4) {
+            if (p.epilogue) {
+                static bool epi_attr_dev[RFB_MAX_DEVICES] = {};
+                if (!cacheable || !epi_attr_dev[dev]) {
+                    e = cudaFuncSetAttribute(fused_tile_kernel<CT, R, TS, FMODE_P2, RAGGED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)fused_tile_smem_bytes(TS, 2 * FMAX_SCANS * R * TS));
+                    if (e != cudaSuccess) return e;
+                    if (cacheable) epi_attr_dev[dev] = true;
+                }
+                return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P2, RAGGED, true>, dim3((unsigned)nblocks), dim3(TS), smem, st, pp, tm_in, tm_out);
+            }
+        } else if (p.epilogue) return cudaErrorInvalidValue;
         return launch_pdl(fused_tile_kernel<CT, R, TS, FMODE_P2, RAGGED>, dim3((unsigned)nblocks), dim3(TS), smem, st, pp, tm_in, tm_out);
     }
 }

@@ -1340,7 +1340,8 @@ struct FusedPass : PassBase {
 
     bool set_epilogue(float a_in, float a_out) override
     {
-        if (!std::is_same<CT, float>::value || fp.mx == 0 || d_open() || local_p2) return false;
+        if (!std::is_same<CT, float>::value || R > 4 || fp.mx == 0 || d_open() || local_p2) return false;
+        stream_ok = false;                       // the one-launch kernel has no epilogue instantiation
         fp.epilogue = 1; fp.epi_in = (CT)a_in; fp.epi_out = (CT)a_out;
         return true;
     }
