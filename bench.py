@@ -66,6 +66,8 @@ def bench_config(N: int, batch: int, strong: bool, exchange: str, graph: bool, o
         tail_bytes = 2 * ORDER * W * B * 4
         chunked = exchange == "alltoall" or (exchange == "auto" and N >= 4 and tail_bytes * N >= (8 << 20))
         how = ("peer-to-peer exchange windows over NVLink (rf_xchg_put / rf_xchg_wait)" if exchange == "p2p" else
+               "peer-to-peer exchange windows, neighbouring strips only: causal tails to rank + 1, anticausal to rank - 1 "
+               "(rf_xchg_put_part / rf_xchg_wait_from; the filter forgets a strip before it leaves it)" if exchange == "neighbor" else
                "two column-chunked NCCL all-to-alls" if chunked else "one NCCL all-gather")
         sharding = (f"every image cut into {N} row strips, one per GPU; the order-3 strip tails travel once per step ({how}); "
                     f"{batch} images' worth of samples per GPU per step")
@@ -73,7 +75,7 @@ def bench_config(N: int, batch: int, strong: bool, exchange: str, graph: bool, o
     return {"workload": WORKLOAD, "images_per_step": B, "sharding": sharding,
             "l2": "every image (268 MB) exceeds L2 and a step sweeps %d distinct images (one stack)" % B,
             "tile": "128x128 register tiles (fused engine)",
-            "launch": "one CUDA graph per step (captured once, replayed)" if (graph and B > 1 and exchange != "p2p") else "eager launches",
+            "launch": "one CUDA graph per step (captured once, replayed)" if (graph and B > 1 and exchange not in ("p2p", "neighbor")) else "eager launches",
             "streams": f"{groups} sub-stacks of {B // groups} images on their own CUDA streams" if B > 1 else "1"}
 
 
@@ -343,9 +345,10 @@ def main():
     ap.add_argument("--overlap", type=int, default=1,
                     help="sub-stacks of a step that run on their own CUDA streams (carry stage of one beside the tile "
                          "kernels of another); 1 = one stream")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "allgather", "alltoall"],
-                    help="N > 1: how the strip tails travel (auto = p2p: peer-to-peer exchange windows over NVLink; "
-                         "allgather / alltoall: NCCL collectives)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "neighbor", "allgather", "alltoall"],
+                    help="N > 1: how the strip tails travel (auto: NCCL all-gather, or two column-chunked all-to-alls from 4 "
+                         "ranks on; p2p: peer-to-peer exchange windows over NVLink, every rank to every rank; neighbor: the "
+                         "windows, adjacent strips only -- for filters that forget a strip before they leave it)")
     ap.add_argument("--graph", type=int, default=1,
                     help="1 (default): a step is captured once in a CUDA graph and replayed (a sharded step is a dozen short "
                          "launches: from 4 ranks on the host cannot issue them as fast as the GPUs finish them); 0: eager launches")

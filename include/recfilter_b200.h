@@ -211,6 +211,7 @@ size_t rf_plan_shard_tail_bytes(const rf_plan* plan);
  * whose ext_dev is the [vectors][lines] array of carries entering this shard.
  */
 int rf_plan_shard_vectors(const rf_plan* plan);
+int rf_plan_shard_neighbors_suffice(const rf_plan* plan);   /* 1: only the adjacent strips' tails matter (see rf_xchg_put_part) */
 int rf_plan_shard_resolve_lines(rf_plan* plan, const void* gathered_tails_dev, int nshards, int64_t nlines,
                                 void* ext_all_dev, void* stream);
 int rf_plan_stage2_ext(rf_plan* plan, const void* in_dev, void* out_dev, const void* ext_dev, void* stream);
@@ -254,6 +255,17 @@ int    rf_xchg_open_peer(rf_xchg* x, int peer, const void* handle);
 int    rf_xchg_set_peer(rf_xchg* x, int peer, rf_xchg* peer_window);
 int    rf_xchg_put(rf_xchg* x, const void* src_dev, size_t bytes, void* stream);
 int    rf_xchg_wait(rf_xchg* x, void* stream, void** gathered_dev);
+/*
+ * Neighbour exchange.  When rf_plan_shard_neighbors_suffice(plan) is 1 -- the filter forgets what entered a strip
+ * before it leaves it, i.e. every entry of the whole-strip transition matrices is below 1e-30 -- the carries entering
+ * strip s follow from the tails of strips s-1 and s+1 (and its own); the tails of farther strips may be left zero.
+ * rf_xchg_put_part assembles a step from parts: bytes [offset, offset + bytes) of the tails go into this rank's slot of
+ * the windows of the ranks in peer_mask (bit p = rank p, the own bit = the own window), the part with last != 0 raises
+ * the arrival word in every window touched; rf_xchg_wait_from waits for the ranks in from_mask only.  Causal scans'
+ * vectors go to rank + 1, anticausal ones to rank - 1 (layout of the tails: [vectors][lines], rf_plan_shard_vectors).
+ */
+int    rf_xchg_put_part(rf_xchg* x, unsigned peer_mask, const void* src_dev, size_t offset, size_t bytes, int last, void* stream);
+int    rf_xchg_wait_from(rf_xchg* x, unsigned from_mask, void* stream, void** gathered_dev);
 int    rf_xchg_check(rf_xchg* x);
 const char* rf_xchg_last_error(void);
 

@@ -147,6 +147,7 @@ int rf_plan_stage2(rf_plan* p, const void* i, void* o, const void* g, int n, int
 { (void)p; (void)i; (void)o; (void)g; (void)n; (void)r; (void)s; return RF_EUNSUPPORTED; }
 
 int rf_plan_shard_vectors(const rf_plan* p) { (void)p; return 0; }
+int rf_plan_shard_neighbors_suffice(const rf_plan* p) { (void)p; return 0; }
 int rf_plan_shard_resolve_lines(rf_plan* p, const void* g, int n, int64_t l, void* e, void* s)
 { (void)p; (void)g; (void)n; (void)l; (void)e; (void)s; return RF_EUNSUPPORTED; }
 int rf_plan_stage2_ext(rf_plan* p, const void* i, void* o, const void* e, void* s)
@@ -201,5 +202,7 @@ int rf_xchg_open_peer(rf_xchg* x, int p, const void* h) { (void)x; (void)p; (voi
 int rf_xchg_set_peer(rf_xchg* x, int p, rf_xchg* o) { (void)x; (void)p; (void)o; return RF_EUNSUPPORTED; }
 int rf_xchg_put(rf_xchg* x, const void* s, size_t b, void* st) { (void)x; (void)s; (void)b; (void)st; return RF_EUNSUPPORTED; }
 int rf_xchg_wait(rf_xchg* x, void* st, void** g) { (void)x; (void)st; (void)g; return RF_EUNSUPPORTED; }
+int rf_xchg_put_part(rf_xchg* x, unsigned m, const void* s, size_t o, size_t b, int l, void* st) { (void)x; (void)m; (void)s; (void)o; (void)b; (void)l; (void)st; return RF_EUNSUPPORTED; }
+int rf_xchg_wait_from(rf_xchg* x, unsigned m, void* st, void** g) { (void)x; (void)m; (void)st; (void)g; return RF_EUNSUPPORTED; }
 int rf_xchg_check(rf_xchg* x) { (void)x; return RF_EUNSUPPORTED; }
 const char* rf_xchg_last_error(void) { return g_err; }

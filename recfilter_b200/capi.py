@@ -101,6 +101,7 @@ def lib():
     L.rf_plan_stage1.argtypes = [vp, vp, vp, vp, vp]
     L.rf_plan_stage2.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     L.rf_plan_shard_vectors.argtypes = [vp]
+    L.rf_plan_shard_neighbors_suffice.argtypes = [vp]
     L.rf_plan_shard_resolve_lines.argtypes = [vp, vp, i32, C.c_int64, vp, vp]
     L.rf_plan_stage2_ext.argtypes = [vp, vp, vp, vp, vp]
     L.rf_plan_stage_timing.argtypes = [vp, i32]
@@ -124,6 +125,8 @@ def lib():
     L.rf_xchg_set_peer.argtypes = [vp, i32, vp]
     L.rf_xchg_put.argtypes = [vp, vp, sz, vp]
     L.rf_xchg_wait.argtypes = [vp, vp, C.POINTER(vp)]
+    L.rf_xchg_put_part.argtypes = [vp, C.c_uint, vp, sz, sz, i32, vp]
+    L.rf_xchg_wait_from.argtypes = [vp, C.c_uint, vp, C.POINTER(vp)]
     L.rf_xchg_check.argtypes = [vp]
     L.rf_xchg_last_error.restype = C.c_char_p
     L.rf_malloc.argtypes = [C.POINTER(vp), sz]
@@ -347,6 +350,12 @@ class Plan:
     def shard_vectors(self) -> int:
         return int(lib().rf_plan_shard_vectors(self._h))
 
+    @property
+    def shard_neighbors_suffice(self) -> bool:
+        """True when the carries entering this strip follow from the tails of the two adjacent strips alone
+        (rf_plan_shard_neighbors_suffice: whole-strip transition matrices below 1e-30)."""
+        return bool(lib().rf_plan_shard_neighbors_suffice(self._h))
+
     def shard_resolve_lines(self, gathered, nshards: int, nlines: int, ext_all, stream=None):
         import torch
         st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
@@ -456,6 +465,21 @@ class Exchange:
         st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
         out = C.c_void_p()
         self._xcheck(lib().rf_xchg_wait(self._h, C.c_void_p(st), C.byref(out)), "rf_xchg_wait")
+        return int(out.value)
+
+    def put_part(self, peer_mask: int, tails, offset: int, nbytes: int, last: bool, stream=None):
+        """One part of a step: bytes [offset, offset + nbytes) of `tails` into this rank's slot of the windows of the
+        ranks in `peer_mask`; the part with last=True raises the arrival words (rf_xchg_put_part)."""
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        self._xcheck(lib().rf_xchg_put_part(self._h, C.c_uint(peer_mask), C.c_void_p(tails.data_ptr() if tails is not None else None),
+                                            C.c_size_t(offset), C.c_size_t(nbytes), 1 if last else 0, C.c_void_p(st)), "rf_xchg_put_part")
+
+    def wait_from(self, from_mask: int, stream=None) -> int:
+        import torch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else int(stream)
+        out = C.c_void_p()
+        self._xcheck(lib().rf_xchg_wait_from(self._h, C.c_uint(from_mask), C.c_void_p(st), C.byref(out)), "rf_xchg_wait_from")
         return int(out.value)
 
     def check(self):

@@ -538,6 +538,9 @@ struct ShardResolver {
     DevBuf dP, dM, dC;
     int md = 0;
     bool ready = false;
+    // every entry of the whole-shard transition matrices is below 1e-30 (fp64): what enters a shard is decided by the
+    // tails of the two adjacent shards alone, farther shards contribute P * (...) = nothing an fp32 carry can hold
+    bool neighbors_suffice = false;
     int init(const std::vector<HostScan>& sd, int64_t n, bool clamp, bool scaled)
     {
         md = (int)sd.size();
@@ -548,6 +551,8 @@ struct ShardResolver {
             P3.insert(P3.end(), Pt.begin(), Pt.end());
             M3.insert(M3.end(), Mt.begin(), Mt.end());
         }
+        neighbors_suffice = std::is_same<CT, float>::value;
+        for (const HT& v : P3) if (!(std::fabs((double)v) < 1e-30)) neighbors_suffice = false;
         CUDA_TRY((upload<HT, TT>(dP, P3)));
         CUDA_TRY((upload<HT, TT>(dM, M3)));
         std::vector<int> causal(md);
@@ -587,6 +592,7 @@ struct PassBase {
     // carries entering every shard for `nlines` lines of the cut (column-chunked exchange); vectors = scans x order
     virtual int shard_resolve_lines(const void* gathered, int nshards, int64_t nlines, void* ext_all, cudaStream_t st) = 0;
     virtual int shard_vectors() const = 0;
+    virtual bool shard_neighbors_suffice() const { return false; }
     virtual const void* ext_buffer() const = 0;
     // device word a kernel of the pass sets when it gave up waiting (look-back kernels), or null
     virtual const uint32_t* error_flag() const { return nullptr; }
@@ -793,6 +799,7 @@ struct Pass : PassBase {
         return resolver->run(nlines, gathered, nshards, -1, ext_all, st);
     }
     int shard_vectors() const override { return pp.md * R; }
+    bool shard_neighbors_suffice() const override { return resolver && resolver->neighbors_suffice; }
 
     std::string describe() const override
     {
@@ -1357,6 +1364,7 @@ struct FusedPass : PassBase {
         return resolver->run(nlines, gathered, nshards, -1, ext_all, st);
     }
     int shard_vectors() const override { return fp.md * R; }
+    bool shard_neighbors_suffice() const override { return resolver && resolver->neighbors_suffice; }
 
     std::string describe() const override
     {
@@ -2624,6 +2632,12 @@ int rf_plan_stage2(rf_plan* plan, const void* in_dev, void* out_dev, const void*
         src = out_dev;
     }
     return RF_OK;
+}
+
+int rf_plan_shard_neighbors_suffice(const rf_plan* plan)
+{
+    if (!plan || plan->shard_pass < 0) return 0;
+    return plan->passes[plan->shard_pass]->shard_neighbors_suffice() ? 1 : 0;
 }
 
 int rf_plan_shard_vectors(const rf_plan* plan)

@@ -52,16 +52,16 @@ struct PeerWords { unsigned* w[XCHG_MAX_RANKS]; };
 __global__ void xchg_signal_kernel(PeerWords words, int nranks, unsigned step)
 {
     const int p = threadIdx.x;
-    if (p < nranks) {
+    if (p < nranks && words.w[p]) {
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(words.w[p]), "r"(step) : "memory");
     }
 }
 // thread r: wait for rank r's slot of this generation
-__global__ void xchg_wait_kernel(const unsigned* words, int nranks, unsigned step, unsigned* err)
+__global__ void xchg_wait_kernel(const unsigned* words, int nranks, unsigned step, unsigned* err, unsigned mask)
 {
     const int r = threadIdx.x;
-    if (r >= nranks) return;
+    if (r >= nranks || !((mask >> r) & 1u)) return;
     unsigned spins = 0;
     while (true) {
         unsigned v;
@@ -86,6 +86,8 @@ struct rf_xchg {
     unsigned* err = nullptr;          // device error word
     unsigned step = 0;                // last step put
     unsigned waited = 0;              // last step waited for
+    bool open = false;                // a step is being assembled from parts (rf_xchg_put_part)
+    unsigned targets = 0;             // ranks whose windows received a part of the open step
 };
 
 extern "C" {
@@ -172,6 +174,7 @@ int rf_xchg_put(rf_xchg* x, const void* src_dev, size_t bytes, void* stream)
 {
     if (!x || !src_dev) return xfail(RF_EINVAL, "null argument");
     if (bytes > x->bytes) return xfail(RF_EINVAL, "put of %zu bytes into slots of %zu", bytes, x->bytes);
+    if (x->open) return xfail(RF_EINVAL, "rf_xchg_put inside a step opened by rf_xchg_put_part");
     for (int p = 0; p < x->nranks; ++p)
         if (!x->peer[p]) return xfail(RF_EINVAL, "window of rank %d has not been mapped", p);
     cudaStream_t st = (cudaStream_t)stream;
@@ -197,7 +200,57 @@ int rf_xchg_wait(rf_xchg* x, void* stream, void** gathered_dev)
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned step = x->step;
     const size_t gen = step & 1u;
-    xchg_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned*>(x->win + x->words_off) + gen * XCHG_MAX_RANKS, x->nranks, step, x->err);
+    xchg_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned*>(x->win + x->words_off) + gen * XCHG_MAX_RANKS, x->nranks, step, x->err, 0xffffffffu);
+    XCUDA_TRY(cudaGetLastError());
+    x->waited = step;
+    if (gathered_dev) *gathered_dev = x->win + gen * x->gen_bytes;
+    return RF_OK;
+}
+
+// One step assembled from parts: bytes [offset, offset + bytes) of my tails go into my slot of the windows of the ranks in
+// `peer_mask` (bit p = rank p; my own bit = my own window); the call with last != 0 raises my arrival word in every
+// window that received a part.  Parts of a slot that are never written stay zero.
+int rf_xchg_put_part(rf_xchg* x, unsigned peer_mask, const void* src_dev, size_t offset, size_t bytes, int last, void* stream)
+{
+    if (!x) return xfail(RF_EINVAL, "null argument");
+    if (offset + bytes > x->bytes || (bytes && !src_dev)) return xfail(RF_EINVAL, "part [%zu, %zu) outside slots of %zu bytes", offset, offset + bytes, x->bytes);
+    if (x->nranks < 32) peer_mask &= (1u << x->nranks) - 1u;
+    for (int p = 0; p < x->nranks; ++p)
+        if (((peer_mask >> p) & 1u) && !x->peer[p]) return xfail(RF_EINVAL, "window of rank %d has not been mapped", p);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x->open) { ++x->step; x->open = true; x->targets = 0; }
+    const unsigned step = x->step;
+    const size_t gen = step & 1u;
+    if (bytes)
+        for (int i = 1; i <= x->nranks; ++i) {
+            const int p = (x->rank + i) % x->nranks;
+            if (!((peer_mask >> p) & 1u)) continue;
+            XCUDA_TRY(cudaMemcpyAsync(x->peer[p] + gen * x->gen_bytes + (size_t)x->rank * x->bytes + offset,
+                                      (const unsigned char*)src_dev + offset, bytes, cudaMemcpyDefault, st));
+        }
+    x->targets |= peer_mask;
+    if (last) {
+        PeerWords words;
+        std::memset(&words, 0, sizeof(words));
+        for (int p = 0; p < x->nranks; ++p)
+            if ((x->targets >> p) & 1u) words.w[p] = reinterpret_cast<unsigned*>(x->peer[p] + x->words_off) + gen * XCHG_MAX_RANKS + x->rank;
+        xchg_signal_kernel<<<1, 32, 0, st>>>(words, x->nranks, step);
+        XCUDA_TRY(cudaGetLastError());
+        x->open = false;
+    }
+    return RF_OK;
+}
+
+// as rf_xchg_wait, for the slots of the ranks in `from_mask` only
+int rf_xchg_wait_from(rf_xchg* x, unsigned from_mask, void* stream, void** gathered_dev)
+{
+    if (!x) return xfail(RF_EINVAL, "null argument");
+    if (x->open) return xfail(RF_EINVAL, "rf_xchg_wait_from inside an open step (the last part was not marked)");
+    if (x->step == x->waited) return xfail(RF_EINVAL, "rf_xchg_wait_from without a put of this step");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned step = x->step;
+    const size_t gen = step & 1u;
+    xchg_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned*>(x->win + x->words_off) + gen * XCHG_MAX_RANKS, x->nranks, step, x->err, from_mask);
     XCUDA_TRY(cudaGetLastError());
     x->waited = step;
     if (gathered_dev) *gathered_dev = x->win + gen * x->gen_bytes;

@@ -10,7 +10,9 @@ dimensions are strip local.  For the scans along the cut dimension every rank
   exchange  the tails of every strip reach every rank: by default peer to peer over NVLink, straight from
             device memory into the other ranks' exchange windows (rf_xchg_put / rf_xchg_wait: CUDA IPC
             mappings, no collective library and no host in the data path); alternatively ONE NCCL
-            all-gather, or two column-chunked all-to-alls (gloo in the CPU tests);
+            all-gather, or two column-chunked all-to-alls (gloo in the CPU tests); or, for filters that forget a
+            whole strip (rf_plan_shard_neighbors_suffice), the windows of the two adjacent ranks only
+            (exchange="neighbor": rf_xchg_put_part / rf_xchg_wait_from);
   stage 2   resolves the carries entering its strip from the gathered tails with the whole-strip
             transition matrices (a tiny kernel, redundantly on every rank), corrects the stage-1 carries of
             the strip with them (no second carry chain) and finishes the filter (rf_plan_stage2).
@@ -114,6 +116,7 @@ class ShardedFilter:
         else:
             # one plan per image in flight: a plan owns the carry workspace of its image
             self.plans = [Plan(self.local_extents, dtype, scans, border, **kw) for _ in range(batch if world > 1 else 1)]
+        self.shard_causal = [bool(sc.causal) for sc in scans if int(sc.dim) == self.shard_dim]
         self.tail_elems = self.plans[0].shard_tail_bytes // 4 if world > 1 else 0
         self._tails = None
         self.vectors = self.plans[0].shard_vectors if world > 1 else 0
@@ -124,7 +127,19 @@ class ShardedFilter:
         # measured on 4 and 8 B200s (profiles/): the two all-to-alls win once the all-gather would deliver >= ~8 MB
         # per rank; below that its single collective is faster
         big = self.tail_elems * 4 * world >= (8 << 20)
-        self.p2p = world > 1 and exchange == "p2p" and torch.cuda.is_available()
+        # neighbour exchange: peer-to-peer windows, but a rank only sends the causal scans' tails to rank + 1 and the
+        # anticausal ones to rank - 1 (and waits for those two): valid when every rank's plan reports that the adjacent
+        # strips decide its carries (short memory over a whole strip)
+        self.neighbor = False
+        if world > 1 and exchange == "neighbor":
+            if not torch.cuda.is_available():
+                raise ValueError("exchange='neighbor' needs CUDA devices")
+            ok = torch.tensor([1 if all(p.shard_neighbors_suffice for p in self.plans) else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) != 1:
+                raise ValueError("exchange='neighbor': the filter remembers more than one strip (rf_plan_shard_neighbors_suffice is 0)")
+            self.neighbor = True
+        self.p2p = world > 1 and exchange in ("p2p", "neighbor") and torch.cuda.is_available()
         self.use_graph = bool(graph) and self.stacked and not self.p2p and torch.cuda.is_available()
         self._graphs = {}
         self.chunked = (not self.p2p) and chunked_ok and (exchange == "alltoall" or (exchange == "auto" and world >= 4 and big))
@@ -138,7 +153,23 @@ class ShardedFilter:
 
     def _finish(self, plan, src, dst, tails):
         """Exchange the strip tails and finish the filter (stage 2) for one plan."""
-        if self.p2p:
+        if self.neighbor:
+            x = self.windows[self.plans.index(plan)]
+            me, lo, hi = 1 << self.rank, self.rank - 1, self.rank + 1
+            nbytes = self.tail_elems * 4
+            per_scan = nbytes // len(self.shard_causal)               # [scan][order][lines]: one contiguous block per scan
+            x.put_part(me, tails, 0, nbytes, False)                   # own slot: the resolver reads this strip's tails too
+            mask = me
+            for s, causal in enumerate(self.shard_causal):
+                to = hi if causal else lo
+                if 0 <= to < self.world:
+                    x.put_part(1 << to, tails, s * per_scan, per_scan, False)
+            for nb in (lo, hi):
+                if 0 <= nb < self.world:
+                    mask |= 1 << nb
+            x.put_part(mask, None, 0, 0, True)                         # arrival words: own window and both neighbours'
+            plan.stage2(src, dst, x.wait_from(mask), self.world, self.rank)
+        elif self.p2p:
             x = self.windows[self.plans.index(plan)]
             x.put(tails)
             plan.stage2(src, dst, x.wait(), self.world, self.rank)

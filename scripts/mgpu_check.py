@@ -36,7 +36,7 @@ gen = torch.Generator(device="cuda").manual_seed(7)
 full = torch.rand((B, H, W), device="cuda", generator=gen)
 flt = ShardedFilter((W, H), "f32", scans, "clamp", rank=rank, world=world, shard_dim=1, batch=B, stacked=True,
                     exchange=os.environ.get("RF_EXCHANGE", "auto"))
-if rank == 0: print("exchange:", "p2p windows" if flt.p2p else ("alltoall (column-chunked)" if flt.chunked else "allgather"), flush=True)
+if rank == 0: print("exchange:", "p2p windows, neighbours only" if flt.neighbor else "p2p windows" if flt.p2p else ("alltoall (column-chunked)" if flt.chunked else "allgather"), flush=True)
 lo, hi = flt.rows
 src = full[:, lo:hi].contiguous(); dst = torch.empty_like(src)
 flt.run_stacked(src, dst); torch.cuda.synchronize()
