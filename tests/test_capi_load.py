@@ -55,3 +55,41 @@ def test_tap_struct_matches_header():
     from recfilter_b200.capi import _Tap
     assert ctypes.sizeof(_Tap) == 4 + 4 + 3 * 4 * 4
     assert _Tap.offset.offset == 8 and _Tap.lo.offset == 24 and _Tap.hi.offset == 40
+
+
+def test_ctypes_layouts_equal_what_the_c_compiler_sees(tmp_path):
+    """sizeof / offsetof of the descriptor structs as gcc lays them out from include/recfilter_b200.h, against the
+    ctypes mirrors in recfilter_b200/capi.py (a silent mismatch would shift every option a plan is created with)."""
+    import os, shutil, subprocess
+    from recfilter_b200.capi import _Desc, _Scan, _Options, _Tap
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "recfilter_b200.h"
+#define O(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void)
+{
+    printf("rf_scan %zu\nrf_options %zu\nrf_desc %zu\nrf_tap %zu\n", sizeof(rf_scan), sizeof(rf_options), sizeof(rf_desc), sizeof(rf_tap));
+    O(rf_options, honor_tile); O(rf_options, fuse_dims); O(rf_options, open_lo); O(rf_options, open_hi); O(rf_options, shard_dim);
+    O(rf_options, engine); O(rf_options, epilogue); O(rf_options, epi_in); O(rf_options, epi_out); O(rf_options, reserved);
+    O(rf_desc, extent); O(rf_desc, dtype); O(rf_desc, border); O(rf_desc, nscans); O(rf_desc, scans); O(rf_desc, opt);
+    O(rf_scan, causal); O(rf_scan, order); O(rf_scan, coeff);
+    O(rf_tap, source); O(rf_tap, offset); O(rf_tap, lo); O(rf_tap, hi);
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    mirror = {"rf_scan": _Scan, "rf_options": _Options, "rf_desc": _Desc, "rf_tap": _Tap}
+    for key, val in got.items():
+        if "." in key:
+            st, field = key.split(".")
+            assert getattr(mirror[st], field).offset == int(val), key
+        else:
+            assert ctypes.sizeof(mirror[key]) == int(val), key
