@@ -1079,6 +1079,9 @@ Func RecFilter::func(string func_name) { return Func(contents, func_name); }
 RecFilterSchedule RecFilter::intra_schedule(int) { return RecFilterSchedule(*this, { contents->name }); }
 RecFilterSchedule RecFilter::inter_schedule() { return RecFilterSchedule(*this, { contents->name }); }
 RecFilterSchedule RecFilter::full_schedule() { return RecFilterSchedule(*this, { contents->name }); }
+// compute_at merges a filter into its pointwise consumer (lib/recfilter.cpp:473-573).  Nothing to record here: the merge
+// the in-scope apps ask for (apps/usm: blur into the unsharp mask) is found from the definitions themselves and done by
+// the store of the filter's last kernel (epilogue_match / rf_options.epilogue), whether or not compute_at was called.
 void RecFilter::compute_at(RecFilter) {}
 void RecFilter::compute_at(Func, Var) {}
 void RecFilter::gpu_auto_full_schedule(int) {}
