@@ -274,3 +274,33 @@ def test_lookback_plans_replay_in_a_cuda_graph(oracle):
         assert rel_err(bo.cpu().numpy(), truth) <= TOL
     sat.check(); sig.check()
     sat.close(); sig.close()
+
+
+def test_several_scans_along_long_lines_run_one_signal_pass_each(oracle):
+    """apps/audio/audio_filter_biquads.cpp: up to a dozen causal order-2 scans on one signal.  No tile engine fuses them,
+    so the planner emits one single-pass signal kernel per scan (the passes run in place, one after the other)."""
+    biquad = [1.0, 0.1, 0.1]
+    a = (rand_image((2, 1 << 17), np.float32, 91) * 2 - 1).astype(np.float32)
+    scans = [(0, True, biquad)] * 6
+    plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in scans])
+    text = plan.describe()
+    assert text.count("look-back signal pass") == 6 and plan.num_launches == 6, text
+    out = plan.realize(a)
+    plan.close()
+    truth = oracle.apply_filter(a.astype(np.float64), scans, threads=8)
+    assert rel_err(out, truth) <= 1e-5
+    # causal and anticausal scans of different orders, clamped border
+    mixed = [(0, True, [0.3, 0.4, 0.2, 0.05]), (0, False, [0.5, 0.3, 0.1]), (0, True, biquad), (0, False, [0.6, 0.35]), (0, True, biquad)]
+    plan = Plan(a.shape[::-1], a.dtype, [Scan(*s) for s in mixed], "clamp")
+    assert plan.describe().count("look-back signal pass") == 5
+    out = plan.realize(a)
+    plan.close()
+    truth = oracle.apply_filter(a.astype(np.float64), mixed, "clamp", threads=8)
+    assert rel_err(out, truth) <= 1e-5
+    # integer ring: bit exact
+    b = rand_image((3, 1 << 16), np.uint32, 92)
+    isc = [(0, True, [1, 1]), (0, True, [1, 2, -1]), (0, False, [1, 1]), (0, True, [1, 3]), (0, False, [1, -1, 2])]
+    plan = Plan(b.shape[::-1], b.dtype, [Scan(*s) for s in isc])
+    assert plan.describe().count("look-back signal pass") == 5
+    assert np.array_equal(plan.realize(b), oracle.apply_filter(b, isc))
+    plan.close()
