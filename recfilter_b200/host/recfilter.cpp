@@ -59,6 +59,9 @@ struct RecFilterContents {
     // second source of a stencil: an image read beside the result of src_filter
     // (unsharp mask: (1+w)*image - w*blur, apps/usm/unsharp_mask_naive.cpp:61); taps with source == 1 read it
     std::shared_ptr<BufferData> side_image;
+    // ... or the result of a second filter (difference of Gaussians: two channels of a Tuple filter subtracted,
+    // apps/DoG/diff_gauss.cpp:96): taps with source == 1 read it.  At most one of side_image / side_filter is set.
+    std::shared_ptr<RecFilterContents> side_filter;
     void* dev_side = nullptr;
     vector<ScanDef> scans;
     std::map<string, int> tiles;    // split() hints
@@ -72,12 +75,14 @@ struct RecFilterContents {
     // independently with the same scans -- one channel filter per element, kept in step by sync_channels()
     vector<std::shared_ptr<RecFilterContents>> channels;
     void* dev_out = nullptr;        // device result buffer, reused across realize()/profile()
+    void* dev_in = nullptr;         // the input image on the device while profile() keeps inputs resident
     void* dev_tmp = nullptr;        // stencil output when scans follow
     ~RecFilterContents()
     {
         if (plan) rf_plan_destroy(plan);
         if (mgpu) rf_mgpu_destroy(mgpu);
         if (dev_out) rf_free(dev_out);
+        if (dev_in) rf_free(dev_in);
         if (dev_tmp) rf_free(dev_tmp);
         if (dev_side) rf_free(dev_side);
     }
@@ -431,12 +436,30 @@ void* upload_image(RecFilterContents& c, const BufferData& b)
     return dev;
 }
 
+// profile(): images stay resident over the timed iterations (kernels only are timed, lib/recfilter.cpp:995-1011), also
+// the root image of a second-source filter chain that run_unit evaluates on the way (apps/DoG)
+bool g_resident_inputs = false;
+vector<RecFilterContents*> g_resident_owners;
+
 void* input_device(RecFilterContents& c, bool& owned)
 {
     if (c.src_filter) { owned = false; return evaluate_device(*c.src_filter); }
     if (!c.src_image) die("RecFilter " + c.name + ": the input image is not set (ImageParam::set was not called?)");
+    if (g_resident_inputs) {
+        if (!c.dev_in) { c.dev_in = upload_image(c, *c.src_image); g_resident_owners.push_back(&c); }
+        owned = false;
+        return c.dev_in;
+    }
     owned = true;
     return upload_image(c, *c.src_image);
+}
+void release_resident_inputs()
+{
+    g_resident_inputs = false;
+    if (!g_resident_owners.empty()) engine_check(rf_synchronize(), "rf_synchronize");
+    for (RecFilterContents* o : g_resident_owners)
+        if (o->dev_in) { engine_check(rf_free(o->dev_in), "rf_free"); o->dev_in = nullptr; }
+    g_resident_owners.clear();
 }
 
 // run the unit first..c on the device buffer `in` (the input of `first`): the stencil of first's definition
@@ -461,8 +484,11 @@ void* run_unit(RecFilterContents& first, RecFilterContents& c, const void* in, b
             if (f.dev_side) { engine_check(rf_synchronize(), "rf_synchronize"); engine_check(rf_free(f.dev_side), "rf_free"); f.dev_side = nullptr; }
             f.dev_side = upload_image(f, *f.side_image);
         }
+        // the second source: the resident side image, or the result of the second filter (evaluated now, into that
+        // filter's own device buffer)
+        const void* in2 = f.side_filter ? evaluate_device(*f.side_filter) : f.dev_side;
         engine_check(rf_stencil_execute((int)c.dims.size(), ext, engine_dtype(c.type), (int)f.stencil.size(), f.stencil.data(),
-                                        f.stencil_scale, in, f.dev_side, dst, nullptr), "rf_stencil_execute");
+                                        f.stencil_scale, in, in2, dst, nullptr), "rf_stencil_execute");
         if (scans.empty()) return c.dev_out;
         in = dst;
     }
@@ -681,7 +707,7 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
         c.dims = pure_args;
         c.rhs = pure_def;
         c.scans.clear();
-        c.src_image.reset(); c.src_filter.reset(); c.stencil.clear(); c.side_image.reset();
+        c.src_image.reset(); c.src_filter.reset(); c.stencil.clear(); c.side_image.reset(); c.side_filter.reset();
         if (c.plan) { rf_plan_destroy(c.plan); c.plan = nullptr; }
         for (size_t i = 0; i < pure_def.size(); ++i) {
             RecFilter ch(c.name + "_" + std::to_string(i));
@@ -711,11 +737,15 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     // merge equal taps; everything must read ONE filter result and / or ONE image, with the filter's own
     // dimension order.  With both, the filter result is source 0 and the image source 1.
     std::shared_ptr<BufferData> image;
-    std::shared_ptr<RecFilterContents> filter;
+    std::shared_ptr<RecFilterContents> filter, filter2;
     for (const LinTap& t : taps) {
-        if (t.filter) { if (filter && filter != t.filter) die("RecFilter " + c.name + ": the definition may read one filter only"); filter = t.filter; }
-        else          { if (image && image != t.image) die("RecFilter " + c.name + ": the definition may read one image only"); image = t.image; }
+        if (t.filter) {
+            if (!filter || filter == t.filter) filter = t.filter;
+            else if (!filter2 || filter2 == t.filter) filter2 = t.filter;
+            else die("RecFilter " + c.name + ": the definition may read two filters at most");
+        } else { if (image && image != t.image) die("RecFilter " + c.name + ": the definition may read one image only"); image = t.image; }
     }
+    if (filter2 && image) die("RecFilter " + c.name + ": the definition may read two filters, or one filter and one image");
     vector<LinTap> merged;
     for (const LinTap& t : taps) {
         if (t.idx.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch in the definition");
@@ -730,7 +760,7 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
         }
         if (!found) merged.push_back(t);
     }
-    c.side_image.reset();
+    c.side_image.reset(); c.side_filter.reset();
     if (c.dev_side) { rf_free(c.dev_side); c.dev_side = nullptr; }
     if (image) {
         if (!image->has_data()) die("RecFilter " + c.name + ": the image in the definition has no data");
@@ -747,6 +777,15 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
             if (image->type != filter->type) die("RecFilter " + c.name + ": the image and the filter in the definition differ in type");
             c.side_image = image;
         }
+        if (filter2) {
+            if (!filter2->defined) die("RecFilter " + c.name + ": the second filter called in the definition is not defined");
+            if (filter2->dims.size() != c.dims.size()) die("RecFilter " + c.name + ": dimension mismatch with the second called filter");
+            if (!(filter2->type == filter->type)) die("RecFilter " + c.name + ": the two filters in the definition differ in type");
+            for (size_t i = 0; i < c.dims.size(); ++i)
+                if (filter2->dims[i].num_pixels() != filter->dims[i].num_pixels())
+                    die("RecFilter " + c.name + ": the two filters in the definition differ in extent");
+            c.side_filter = filter2;
+        }
     } else {
         c.src_image = image;
         c.type = image->type;                                       // type of the filter = type of the RHS (lib/recfilter.cpp:197)
@@ -760,7 +799,7 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
     }
     // a single unit tap whose indices are the identity inside the domain is the input itself
     c.stencil.clear();
-    bool identity = merged.size() == 1 && merged[0].w == 1.0 && !c.side_image;
+    bool identity = merged.size() == 1 && merged[0].w == 1.0 && !c.side_image && !c.side_filter;
     for (size_t i = 0; identity && i < c.dims.size(); ++i) {
         const IndexMap& m = merged[0].idx[i];
         identity = m.off == 0 && m.lo <= 0 && m.hi >= (long long)c.dims[i].num_pixels() - 1;
@@ -784,7 +823,7 @@ void RecFilter::define(vector<RecFilterDim> pure_args, vector<Expr> pure_def)
             rf_tap rt;
             std::memset(&rt, 0, sizeof(rt));
             rt.weight = (float)(t.w / w0);
-            rt.source = (c.side_image && !t.filter) ? 1 : 0;
+            rt.source = ((c.side_image && !t.filter) || (c.side_filter && t.filter == c.side_filter)) ? 1 : 0;
             for (int d = 0; d < RF_MAX_DIMS; ++d) { rt.lo[d] = INT32_MIN; rt.hi[d] = INT32_MAX; }
             for (size_t i = 0; i < t.idx.size(); ++i) {
                 rt.offset[i] = (int32_t)t.idx[i].off;
@@ -890,7 +929,7 @@ vector<RecFilter> RecFilter::cascade(vector<vector<int> > groups)
         RecFilter f(c.name + "_" + std::to_string(g));
         RecFilterContents& fc = *f.contents;
         fc.dims = c.dims; fc.type = c.type; fc.clamped = c.clamped; fc.defined = true;
-        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; fc.stencil = c.stencil; fc.stencil_scale = c.stencil_scale; fc.side_image = c.side_image; }
+        if (g == 0) { fc.rhs = c.rhs; fc.src_image = c.src_image; fc.src_filter = c.src_filter; fc.stencil = c.stencil; fc.stencil_scale = c.stencil_scale; fc.side_image = c.side_image; fc.side_filter = c.side_filter; }
         else        { fc.src_filter = out[g - 1].contents; }
         vector<int> ids = groups[g];
         std::sort(ids.begin(), ids.end());                           // add_filter order inside a group
@@ -934,7 +973,7 @@ RecFilter RecFilter::overlap_to_higher_order_filter(RecFilter fB, string overlap
     RecFilter ab(overlap_name);
     RecFilterContents& c = *ab.contents;
     c.dims = a.dims; c.type = a.type; c.clamped = a.clamped; c.defined = true;
-    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter; c.stencil = a.stencil; c.stencil_scale = a.stencil_scale; c.side_image = a.side_image;
+    c.rhs = a.rhs; c.src_image = a.src_image; c.src_filter = a.src_filter; c.stencil = a.stencil; c.stencil_scale = a.stencil_scale; c.side_image = a.side_image; c.side_filter = a.side_filter;
     for (size_t d = 0; d < a.dims.size(); ++d) {
         vector<const ScanDef*> sa, sb;
         for (const ScanDef& s : a.scans) if (s.dim == (int)d) sa.push_back(&s);
@@ -1056,6 +1095,7 @@ float RecFilter::profile(int iterations)
         const void* in = root_in;
         for (auto& u : units) in = run_unit(*u.first, *u.second, in, !warm);
     };
+    g_resident_inputs = true;                                         // (side chains evaluated inside run_unit upload once)
     run_chain();                                                      // warm-up (lib/recfilter.cpp:995-997)
     warm = true;
     void* clock = nullptr;
@@ -1063,6 +1103,7 @@ float RecFilter::profile(int iterations)
     for (int i = 0; i < iterations; ++i) run_chain();
     float ms = 0.0f;
     engine_check(rf_clock_end(clock, nullptr, &ms), "rf_clock_end");
+    release_resident_inputs();
     if (owned) engine_check(rf_free(root_in), "rf_free");
     const float per_iter = ms / float(iterations);
     cerr << c.name << ": " << per_iter << " ms per iteration over " << iterations << " iteration(s), "

@@ -32,7 +32,10 @@ APPS = [("summed_table", ["-w", "512", "-t", "32"], True),
         ("box_filter_6", ["-w", "512", "-t", "32", "-iter", "2"], False),
         # apps/usm: (1+w)*image - w*blur, a pointwise combination of an image and a filter result
         ("unsharp_mask_naive", ["-w", "512", "-t", "32", "-iter", "2"], False),
-        ("unsharp_mask_optimized", ["-w", "512", "-t", "32", "-iter", "2"], False)]
+        ("unsharp_mask_optimized", ["-w", "512", "-t", "32", "-iter", "2"], False),
+        # apps/DoG: int16 image -> float, summed-area tables, Tuple filters feeding Tuple filters, and a last stage that
+        # subtracts two filter results
+        ("diff_gauss", ["-w", "256", "-t", "32", "-iter", "2"], False)]
 MAX_PERCENT = 1e-3          # the programs print percent: 1e-3 % == 1e-5 relative (BASELINE.json tolerance)
 
 
@@ -248,3 +251,11 @@ def test_type_converting_definitions(kind, tmp_path):
     # tests/cpp/cast_check.cpp: cast<float>(image16(x,y)) (apps/DoG/diff_gauss.cpp:66-73) and image16 * 0.5f run as float filters
     rc, out = run(kind, "cast_check", [], cwd=tmp_path)
     assert rc == 0 and out.count(": 0 mismatches") == 2, out[-2000:]
+
+
+@pytest.mark.parametrize("kind", ["pin", pytest.param("gpu", marks=pytest.mark.gpu)])
+def test_definition_reading_two_filters(kind, tmp_path):
+    # tests/cpp/dog_check.cpp: Tuple filter -> Tuple filter -> difference of its two elements (apps/DoG/diff_gauss.cpp:84-96)
+    rc, out = run(kind, "dog_check", ["128"], cwd=tmp_path)
+    assert rc == 0, out[-2000:]
+    assert max_error(out) is not None and max_error(out) <= 1e-4, out[-2000:]
